@@ -1,0 +1,299 @@
+"""ctypes binding of the C ABI in include/cpprob_sis.h (libcpprob_sis.so).
+
+Plumbing for the tests and bench.py: every compute call goes through the same C entry points the
+C++14 host API (include/cpprob/cpprob.hpp) uses.  There is no Python or CPU implementation of the
+path here; if the shared library is missing, importing this module's `lib()` raises.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcpprob_sis.so")
+
+EMIT_NONE, EMIT_ALL = 0, 1
+DIST = {"normal": 0, "uniform_real": 1, "uniform_smallint": 2, "discrete": 3, "poisson": 4, "gamma": 5, "beta": 6}
+BASE_COLS = 8
+CHUNK = 1 << 15
+
+# every symbol include/cpprob_sis.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = [
+    "cpprob_sis_abi_version", "cpprob_sis_last_error", "cpprob_sis_create", "cpprob_sis_destroy",
+    "cpprob_sis_register_model", "cpprob_sis_model_count", "cpprob_sis_model_name", "cpprob_sis_find_model",
+    "cpprob_sis_describe", "cpprob_sis_run", "cpprob_sis_infer_to_files", "cpprob_sis_run_shard",
+    "cpprob_sis_merge", "cpprob_sis_replay", "cpprob_sis_reduce_records", "cpprob_sis_logpdf",
+    "cpprob_sis_sample", "cpprob_sis_philox", "cpprob_sis_dmath", "cpprob_sis_measure_dfma_peak",
+    "cpprob_sis_measure_store_peak",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("seed", C.c_uint64), ("max_batch", C.c_uint64), ("blocks_per_sm", C.c_int)]
+
+
+class Slot(C.Structure):
+    _fields_ = [("is_int", C.c_int), ("id", C.c_int), ("k", C.c_int), ("row", C.c_int)]
+
+
+class Structure(C.Structure):
+    _fields_ = [("n_ids", C.c_int), ("n_slots", C.c_int), ("n_real", C.c_int), ("n_int", C.c_int),
+                ("n_samples", C.c_int), ("ids", C.POINTER(C.c_char_p)), ("slots", C.POINTER(Slot))]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_particles", C.c_uint64), ("n_neg_inf", C.c_uint64), ("n_nan", C.c_uint64),
+                ("m_ref", C.c_double), ("max_log_w", C.c_double), ("log_sum_exp", C.c_double),
+                ("log_evidence", C.c_double), ("ess", C.c_double),
+                ("n_real", C.c_int), ("n_int", C.c_int),
+                ("real_mean", C.POINTER(C.c_double)), ("real_var", C.POINTER(C.c_double)),
+                ("int_lo", C.c_longlong), ("int_bins", C.c_int),
+                ("int_prob", C.POINTER(C.c_double)), ("int_map", C.POINTER(C.c_longlong)),
+                ("n_cols", C.c_int), ("sums", C.POINTER(C.c_double)),
+                ("device_ms", C.c_double), ("kernel_launches", C.c_uint64), ("passes", C.c_int)]
+
+
+class Block(C.Structure):
+    _fields_ = [("first_particle", C.c_uint64), ("n", C.c_uint64), ("stride", C.c_uint64),
+                ("n_real", C.c_int), ("n_int", C.c_int),
+                ("real_rows", C.POINTER(C.c_double)), ("int_rows", C.POINTER(C.c_int32)), ("log_w", C.POINTER(C.c_double))]
+
+
+BLOCK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(Block))
+
+
+class RunOptions(C.Structure):
+    _fields_ = [("emit", C.c_int), ("force_rows", C.c_int), ("on_block", BLOCK_FN), ("user", C.c_void_p)]
+
+
+class Partials(C.Structure):
+    _fields_ = [("device_ptr", C.c_void_p), ("n_chunks_local", C.c_uint32), ("n_chunks_total", C.c_uint32),
+                ("chunk_first", C.c_uint32), ("n_cols", C.c_int), ("m_ref", C.c_double),
+                ("device_ms", C.c_double), ("kernel_launches", C.c_uint64)]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    """Loads libcpprob_sis.so (built by __graft_entry__.build() / cpprob_b200/csrc/Makefile)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(the SIS engine has no CPU fallback)")
+        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        dp, u64 = C.POINTER(C.c_double), C.c_uint64
+        L.cpprob_sis_abi_version.restype = C.c_int
+        L.cpprob_sis_last_error.restype = C.c_char_p
+        L.cpprob_sis_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+        L.cpprob_sis_destroy.argtypes = [C.c_void_p]
+        L.cpprob_sis_destroy.restype = None
+        L.cpprob_sis_model_name.argtypes = [C.c_int]
+        L.cpprob_sis_model_name.restype = C.c_char_p
+        L.cpprob_sis_find_model.argtypes = [C.c_char_p]
+        L.cpprob_sis_describe.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t, C.POINTER(Structure)]
+        L.cpprob_sis_run.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t, u64, C.POINTER(RunOptions), C.POINTER(Stats)]
+        L.cpprob_sis_infer_to_files.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t, u64, C.c_char_p, C.POINTER(Stats)]
+        L.cpprob_sis_run_shard.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t, u64, C.c_int, C.c_int, dp, C.POINTER(Partials)]
+        L.cpprob_sis_merge.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t, C.c_void_p, C.c_uint32, C.c_int, C.c_double, u64,
+                                       C.POINTER(Stats)]
+        L.cpprob_sis_replay.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t, dp, C.POINTER(C.c_int32), u64, u64, dp]
+        L.cpprob_sis_reduce_records.argtypes = [C.c_void_p, dp, C.c_int, C.POINTER(C.c_int32), C.c_int, dp, u64, u64, C.POINTER(Stats)]
+        L.cpprob_sis_logpdf.argtypes = [C.c_void_p, C.c_int, dp, C.c_int, dp, u64, dp]
+        L.cpprob_sis_sample.argtypes = [C.c_void_p, C.c_int, dp, C.c_int, u64, u64, u64, dp]
+        L.cpprob_sis_philox.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), u64, C.POINTER(C.c_uint32)]
+        L.cpprob_sis_dmath.argtypes = [C.c_void_p, C.c_int, dp, u64, dp]
+        L.cpprob_sis_measure_dfma_peak.argtypes = [C.c_void_p, dp, dp]
+        L.cpprob_sis_measure_store_peak.argtypes = [C.c_void_p, dp]
+        _lib = L
+        return L
+
+
+class SisError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"cpprob_sis error {code}: {msg}")
+        self.code = code
+
+
+def _check(rc):
+    if rc < 0:
+        raise SisError(rc, lib().cpprob_sis_last_error().decode())
+    return rc
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def stats_to_dict(st, structure=None):
+    d = {k: getattr(st, k) for k in ("n_particles", "n_neg_inf", "n_nan", "m_ref", "max_log_w", "log_sum_exp",
+                                      "log_evidence", "ess", "n_real", "n_int", "int_lo", "int_bins", "n_cols",
+                                      "device_ms", "kernel_launches", "passes")}
+    d["real_mean"] = np.array([st.real_mean[i] for i in range(st.n_real)])
+    d["real_var"] = np.array([st.real_var[i] for i in range(st.n_real)])
+    d["int_prob"] = np.array([st.int_prob[i] for i in range(st.n_int * st.int_bins)]).reshape(st.n_int, st.int_bins or 1)[:, :st.int_bins]
+    d["int_map"] = np.array([st.int_map[i] for i in range(st.n_int)], dtype=np.int64)
+    d["sums"] = np.array([st.sums[i] for i in range(st.n_cols)])
+    return d
+
+
+class Engine:
+    """One GPU's SIS engine (cpprob_sis_create / cpprob_sis_destroy)."""
+
+    def __init__(self, device=0, seed=0x5EED, max_batch=0, blocks_per_sm=0):
+        self._L = lib()
+        self._h = C.c_void_p()
+        cfg = Config(device, seed, max_batch, blocks_per_sm)
+        _check(self._L.cpprob_sis_create(C.byref(cfg), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._L.cpprob_sis_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- registry -----------------------------------------------------------------------------
+    def model_id(self, name):
+        return _check(self._L.cpprob_sis_find_model(name.encode()))
+
+    def models(self):
+        return [self._L.cpprob_sis_model_name(i).decode() for i in range(self._L.cpprob_sis_model_count())]
+
+    def describe(self, model, obs):
+        obs = _f64(obs)
+        s = Structure()
+        _check(self._L.cpprob_sis_describe(self._h, self.model_id(model), _dptr(obs), obs.size, C.byref(s)))
+        return {"ids": [s.ids[i].decode() for i in range(s.n_ids)],
+                "slots": [(s.slots[i].is_int, s.slots[i].id, s.slots[i].k, s.slots[i].row) for i in range(s.n_slots)],
+                "n_real": s.n_real, "n_int": s.n_int, "n_samples": s.n_samples}
+
+    # ---- inference ----------------------------------------------------------------------------
+    def run(self, model, obs, n, emit=EMIT_NONE, force_rows=False, collect=False):
+        """cpprob_sis_run.  With collect=True (implies EMIT_ALL) also returns the SoA trace as numpy arrays."""
+        obs = _f64(obs)
+        blocks = []
+
+        def on_block(_user, blk):
+            b = blk.contents
+            n_, st = int(b.n), int(b.stride)
+            real = np.ctypeslib.as_array(b.real_rows, shape=(b.n_real, st))[:, :n_].copy() if b.n_real else np.zeros((0, n_))
+            ints = np.ctypeslib.as_array(b.int_rows, shape=(b.n_int, st))[:, :n_].copy() if b.n_int else np.zeros((0, n_), np.int32)
+            lw = np.ctypeslib.as_array(b.log_w, shape=(n_,)).copy()
+            blocks.append((int(b.first_particle), real, ints, lw))
+            return 0
+
+        cb = BLOCK_FN(on_block) if collect else C.cast(None, BLOCK_FN)
+        opt = RunOptions(EMIT_ALL if collect else emit, 1 if force_rows else 0, cb, None)
+        st = Stats()
+        _check(self._L.cpprob_sis_run(self._h, self.model_id(model), _dptr(obs), obs.size, int(n), C.byref(opt), C.byref(st)))
+        out = stats_to_dict(st)
+        if collect:
+            blocks.sort(key=lambda b: b[0])
+            out["real_rows"] = np.concatenate([b[1] for b in blocks], axis=1)
+            out["int_rows"] = np.concatenate([b[2] for b in blocks], axis=1)
+            out["log_w"] = np.concatenate([b[3] for b in blocks])
+        return out
+
+    def infer_to_files(self, model, obs, n, prefix):
+        obs = _f64(obs)
+        st = Stats()
+        _check(self._L.cpprob_sis_infer_to_files(self._h, self.model_id(model), _dptr(obs), obs.size, int(n), prefix.encode(), C.byref(st)))
+        return stats_to_dict(st)
+
+    def run_shard(self, model, obs, n_total, rank, world, m_ref=None):
+        obs = _f64(obs)
+        p = Partials()
+        mr = C.c_double(m_ref) if m_ref is not None else None
+        _check(self._L.cpprob_sis_run_shard(self._h, self.model_id(model), _dptr(obs), obs.size, int(n_total), rank, world,
+                                            C.byref(mr) if mr is not None else None, C.byref(p)))
+        return p
+
+    def merge(self, model, obs, gathered_ptr, n_chunks_total, n_cols, m_ref, n_total):
+        """gathered_ptr: device address of the [n_chunks_total][n_cols] partials.  Returns (stats, needs_rebase)."""
+        obs = _f64(obs)
+        st = Stats()
+        rc = _check(self._L.cpprob_sis_merge(self._h, self.model_id(model), _dptr(obs), obs.size, C.c_void_p(gathered_ptr),
+                                             n_chunks_total, n_cols, m_ref, int(n_total), C.byref(st)))
+        return stats_to_dict(st), rc == 1
+
+    def replay(self, model, obs, real_rows=None, int_rows=None):
+        obs = _f64(obs)
+        real = _f64(real_rows) if real_rows is not None and np.size(real_rows) else None
+        ints = np.ascontiguousarray(np.asarray(int_rows, dtype=np.int32)) if int_rows is not None and np.size(int_rows) else None
+        ref = real if real is not None else ints
+        n = ref.shape[1]
+        out = np.empty(n, dtype=np.float64)
+        _check(self._L.cpprob_sis_replay(self._h, self.model_id(model), _dptr(obs), obs.size,
+                                         _dptr(real) if real is not None else None,
+                                         ints.ctypes.data_as(C.POINTER(C.c_int32)) if ints is not None else None,
+                                         n, n, _dptr(out)))
+        return out
+
+    def reduce_records(self, log_w, real_rows=None, int_rows=None):
+        lw = _f64(log_w)
+        n = lw.size
+        real = _f64(real_rows) if real_rows is not None and np.size(real_rows) else None
+        ints = np.ascontiguousarray(np.asarray(int_rows, dtype=np.int32)) if int_rows is not None and np.size(int_rows) else None
+        st = Stats()
+        _check(self._L.cpprob_sis_reduce_records(self._h, _dptr(real) if real is not None else None, 0 if real is None else real.shape[0],
+                                                 ints.ctypes.data_as(C.POINTER(C.c_int32)) if ints is not None else None,
+                                                 0 if ints is None else ints.shape[0], _dptr(lw), n, n, C.byref(st)))
+        return stats_to_dict(st)
+
+    # ---- device distribution layer --------------------------------------------------------------
+    def logpdf(self, kind, params, x):
+        params, x = _f64(params), _f64(x)
+        out = np.empty_like(x)
+        _check(self._L.cpprob_sis_logpdf(self._h, DIST[kind], _dptr(params), params.size, _dptr(x), x.size, _dptr(out)))
+        return out
+
+    def sample(self, kind, params, n, seed=1, first=0):
+        params = _f64(params)
+        out = np.empty(int(n), dtype=np.float64)
+        _check(self._L.cpprob_sis_sample(self._h, DIST[kind], _dptr(params), params.size, seed, first, int(n), _dptr(out)))
+        return out
+
+    def philox(self, ctr, key):
+        ctr = np.ascontiguousarray(np.asarray(ctr, dtype=np.uint32)).reshape(-1, 4)
+        key = np.ascontiguousarray(np.asarray(key, dtype=np.uint32)).reshape(-1, 2)
+        out = np.empty_like(ctr)
+        u32p = C.POINTER(C.c_uint32)
+        _check(self._L.cpprob_sis_philox(self._h, ctr.ctypes.data_as(u32p), key.ctypes.data_as(u32p), ctr.shape[0], out.ctypes.data_as(u32p)))
+        return out
+
+    def dmath(self, fn, x):
+        x = _f64(x)
+        n = x.size // 2 if fn == 5 else x.size
+        out = np.empty(n, dtype=np.float64)
+        _check(self._L.cpprob_sis_dmath(self._h, fn, _dptr(x), n, _dptr(out)))
+        return out
+
+    def dfma_peak(self):
+        t, mhz = C.c_double(), C.c_double()
+        _check(self._L.cpprob_sis_measure_dfma_peak(self._h, C.byref(t), C.byref(mhz)))
+        return t.value, mhz.value
+
+    def store_peak(self):
+        g = C.c_double()
+        _check(self._L.cpprob_sis_measure_store_peak(self._h, C.byref(g)))
+        return g.value

@@ -1,0 +1,184 @@
+// cpprob-b200: model-independent posterior reduction kernels over the SoA trace rows, and the
+// chunk-partial merge.  Together with the sums formed inside k_sis_fused / k_sis_rows they replace
+// the reference's CPU estimator pass (/root/reference: include/cpprob/postprocess/
+// stats_printer.hpp:88-120 keyed by (address id, k-th occurrence); empirical_distribution.hpp:52-81
+// mean / variance, :30-40 distribution, :117-143 max-shifted logsumexp).
+#ifndef CPPROB_B200_REDUCE_KERNELS_CUH
+#define CPPROB_B200_REDUCE_KERNELS_CUH
+
+#include "sis_kernels.cuh"
+
+namespace cpprob {
+namespace engine {
+
+// ------------------------------------------------------------------------------------------------
+// K4a k_row_moments: S1 = sum w x, S2 = sum w x^2 for kMomTile real rows of one chunk.
+// grid = (n_chunks, ceil(n_real / kMomTile)).  Each row element is read once (coalesced 8 B/lane);
+// w is re-read once per tile (L2-resident: a chunk of w is 256 KB).
+// Output: partials[chunk][kBaseCols + 2*row + {0,1}].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_row_moments(const double * __restrict__ real_rows, const double * __restrict__ w,
+                                                        unsigned long long stride, unsigned long long n_particles,
+                                                        int n_real, double * __restrict__ partials, int n_cols)
+{
+    __shared__ double smem[kWarps * 2 * kMomTile];
+    const unsigned c = blockIdx.x;
+    const int row0 = blockIdx.y * kMomTile;
+    const unsigned long long base = static_cast<unsigned long long>(c) * kChunk;
+    const unsigned long long left = n_particles - base;
+    const unsigned n_here = left < kChunk ? static_cast<unsigned>(left) : kChunk;
+
+    double acc[2 * kMomTile];
+#pragma unroll
+    for (int j = 0; j < 2 * kMomTile; ++j) acc[j] = 0.0;
+
+    for (unsigned i = threadIdx.x; i < n_here; i += kBlock) {
+        const unsigned long long colidx = base + i;
+        const double wi = w[colidx];
+#pragma unroll
+        for (int j = 0; j < kMomTile; ++j) {
+            if (row0 + j < n_real) {
+                const double x = __ldcs(real_rows + static_cast<unsigned long long>(row0 + j) * stride + colidx);
+                const double wx = wi * x;
+                acc[2 * j] += wx;
+                acc[2 * j + 1] = fma(wx, x, acc[2 * j + 1]);
+            }
+        }
+    }
+    const double r = block_reduce<2 * kMomTile>(acc, 0ull, smem);
+    if (threadIdx.x < 2 * kMomTile && row0 + static_cast<int>(threadIdx.x >> 1) < n_real) {
+        partials[static_cast<size_t>(c) * n_cols + kBaseCols + 2 * row0 + threadIdx.x] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4b k_row_hist<V>: weighted histogram sum_i w_i [x_i == lo + b], b < V, for one int row of one
+// chunk.  grid = (n_chunks, n_int).  V <= 8 bins live in registers; wider windows are covered by
+// several launches with shifted `lo` (bin_offset selects the output columns).
+// Output: partials[chunk][hist_col0 + row*hist_bins + bin_offset + b].
+// ------------------------------------------------------------------------------------------------
+template<int V>
+__global__ void __launch_bounds__(kBlock) k_row_hist(const int * __restrict__ int_rows, const double * __restrict__ w,
+                                                     unsigned long long stride, unsigned long long n_particles,
+                                                     long long lo, int bin_offset, int hist_bins, int hist_col0,
+                                                     double * __restrict__ partials, int n_cols)
+{
+    __shared__ double smem[kWarps * V];
+    const unsigned c = blockIdx.x;
+    const int row = blockIdx.y;
+    const unsigned long long base = static_cast<unsigned long long>(c) * kChunk;
+    const unsigned long long left = n_particles - base;
+    const unsigned n_here = left < kChunk ? static_cast<unsigned>(left) : kChunk;
+    const int * __restrict__ src = int_rows + static_cast<unsigned long long>(row) * stride + base;
+    const double * __restrict__ wsrc = w + base;
+
+    double h[V];
+#pragma unroll
+    for (int b = 0; b < V; ++b) h[b] = 0.0;
+    for (unsigned i = threadIdx.x; i < n_here; i += kBlock) {
+        const long long x = static_cast<long long>(__ldcs(src + i)) - lo;
+        const double wi = wsrc[i];
+#pragma unroll
+        for (int b = 0; b < V; ++b) h[b] += (x == b) ? wi : 0.0;
+    }
+    const double r = block_reduce<V>(h, 0ull, smem);
+    if (threadIdx.x < V && bin_offset + static_cast<int>(threadIdx.x) < hist_bins) {
+        partials[static_cast<size_t>(c) * n_cols + hist_col0 + row * hist_bins + bin_offset + threadIdx.x] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_merge_columns: out[col] = reduce over chunks (rows of `partials`) in a fixed order.
+// grid = n_cols CTAs.  Thread t folds rows t, t+256, ... sequentially, then the fixed CTA tree.
+// The input is the concatenation of every rank's partials in chunk order, so the result is
+// bit-identical on every rank and for every GPU count.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_merge_columns(const double * __restrict__ partials, unsigned n_rows, int n_cols,
+                                                          unsigned long long max_mask, double * __restrict__ out)
+{
+    __shared__ double smem[kWarps];
+    const int c = blockIdx.x;
+    const bool is_max = c < 64 && ((max_mask >> c) & 1ull);
+    double v[1];
+    v[0] = is_max ? dm::neg_inf() : 0.0;
+    for (unsigned r = threadIdx.x; r < n_rows; r += kBlock) {
+        const double x = partials[static_cast<size_t>(r) * n_cols + c];
+        v[0] = is_max ? fmax(v[0], x) : v[0] + x;
+    }
+    const double res = block_reduce<1>(v, is_max ? 1ull : 0ull, smem);
+    if (threadIdx.x == 0) out[c] = res;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 k_reduce_logw: base sums from a log-weight array alone (used by replay / external traces).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_reduce_logw(const double * __restrict__ logw, unsigned long long n_particles,
+                                                        const double * __restrict__ m_ref_ptr, double * __restrict__ w_out,
+                                                        double * __restrict__ partials, int n_cols)
+{
+    __shared__ double smem[kWarps * kBaseCols];
+    const unsigned c = blockIdx.x;
+    const double m_ref = *m_ref_ptr;
+    const unsigned long long base = static_cast<unsigned long long>(c) * kChunk;
+    const unsigned long long left = n_particles - base;
+    const unsigned n_here = left < kChunk ? static_cast<unsigned>(left) : kChunk;
+    double v[kBaseCols];
+#pragma unroll
+    for (int j = 0; j < kBaseCols; ++j) v[j] = 0.0;
+    v[col::max_lw] = dm::neg_inf();
+    v[col::neg_imin] = dm::neg_inf();
+    v[col::imax] = dm::neg_inf();
+    for (unsigned i = threadIdx.x; i < n_here; i += kBlock) {
+        const double lw = logw[base + i];
+        const double wi = dm::exp_weight(lw - m_ref);
+        if (w_out) w_out[base + i] = wi;
+        v[col::max_lw] = fmax(v[col::max_lw], lw);
+        v[col::s0] += wi;
+        v[col::s00] = fma(wi, wi, v[col::s00]);
+        v[col::n_neginf] += (lw == dm::neg_inf()) ? 1.0 : 0.0;
+        v[col::n_nan] += (lw != lw) ? 1.0 : 0.0;
+    }
+    const double r = block_reduce<kBaseCols>(v, kMaxColsMask, smem);
+    if (threadIdx.x < kBaseCols) partials[static_cast<size_t>(c) * n_cols + threadIdx.x] = r;
+}
+
+// k_max_array: max of an array (for choosing m_ref from external log-weights).  One CTA.
+__global__ void __launch_bounds__(kBlock) k_max_array(const double * __restrict__ x, unsigned long long n, double * __restrict__ out)
+{
+    __shared__ double smem[kWarps];
+    double v[1] = {dm::neg_inf()};
+    for (unsigned long long i = threadIdx.x; i < n; i += kBlock) v[0] = fmax(v[0], x[i]);
+    const double r = block_reduce<1>(v, 1ull, smem);
+    if (threadIdx.x == 0) out[0] = (r > -1.0e300 && r < 1.0e300) ? r : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0 micro-benchmarks: the roofline denominators (MEASURED_PEAKS.json has no FP64 entry).
+// ------------------------------------------------------------------------------------------------
+// Register-only DFMA chains: 8 independent accumulators per thread, `iters` x 8 x 4 DFMA each.
+__global__ void __launch_bounds__(kBlock) k_dfma_peak(double * __restrict__ out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) out[blockIdx.x * kBlock + threadIdx.x] = s;   // never true; keeps the chain alive
+}
+
+// Streaming store of doubles (HBM write roofline for the trace rows).
+__global__ void __launch_bounds__(kBlock) k_store_peak(double2 * __restrict__ dst, unsigned long long n2, double v)
+{
+    for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(kBlock) + threadIdx.x; i < n2;
+         i += static_cast<unsigned long long>(gridDim.x) * kBlock) {
+        dst[i] = make_double2(v, v);
+    }
+}
+
+}  // namespace engine
+}  // namespace cpprob
+#endif  // CPPROB_B200_REDUCE_KERNELS_CUH

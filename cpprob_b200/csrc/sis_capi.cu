@@ -1,0 +1,1060 @@
+// cpprob-b200: engine core behind the C ABI of include/cpprob_sis.h.
+//
+// Model-agnostic: all model code is reached through cpprob_sis_model_vtable launchers
+// (model_vtable.cuh).  One engine drives one GPU with a compute stream and a copy stream; device
+// and pinned buffers grow on demand and are kept between calls.
+#include <algorithm>
+#include <cerrno>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "cpprob_sis.h"
+#include "dist_kernels.cuh"
+#include "model_vtable.cuh"
+#include "posterior_text.hpp"
+#include "reduce_kernels.cuh"
+
+using namespace cpprob;
+using namespace cpprob::engine;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string & msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        const cudaError_t cu_try_err = (expr);                                                         \
+        if (cu_try_err != cudaSuccess) {                                                               \
+            return fail(CPPROB_SIS_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(cu_try_err)); \
+        }                                                                                              \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// registry
+// ------------------------------------------------------------------------------------------------
+std::vector<const cpprob_sis_model_vtable *> & registry()
+{
+    static std::vector<const cpprob_sis_model_vtable *> r;
+    return r;
+}
+std::mutex & registry_mutex()
+{
+    static std::mutex m;
+    return m;
+}
+
+template<class T>
+struct device_buffer {
+    T * ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        const cudaError_t err = cudaMalloc(reinterpret_cast<void **>(&ptr), n * sizeof(T));
+        if (err == cudaSuccess) cap = n;
+        return err;
+    }
+    void release()
+    {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+template<class T>
+struct pinned_buffer {
+    T * ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        cap = 0;
+        const cudaError_t err = cudaMallocHost(reinterpret_cast<void **>(&ptr), n * sizeof(T));
+        if (err == cudaSuccess) cap = n;
+        return err;
+    }
+    void release()
+    {
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct cpprob_sis_engine {
+    int device = 0;
+    int sm_count = 0;
+    int blocks_per_sm = 0;
+    uint64_t seed = 0;
+    uint64_t max_batch = 0;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_computed[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    cudaEvent_t ev_batch_begin[2] = {nullptr, nullptr};
+
+    device_buffer<double> d_obs, d_pilot, d_partials, d_merged, d_w[2], d_logw[2], d_real[2], d_gather;
+    device_buffer<int> d_int[2];
+    device_buffer<unsigned> d_counter;
+    pinned_buffer<double> h_real[2], h_logw[2], h_merged;
+    pinned_buffer<int> h_int[2];
+
+    // results kept alive for the caller
+    model_structure structure;
+    std::vector<const char *> id_ptrs;
+    std::vector<cpprob_sis_slot> slots;
+    std::vector<double> real_mean, real_var, int_prob, sums;
+    std::vector<long long> int_map;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+int use_device(cpprob_sis_engine * e)
+{
+    CU_TRY(cudaSetDevice(e->device));
+    return 0;
+}
+
+const cpprob_sis_model_vtable * model_of(int id)
+{
+    std::lock_guard<std::mutex> lock(registry_mutex());
+    if (id < 0 || static_cast<size_t>(id) >= registry().size()) return nullptr;
+    return registry()[static_cast<size_t>(id)];
+}
+
+int probe_structure(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, const double * obs, size_t n_obs)
+{
+    if (vt->n_scalar_obs >= 0 && n_obs != static_cast<size_t>(vt->n_scalar_obs)) {
+        return fail(CPPROB_SIS_EINVAL, std::string("model ") + vt->name + " takes " + std::to_string(vt->n_scalar_obs) +
+                                           " observations, got " + std::to_string(n_obs));
+    }
+    if (n_obs == 0) {
+        // cpprob.hpp:182 static_assert: the model has to receive the observed values
+        return fail(CPPROB_SIS_EINVAL, "The function has to receive the observed values as parameters.");
+    }
+    e->structure = model_structure();
+    vt->probe(obs, static_cast<int>(n_obs), e->seed, &e->structure);
+    e->id_ptrs.clear();
+    for (const auto & s : e->structure.ids) e->id_ptrs.push_back(s.c_str());
+    e->slots.clear();
+    for (const auto & s : e->structure.slots) {
+        e->slots.push_back(cpprob_sis_slot{s.is_int ? 1 : 0, static_cast<int>(s.id), static_cast<int>(s.k), static_cast<int>(s.row)});
+    }
+    return 0;
+}
+
+struct shard_plan {
+    uint32_t n_chunks_total = 0, chunk_first = 0, n_chunks_local = 0;
+    uint64_t first_particle = 0, n_local = 0;
+};
+
+shard_plan plan_shard(uint64_t n_total, int rank, int world)
+{
+    shard_plan p;
+    p.n_chunks_total = static_cast<uint32_t>((n_total + kChunk - 1) / kChunk);
+    const uint64_t c0 = static_cast<uint64_t>(p.n_chunks_total) * static_cast<uint64_t>(rank) / static_cast<uint64_t>(world);
+    const uint64_t c1 = static_cast<uint64_t>(p.n_chunks_total) * static_cast<uint64_t>(rank + 1) / static_cast<uint64_t>(world);
+    p.chunk_first = static_cast<uint32_t>(c0);
+    p.n_chunks_local = static_cast<uint32_t>(c1 - c0);
+    p.first_particle = c0 * kChunk;
+    const uint64_t end = std::min<uint64_t>(n_total, c1 * kChunk);
+    p.n_local = end > p.first_particle ? end - p.first_particle : 0;
+    return p;
+}
+
+struct hist_window {
+    long long lo = 0;
+    int bins = 0;
+};
+
+template<int V>
+cudaError_t launch_hist(cudaStream_t s, dim3 grid, const int * rows, const double * w, unsigned long long stride,
+                        unsigned long long n, long long lo, int off, int bins, int col0, double * partials, int n_cols)
+{
+    k_row_hist<V><<<grid, kBlock, 0, s>>>(rows, w, stride, n, lo, off, bins, col0, partials, n_cols);
+    return cudaGetLastError();
+}
+
+// all histogram passes for one batch; returns number of launches through *launches
+cudaError_t launch_hist_all(cudaStream_t s, unsigned n_chunks, int n_int, const int * rows, const double * w,
+                            unsigned long long stride, unsigned long long n, hist_window hw, int col0,
+                            double * partials, int n_cols, uint64_t * launches)
+{
+    const dim3 grid(n_chunks, static_cast<unsigned>(n_int));
+    for (int off = 0; off < hw.bins; off += 8) {
+        const int left = hw.bins - off;
+        cudaError_t err;
+        const long long lo = hw.lo + off;
+        switch (left >= 8 ? 8 : left) {
+        case 1: err = launch_hist<1>(s, grid, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        case 2: err = launch_hist<2>(s, grid, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        case 3: err = launch_hist<3>(s, grid, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        case 4: err = launch_hist<4>(s, grid, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        case 5: err = launch_hist<5>(s, grid, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        case 6: err = launch_hist<6>(s, grid, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        case 7: err = launch_hist<7>(s, grid, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        default: err = launch_hist<8>(s, grid, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        }
+        if (err != cudaSuccess) return err;
+        ++*launches;
+    }
+    return cudaSuccess;
+}
+
+struct shard_options {
+    int emit = CPPROB_SIS_EMIT_NONE;
+    int force_rows = 0;
+    cpprob_sis_block_fn on_block = nullptr;
+    void * user = nullptr;
+};
+
+struct shard_result {
+    shard_plan plan;
+    int n_cols = 0;
+    hist_window hw;
+    double m_ref = 0.0;
+    double device_ms = 0.0;
+    uint64_t launches = 0;
+};
+
+// The particle pass of one rank.  Leaves [n_chunks_local][n_cols] partial sums in e->d_partials.
+int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, const double * obs, size_t n_obs,
+                   uint64_t n_total, int rank, int world, const double * m_ref_override, const hist_window * hw_override,
+                   const shard_options & opt, shard_result * res)
+{
+    if (world <= 0 || rank < 0 || rank >= world) return fail(CPPROB_SIS_EINVAL, "bad rank / world");
+    if (n_total == 0) return fail(CPPROB_SIS_EINVAL, "n_particles must be positive");
+    if (n_total > (static_cast<uint64_t>(1) << 46)) return fail(CPPROB_SIS_EINVAL, "n_particles too large");
+    if (int rc = use_device(e)) return rc;
+    if (int rc = probe_structure(e, vt, obs, n_obs)) return rc;
+    const int n_real = static_cast<int>(e->structure.n_real);
+    const int n_int = static_cast<int>(e->structure.n_int);
+    const shard_plan plan = plan_shard(n_total, rank, world);
+    res->plan = plan;
+    res->launches = 0;
+    res->device_ms = 0.0;
+
+    CU_TRY(e->d_obs.reserve(n_obs));
+    CU_TRY(e->d_pilot.reserve(4));
+    CU_TRY(e->d_counter.reserve(1));
+    CU_TRY(cudaMemcpyAsync(e->d_obs.ptr, obs, n_obs * sizeof(double), cudaMemcpyHostToDevice, e->compute));
+
+    // pilot: m_ref and the int window, identical on every rank
+    const philox_keys keys(e->seed);
+    const int n_pilot = static_cast<int>(std::min<uint64_t>(n_total, kPilot));
+    double pilot[3] = {0, 0, 0};
+    CU_TRY(vt->launch_pilot(e->compute, &keys, e->d_obs.ptr, static_cast<int>(n_obs), n_pilot, e->d_pilot.ptr));
+    ++res->launches;
+    CU_TRY(cudaMemcpyAsync(pilot, e->d_pilot.ptr, 3 * sizeof(double), cudaMemcpyDeviceToHost, e->compute));
+    CU_TRY(cudaStreamSynchronize(e->compute));
+    double m_ref = pilot[0];
+    if (m_ref_override) {
+        m_ref = *m_ref_override;
+        CU_TRY(cudaMemcpyAsync(e->d_pilot.ptr, &m_ref, sizeof(double), cudaMemcpyHostToDevice, e->compute));
+    }
+    hist_window hw;
+    if (n_int > 0) {
+        if (hw_override) {
+            hw = *hw_override;
+        } else if (pilot[1] <= pilot[2]) {
+            hw.lo = static_cast<long long>(pilot[1]);
+            hw.bins = static_cast<int>(std::min<double>(pilot[2] - pilot[1] + 1.0, 1.0e9));
+        } else {
+            hw.lo = 0;
+            hw.bins = 1;
+        }
+        if (hw.bins > 4096) return fail(CPPROB_SIS_ERANGE, "int predicts span more than 4096 values");
+    }
+    res->hw = hw;
+    res->m_ref = m_ref;
+    const int n_cols = kBaseCols + 2 * n_real + n_int * hw.bins;
+    res->n_cols = n_cols;
+    if (plan.n_chunks_local == 0) return 0;
+    CU_TRY(e->d_partials.reserve(static_cast<size_t>(plan.n_chunks_local) * n_cols));
+
+    const bool fused = !opt.force_rows && opt.emit == CPPROB_SIS_EMIT_NONE && n_int == 0 && n_real <= kMaxFusedReal;
+
+    run_args a;
+    std::memset(&a, 0, sizeof a);
+    a.keys = keys;
+    a.n_obs = static_cast<int>(n_obs);
+    a.obs = e->d_obs.ptr;
+    a.m_ref = e->d_pilot.ptr;
+    a.chunk_counter = e->d_counter.ptr;
+    a.n_cols = n_cols;
+    a.hist_lo = hw.lo;
+    a.hist_bins = hw.bins;
+
+    if (fused) {
+        const int nr = n_real <= 1 ? 1 : (n_real == 2 ? 2 : 4);
+        int occ = vt->occupancy(nr == 1 ? 0 : (nr == 2 ? 1 : 2));
+        if (occ <= 0) occ = 1;
+        if (e->blocks_per_sm > 0) occ = std::min(occ, e->blocks_per_sm);
+        const int grid = static_cast<int>(std::min<uint64_t>(plan.n_chunks_local, static_cast<uint64_t>(e->sm_count) * occ));
+        a.first_particle = plan.first_particle;
+        a.n_particles = plan.n_local;
+        a.n_chunks = plan.n_chunks_local;
+        a.partials = e->d_partials.ptr;
+        CU_TRY(cudaMemsetAsync(e->d_counter.ptr, 0, sizeof(unsigned), e->compute));
+        CU_TRY(cudaEventRecord(e->ev_begin, e->compute));
+        CU_TRY(vt->launch_fused(e->compute, grid, nr, &a));
+        CU_TRY(cudaEventRecord(e->ev_end, e->compute));
+        ++res->launches;
+        CU_TRY(cudaStreamSynchronize(e->compute));
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));
+        res->device_ms = ms;
+        return 0;
+    }
+
+    // ---- row path: batches of whole chunks ------------------------------------------------------
+    const bool emit = opt.emit == CPPROB_SIS_EMIT_ALL;
+    const uint64_t bytes_per_particle = 8ull * n_real + 4ull * n_int + 16ull;
+    const uint64_t budget = emit ? (256ull << 20) : (4096ull << 20);
+    uint64_t cap = e->max_batch ? e->max_batch : budget / bytes_per_particle;
+    cap = std::max<uint64_t>(kChunk, cap / kChunk * kChunk);
+    cap = std::min<uint64_t>(cap, static_cast<uint64_t>(plan.n_chunks_local) * kChunk);
+    const int n_buf = emit ? 2 : 1;
+    for (int b = 0; b < n_buf; ++b) {
+        CU_TRY(e->d_real[b].reserve(std::max<size_t>(1, static_cast<size_t>(n_real) * cap)));
+        CU_TRY(e->d_int[b].reserve(std::max<size_t>(1, static_cast<size_t>(n_int) * cap)));
+        CU_TRY(e->d_logw[b].reserve(cap));
+        CU_TRY(e->d_w[b].reserve(cap));
+        if (emit) {
+            CU_TRY(e->h_real[b].reserve(std::max<size_t>(1, static_cast<size_t>(n_real) * cap)));
+            CU_TRY(e->h_int[b].reserve(std::max<size_t>(1, static_cast<size_t>(n_int) * cap)));
+            CU_TRY(e->h_logw[b].reserve(cap));
+        }
+    }
+    int occ = vt->occupancy(3);
+    if (occ <= 0) occ = 1;
+    if (e->blocks_per_sm > 0) occ = std::min(occ, e->blocks_per_sm);
+
+    const uint64_t n_batches = (plan.n_local + cap - 1) / cap;
+    struct pending_block { bool valid = false; uint64_t first = 0, n = 0; };
+    pending_block pending[2];
+    auto deliver = [&](int buf) -> int {
+        if (!pending[buf].valid) return 0;
+        CU_TRY(cudaEventSynchronize(e->ev_copied[buf]));
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, e->ev_batch_begin[buf], e->ev_computed[buf]));
+        res->device_ms += ms;
+        pending[buf].valid = false;
+        if (opt.on_block) {
+            cpprob_sis_block blk;
+            blk.first_particle = pending[buf].first;
+            blk.n = pending[buf].n;
+            blk.stride = cap;
+            blk.n_real = n_real;
+            blk.n_int = n_int;
+            blk.real_rows = e->h_real[buf].ptr;
+            blk.int_rows = e->h_int[buf].ptr;
+            blk.log_w = e->h_logw[buf].ptr;
+            if (opt.on_block(opt.user, &blk) != 0) return fail(CPPROB_SIS_EIO, "trace block consumer failed");
+        }
+        return 0;
+    };
+
+    if (!emit) CU_TRY(cudaEventRecord(e->ev_begin, e->compute));
+    for (uint64_t b = 0; b < n_batches; ++b) {
+        const int buf = emit ? static_cast<int>(b & 1) : 0;
+        const uint64_t off = b * cap;
+        const uint64_t n_here = std::min<uint64_t>(cap, plan.n_local - off);
+        const unsigned chunks_here = static_cast<unsigned>((n_here + kChunk - 1) / kChunk);
+        if (emit) {
+            // the previous user of this buffer pair (batch b-2) must have been handed to the consumer
+            if (int rc = deliver(buf)) return rc;
+            // ... and its device->host copy must be done before the rows are overwritten
+            if (b >= 2) CU_TRY(cudaStreamWaitEvent(e->compute, e->ev_copied[buf], 0));
+            CU_TRY(cudaEventRecord(e->ev_batch_begin[buf], e->compute));
+        }
+        a.first_particle = plan.first_particle + off;
+        a.n_particles = n_here;
+        a.n_chunks = chunks_here;
+        a.partials = e->d_partials.ptr + (off / kChunk) * n_cols;
+        a.real_rows = e->d_real[buf].ptr;
+        a.int_rows = e->d_int[buf].ptr;
+        a.logw = e->d_logw[buf].ptr;
+        a.w = e->d_w[buf].ptr;
+        a.row_stride = cap;
+        const int grid = static_cast<int>(std::min<uint64_t>(chunks_here, static_cast<uint64_t>(e->sm_count) * occ));
+        CU_TRY(cudaMemsetAsync(e->d_counter.ptr, 0, sizeof(unsigned), e->compute));
+        CU_TRY(vt->launch_rows(e->compute, grid, &a));
+        ++res->launches;
+        if (n_real > 0) {
+            const dim3 g(chunks_here, static_cast<unsigned>((n_real + kMomTile - 1) / kMomTile));
+            k_row_moments<<<g, kBlock, 0, e->compute>>>(a.real_rows, a.w, cap, n_here, n_real, a.partials, n_cols);
+            CU_TRY(cudaGetLastError());
+            ++res->launches;
+        }
+        if (n_int > 0) {
+            CU_TRY(launch_hist_all(e->compute, chunks_here, n_int, a.int_rows, a.w, cap, n_here, hw, kBaseCols + 2 * n_real,
+                                   a.partials, n_cols, &res->launches));
+        }
+        if (emit) {
+            CU_TRY(cudaEventRecord(e->ev_computed[buf], e->compute));
+            CU_TRY(cudaStreamWaitEvent(e->copy, e->ev_computed[buf], 0));
+            if (n_real > 0) {
+                CU_TRY(cudaMemcpy2DAsync(e->h_real[buf].ptr, cap * sizeof(double), a.real_rows, cap * sizeof(double),
+                                         n_here * sizeof(double), n_real, cudaMemcpyDeviceToHost, e->copy));
+            }
+            if (n_int > 0) {
+                CU_TRY(cudaMemcpy2DAsync(e->h_int[buf].ptr, cap * sizeof(int), a.int_rows, cap * sizeof(int),
+                                         n_here * sizeof(int), n_int, cudaMemcpyDeviceToHost, e->copy));
+            }
+            CU_TRY(cudaMemcpyAsync(e->h_logw[buf].ptr, a.logw, n_here * sizeof(double), cudaMemcpyDeviceToHost, e->copy));
+            CU_TRY(cudaEventRecord(e->ev_copied[buf], e->copy));
+            pending[buf].valid = true;
+            pending[buf].first = plan.first_particle + off;
+            pending[buf].n = n_here;
+            // while this batch computes and copies, hand the previous one to the consumer
+            if (int rc = deliver(buf ^ 1)) return rc;
+        }
+    }
+    if (emit) {
+        const int last = static_cast<int>((n_batches - 1) & 1);
+        if (int rc = deliver(last ^ 1)) return rc;
+        if (int rc = deliver(last)) return rc;
+    } else {
+        CU_TRY(cudaEventRecord(e->ev_end, e->compute));
+        CU_TRY(cudaStreamSynchronize(e->compute));
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));
+        res->device_ms = ms;
+    }
+    return 0;
+}
+
+// Merge [n_chunks][n_cols] partials (device) and turn the sums into estimators.
+// Returns 1 if the weights must be re-based to out->max_log_w.
+int merge_impl(cpprob_sis_engine * e, const double * gathered, uint32_t n_chunks, int n_cols, int n_real, int n_int,
+               hist_window hw, double m_ref, uint64_t n_total, cpprob_sis_stats * out, uint64_t * launches, double * ms_out)
+{
+    if (n_cols != kBaseCols + 2 * n_real + n_int * hw.bins) return fail(CPPROB_SIS_EINVAL, "n_cols does not match the model structure");
+    CU_TRY(e->d_merged.reserve(static_cast<size_t>(n_cols)));
+    CU_TRY(e->h_merged.reserve(static_cast<size_t>(n_cols)));
+    CU_TRY(cudaEventRecord(e->ev_begin, e->compute));
+    k_merge_columns<<<n_cols, kBlock, 0, e->compute>>>(gathered, n_chunks, n_cols, kMaxColsMask, e->d_merged.ptr);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(e->ev_end, e->compute));
+    ++*launches;
+    CU_TRY(cudaMemcpyAsync(e->h_merged.ptr, e->d_merged.ptr, n_cols * sizeof(double), cudaMemcpyDeviceToHost, e->compute));
+    CU_TRY(cudaStreamSynchronize(e->compute));
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));
+    *ms_out = ms;
+
+    const double * s = e->h_merged.ptr;
+    e->sums.assign(s, s + n_cols);
+    std::memset(out, 0, sizeof *out);
+    out->n_particles = n_total;
+    out->n_neg_inf = static_cast<uint64_t>(s[col::n_neginf]);
+    out->n_nan = static_cast<uint64_t>(s[col::n_nan]);
+    out->m_ref = m_ref;
+    out->max_log_w = s[col::max_lw];
+    const double s0 = s[col::s0], s00 = s[col::s00];
+    out->log_sum_exp = m_ref + std::log(s0);
+    out->log_evidence = out->log_sum_exp - std::log(static_cast<double>(n_total));
+    out->ess = s0 * s0 / s00;
+    out->n_real = n_real;
+    out->n_int = n_int;
+    e->real_mean.assign(static_cast<size_t>(n_real), 0.0);
+    e->real_var.assign(static_cast<size_t>(n_real), 0.0);
+    for (int j = 0; j < n_real; ++j) {
+        // empirical_distribution.hpp:52-81: mean = sum w~ x, variance = sum w~ x^2 - mean*mean
+        const double mean = s[kBaseCols + 2 * j] / s0;
+        e->real_mean[static_cast<size_t>(j)] = mean;
+        e->real_var[static_cast<size_t>(j)] = s[kBaseCols + 2 * j + 1] / s0 - mean * mean;
+    }
+    e->int_prob.assign(static_cast<size_t>(n_int) * hw.bins, 0.0);
+    e->int_map.assign(static_cast<size_t>(n_int), 0);
+    const int hist0 = kBaseCols + 2 * n_real;
+    for (int j = 0; j < n_int; ++j) {
+        int best = 0;
+        for (int b = 0; b < hw.bins; ++b) {
+            const double p = s[hist0 + j * hw.bins + b] / s0;
+            e->int_prob[static_cast<size_t>(j) * hw.bins + b] = p;
+            if (p > e->int_prob[static_cast<size_t>(j) * hw.bins + best]) best = b;   // first maximum wins
+        }
+        e->int_map[static_cast<size_t>(j)] = hw.lo + best;
+    }
+    out->real_mean = e->real_mean.data();
+    out->real_var = e->real_var.data();
+    out->int_lo = hw.lo;
+    out->int_bins = hw.bins;
+    out->int_prob = e->int_prob.data();
+    out->int_map = e->int_map.data();
+    out->n_cols = n_cols;
+    out->sums = e->sums.data();
+
+    // re-base if exp(log_w - m_ref) could have overflowed / underflowed the interesting weights
+    const double mx = out->max_log_w;
+    if (std::isfinite(mx) && std::fabs(mx - m_ref) > 600.0) return 1;
+    return 0;
+}
+
+// window that covers every int value seen (from merged columns); false if it already did
+bool widen_window(const cpprob_sis_stats & st, int n_int, hist_window * hw)
+{
+    if (n_int == 0) return false;
+    if (st.sums[col::int_oor] == 0.0) return false;
+    const double lo = -st.sums[col::neg_imin], hi = st.sums[col::imax];
+    hw->lo = static_cast<long long>(lo);
+    hw->bins = static_cast<int>(std::min<double>(hi - lo + 1.0, 1.0e9));
+    return true;
+}
+
+int run_full(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, const double * obs, size_t n_obs, uint64_t n,
+             const shard_options & opt_in, cpprob_sis_stats * out)
+{
+    shard_options opt = opt_in;
+    shard_result res;
+    double m_ref_override = 0.0;
+    const double * mo = nullptr;
+    hist_window hw_override;
+    const hist_window * ho = nullptr;
+    double total_ms = 0.0;
+    uint64_t launches = 0;
+    int passes = 0;
+    for (;;) {
+        if (int rc = run_shard_impl(e, vt, obs, n_obs, n, 0, 1, mo, ho, opt, &res)) return rc;
+        ++passes;
+        total_ms += res.device_ms;
+        launches += res.launches;
+        double merge_ms = 0.0;
+        const int rc = merge_impl(e, e->d_partials.ptr, res.plan.n_chunks_total, res.n_cols, static_cast<int>(e->structure.n_real),
+                                  static_cast<int>(e->structure.n_int), res.hw, res.m_ref, n, out, &launches, &merge_ms);
+        if (rc < 0) return rc;
+        total_ms += merge_ms;
+        bool again = false;
+        if (rc == 1 && passes < 3) {
+            m_ref_override = out->max_log_w;
+            mo = &m_ref_override;
+            again = true;
+        }
+        hist_window hw = res.hw;
+        if (passes < 3 && widen_window(*out, static_cast<int>(e->structure.n_int), &hw)) {
+            if (hw.bins > 4096) return fail(CPPROB_SIS_ERANGE, "int predicts span more than 4096 values");
+            hw_override = hw;
+            ho = &hw_override;
+            again = true;
+        }
+        if (!again) break;
+        // the records were already delivered in the first pass; later passes only redo the sums
+        opt.emit = CPPROB_SIS_EMIT_NONE;
+        opt.on_block = nullptr;
+        opt.force_rows = opt_in.force_rows || opt_in.emit == CPPROB_SIS_EMIT_ALL;
+    }
+    out->device_ms = total_ms;
+    out->kernel_launches = launches;
+    out->passes = passes;
+    e->launches += launches;
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int cpprob_sis_abi_version(void) { return CPPROB_SIS_ABI_VERSION; }
+
+const char * cpprob_sis_last_error(void) { return g_last_error.c_str(); }
+
+int cpprob_sis_register_model(const cpprob_sis_model_vtable * vt)
+{
+    if (!vt || vt->abi_version != CPPROB_SIS_ABI_VERSION || !vt->name) return fail(CPPROB_SIS_EINVAL, "bad model vtable");
+    std::lock_guard<std::mutex> lock(registry_mutex());
+    for (size_t i = 0; i < registry().size(); ++i) {
+        if (std::strcmp(registry()[i]->name, vt->name) == 0) {
+            registry()[i] = vt;
+            return static_cast<int>(i);
+        }
+    }
+    registry().push_back(vt);
+    return static_cast<int>(registry().size() - 1);
+}
+
+int cpprob_sis_model_count(void)
+{
+    std::lock_guard<std::mutex> lock(registry_mutex());
+    return static_cast<int>(registry().size());
+}
+
+const char * cpprob_sis_model_name(int model_id)
+{
+    const cpprob_sis_model_vtable * vt = model_of(model_id);
+    return vt ? vt->name : nullptr;
+}
+
+int cpprob_sis_find_model(const char * name)
+{
+    if (!name) return fail(CPPROB_SIS_EINVAL, "null model name");
+    std::lock_guard<std::mutex> lock(registry_mutex());
+    for (size_t i = 0; i < registry().size(); ++i) {
+        if (std::strcmp(registry()[i]->name, name) == 0) return static_cast<int>(i);
+    }
+    return fail(CPPROB_SIS_ENOMODEL, std::string("no device model named '") + name + "' is registered");
+}
+
+int cpprob_sis_create(const cpprob_sis_config * cfg, cpprob_sis_engine ** out)
+{
+    if (!out) return fail(CPPROB_SIS_EINVAL, "null out pointer");
+    *out = nullptr;
+    int n_dev = 0;
+    const cudaError_t err = cudaGetDeviceCount(&n_dev);
+    if (err != cudaSuccess || n_dev == 0) {
+        return fail(CPPROB_SIS_ECUDA, std::string("no usable CUDA device (the SIS engine has no CPU fallback): ") +
+                                          (err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0"));
+    }
+    cpprob_sis_engine * e = new cpprob_sis_engine();
+    e->device = cfg ? cfg->device : 0;
+    e->seed = cfg ? cfg->seed : 0x5eedull;
+    e->max_batch = cfg ? cfg->max_batch / kChunk * kChunk : 0;
+    e->blocks_per_sm = cfg ? cfg->blocks_per_sm : 0;
+    if (e->device < 0 || e->device >= n_dev) {
+        delete e;
+        return fail(CPPROB_SIS_EINVAL, "device ordinal out of range");
+    }
+    auto bail = [&](cudaError_t cerr, const char * what) {
+        const std::string msg = std::string(what) + ": " + cudaGetErrorString(cerr);
+        cpprob_sis_destroy(e);
+        return fail(CPPROB_SIS_ECUDA, msg);
+    };
+    cudaError_t c;
+    if ((c = cudaSetDevice(e->device)) != cudaSuccess) return bail(c, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((c = cudaGetDeviceProperties(&prop, e->device)) != cudaSuccess) return bail(c, "cudaGetDeviceProperties");
+    e->sm_count = prop.multiProcessorCount;
+    if ((c = cudaStreamCreateWithFlags(&e->compute, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
+    if ((c = cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
+    if ((c = cudaEventCreate(&e->ev_begin)) != cudaSuccess) return bail(c, "cudaEventCreate");
+    if ((c = cudaEventCreate(&e->ev_end)) != cudaSuccess) return bail(c, "cudaEventCreate");
+    for (int i = 0; i < 2; ++i) {
+        if ((c = cudaEventCreate(&e->ev_computed[i])) != cudaSuccess) return bail(c, "cudaEventCreate");
+        if ((c = cudaEventCreate(&e->ev_copied[i])) != cudaSuccess) return bail(c, "cudaEventCreate");
+        if ((c = cudaEventCreate(&e->ev_batch_begin[i])) != cudaSuccess) return bail(c, "cudaEventCreate");
+    }
+    *out = e;
+    return 0;
+}
+
+void cpprob_sis_destroy(cpprob_sis_engine * e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->compute) cudaStreamSynchronize(e->compute);
+    if (e->copy) cudaStreamSynchronize(e->copy);
+    e->d_obs.release(); e->d_pilot.release(); e->d_partials.release(); e->d_merged.release(); e->d_gather.release();
+    e->d_counter.release(); e->h_merged.release();
+    for (int i = 0; i < 2; ++i) {
+        e->d_w[i].release(); e->d_logw[i].release(); e->d_real[i].release(); e->d_int[i].release();
+        e->h_real[i].release(); e->h_logw[i].release(); e->h_int[i].release();
+        if (e->ev_computed[i]) cudaEventDestroy(e->ev_computed[i]);
+        if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]);
+        if (e->ev_batch_begin[i]) cudaEventDestroy(e->ev_batch_begin[i]);
+    }
+    if (e->ev_begin) cudaEventDestroy(e->ev_begin);
+    if (e->ev_end) cudaEventDestroy(e->ev_end);
+    if (e->compute) cudaStreamDestroy(e->compute);
+    if (e->copy) cudaStreamDestroy(e->copy);
+    delete e;
+}
+
+int cpprob_sis_describe(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs, cpprob_sis_structure * out)
+{
+    if (!e || !out || !obs) return fail(CPPROB_SIS_EINVAL, "null argument");
+    const cpprob_sis_model_vtable * vt = model_of(model_id);
+    if (!vt) return fail(CPPROB_SIS_ENOMODEL, "unknown model id");
+    if (int rc = probe_structure(e, vt, obs, n_obs)) return rc;
+    out->n_ids = static_cast<int>(e->structure.ids.size());
+    out->n_slots = static_cast<int>(e->slots.size());
+    out->n_real = static_cast<int>(e->structure.n_real);
+    out->n_int = static_cast<int>(e->structure.n_int);
+    out->n_samples = static_cast<int>(e->structure.n_samples);
+    out->ids = e->id_ptrs.data();
+    out->slots = e->slots.data();
+    return 0;
+}
+
+int cpprob_sis_run(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs, uint64_t n_particles,
+                   const cpprob_sis_run_options * opt, cpprob_sis_stats * out)
+{
+    if (!e || !out || !obs) return fail(CPPROB_SIS_EINVAL, "null argument");
+    const cpprob_sis_model_vtable * vt = model_of(model_id);
+    if (!vt) return fail(CPPROB_SIS_ENOMODEL, "unknown model id");
+    shard_options so;
+    if (opt) {
+        so.emit = opt->emit;
+        so.force_rows = opt->force_rows;
+        so.on_block = opt->on_block;
+        so.user = opt->user;
+    }
+    return run_full(e, vt, obs, n_obs, n_particles, so, out);
+}
+
+int cpprob_sis_run_shard(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs, uint64_t n_particles_total,
+                         int rank, int world, const double * m_ref_override, cpprob_sis_partials * out)
+{
+    if (!e || !out || !obs) return fail(CPPROB_SIS_EINVAL, "null argument");
+    const cpprob_sis_model_vtable * vt = model_of(model_id);
+    if (!vt) return fail(CPPROB_SIS_ENOMODEL, "unknown model id");
+    shard_result res;
+    shard_options so;
+    if (int rc = run_shard_impl(e, vt, obs, n_obs, n_particles_total, rank, world, m_ref_override, nullptr, so, &res)) return rc;
+    out->device_ptr = e->d_partials.ptr;
+    out->n_chunks_local = res.plan.n_chunks_local;
+    out->n_chunks_total = res.plan.n_chunks_total;
+    out->chunk_first = res.plan.chunk_first;
+    out->n_cols = res.n_cols;
+    out->m_ref = res.m_ref;
+    out->device_ms = res.device_ms;
+    out->kernel_launches = res.launches;
+    e->launches += res.launches;
+    return 0;
+}
+
+int cpprob_sis_merge(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs, const double * gathered,
+                     uint32_t n_chunks_total, int n_cols, double m_ref, uint64_t n_particles_total, cpprob_sis_stats * out)
+{
+    if (!e || !out || !obs || !gathered) return fail(CPPROB_SIS_EINVAL, "null argument");
+    const cpprob_sis_model_vtable * vt = model_of(model_id);
+    if (!vt) return fail(CPPROB_SIS_ENOMODEL, "unknown model id");
+    if (int rc = use_device(e)) return rc;
+    if (int rc = probe_structure(e, vt, obs, n_obs)) return rc;
+    const int n_real = static_cast<int>(e->structure.n_real), n_int = static_cast<int>(e->structure.n_int);
+    hist_window hw;
+    if (n_int > 0) {
+        // the window is a pure function of (seed, model, obs): recompute it the way run_shard did
+        const int rest = n_cols - kBaseCols - 2 * n_real;
+        if (rest <= 0 || rest % n_int != 0) return fail(CPPROB_SIS_EINVAL, "n_cols does not match the model structure");
+        hw.bins = rest / n_int;
+        CU_TRY(e->d_obs.reserve(n_obs));
+        CU_TRY(e->d_pilot.reserve(4));
+        CU_TRY(cudaMemcpyAsync(e->d_obs.ptr, obs, n_obs * sizeof(double), cudaMemcpyHostToDevice, e->compute));
+        const int n_pilot = static_cast<int>(std::min<uint64_t>(n_particles_total, kPilot));
+        const philox_keys keys(e->seed);
+        double pilot[3];
+        CU_TRY(vt->launch_pilot(e->compute, &keys, e->d_obs.ptr, static_cast<int>(n_obs), n_pilot, e->d_pilot.ptr));
+        CU_TRY(cudaMemcpyAsync(pilot, e->d_pilot.ptr, 3 * sizeof(double), cudaMemcpyDeviceToHost, e->compute));
+        CU_TRY(cudaStreamSynchronize(e->compute));
+        hw.lo = pilot[1] <= pilot[2] ? static_cast<long long>(pilot[1]) : 0;
+    }
+    uint64_t launches = 0;
+    double ms = 0.0;
+    const int rc = merge_impl(e, gathered, n_chunks_total, n_cols, n_real, n_int, hw, m_ref, n_particles_total, out, &launches, &ms);
+    if (rc < 0) return rc;
+    if (n_int > 0 && out->sums[col::int_oor] != 0.0) {
+        return fail(CPPROB_SIS_ERANGE, "int predicts fell outside the pilot's histogram window");
+    }
+    out->device_ms = ms;
+    out->kernel_launches = launches;
+    out->passes = 1;
+    e->launches += launches;
+    return rc;
+}
+
+int cpprob_sis_replay(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs, const double * real_rows,
+                      const int32_t * int_rows, uint64_t stride, uint64_t n, double * logw_out)
+{
+    if (!e || !obs || !logw_out) return fail(CPPROB_SIS_EINVAL, "null argument");
+    const cpprob_sis_model_vtable * vt = model_of(model_id);
+    if (!vt) return fail(CPPROB_SIS_ENOMODEL, "unknown model id");
+    if (!vt->replayable) return fail(CPPROB_SIS_EINVAL, std::string("model ") + vt->name + " is not replayable");
+    if (n == 0) return 0;
+    if (int rc = use_device(e)) return rc;
+    if (int rc = probe_structure(e, vt, obs, n_obs)) return rc;
+    const size_t n_real = e->structure.n_real, n_int = e->structure.n_int;
+    if ((n_real && !real_rows) || (n_int && !int_rows) || stride < n) return fail(CPPROB_SIS_EINVAL, "bad trace rows");
+    CU_TRY(e->d_obs.reserve(n_obs));
+    CU_TRY(e->d_real[0].reserve(std::max<size_t>(1, n_real * stride)));
+    CU_TRY(e->d_int[0].reserve(std::max<size_t>(1, n_int * stride)));
+    CU_TRY(e->d_logw[0].reserve(n));
+    CU_TRY(cudaMemcpyAsync(e->d_obs.ptr, obs, n_obs * sizeof(double), cudaMemcpyHostToDevice, e->compute));
+    if (n_real) CU_TRY(cudaMemcpyAsync(e->d_real[0].ptr, real_rows, n_real * stride * sizeof(double), cudaMemcpyHostToDevice, e->compute));
+    if (n_int) CU_TRY(cudaMemcpyAsync(e->d_int[0].ptr, int_rows, n_int * stride * sizeof(int), cudaMemcpyHostToDevice, e->compute));
+    const int grid = static_cast<int>(std::min<uint64_t>((n + kBlock - 1) / kBlock, static_cast<uint64_t>(e->sm_count) * 8));
+    CU_TRY(vt->launch_replay(e->compute, grid, e->d_obs.ptr, static_cast<int>(n_obs), e->d_real[0].ptr, e->d_int[0].ptr, stride, n,
+                             e->d_logw[0].ptr));
+    ++e->launches;
+    CU_TRY(cudaMemcpyAsync(logw_out, e->d_logw[0].ptr, n * sizeof(double), cudaMemcpyDeviceToHost, e->compute));
+    CU_TRY(cudaStreamSynchronize(e->compute));
+    return 0;
+}
+
+int cpprob_sis_reduce_records(cpprob_sis_engine * e, const double * real_rows, int n_real, const int32_t * int_rows, int n_int,
+                              const double * log_w, uint64_t stride, uint64_t n, cpprob_sis_stats * out)
+{
+    if (!e || !out || !log_w || n == 0 || stride < n || n_real < 0 || n_int < 0) return fail(CPPROB_SIS_EINVAL, "bad argument");
+    if ((n_real && !real_rows) || (n_int && !int_rows)) return fail(CPPROB_SIS_EINVAL, "null rows");
+    if (int rc = use_device(e)) return rc;
+    // int window from the data itself (host pass over the ints is cheap next to the upload)
+    hist_window hw;
+    if (n_int > 0) {
+        int lo = std::numeric_limits<int>::max(), hi = std::numeric_limits<int>::min();
+        for (int r = 0; r < n_int; ++r) {
+            for (uint64_t i = 0; i < n; ++i) {
+                const int v = int_rows[static_cast<uint64_t>(r) * stride + i];
+                lo = std::min(lo, v);
+                hi = std::max(hi, v);
+            }
+        }
+        hw.lo = lo;
+        const long long span = static_cast<long long>(hi) - lo + 1;
+        if (span > 4096) return fail(CPPROB_SIS_ERANGE, "int predicts span more than 4096 values");
+        hw.bins = static_cast<int>(span);
+    }
+    const int n_cols = kBaseCols + 2 * n_real + n_int * hw.bins;
+    const unsigned n_chunks = static_cast<unsigned>((n + kChunk - 1) / kChunk);
+    CU_TRY(e->d_real[0].reserve(std::max<size_t>(1, static_cast<size_t>(n_real) * stride)));
+    CU_TRY(e->d_int[0].reserve(std::max<size_t>(1, static_cast<size_t>(n_int) * stride)));
+    CU_TRY(e->d_logw[0].reserve(n));
+    CU_TRY(e->d_w[0].reserve(n));
+    CU_TRY(e->d_pilot.reserve(4));
+    CU_TRY(e->d_partials.reserve(static_cast<size_t>(n_chunks) * n_cols));
+    if (n_real) CU_TRY(cudaMemcpyAsync(e->d_real[0].ptr, real_rows, static_cast<size_t>(n_real) * stride * sizeof(double), cudaMemcpyHostToDevice, e->compute));
+    if (n_int) CU_TRY(cudaMemcpyAsync(e->d_int[0].ptr, int_rows, static_cast<size_t>(n_int) * stride * sizeof(int), cudaMemcpyHostToDevice, e->compute));
+    CU_TRY(cudaMemcpyAsync(e->d_logw[0].ptr, log_w, n * sizeof(double), cudaMemcpyHostToDevice, e->compute));
+    uint64_t launches = 0;
+    CU_TRY(cudaEventRecord(e->ev_begin, e->compute));
+    k_max_array<<<1, kBlock, 0, e->compute>>>(e->d_logw[0].ptr, n, e->d_pilot.ptr);
+    CU_TRY(cudaGetLastError());
+    k_reduce_logw<<<n_chunks, kBlock, 0, e->compute>>>(e->d_logw[0].ptr, n, e->d_pilot.ptr, e->d_w[0].ptr, e->d_partials.ptr, n_cols);
+    CU_TRY(cudaGetLastError());
+    launches += 2;
+    if (n_real > 0) {
+        const dim3 g(n_chunks, static_cast<unsigned>((n_real + kMomTile - 1) / kMomTile));
+        k_row_moments<<<g, kBlock, 0, e->compute>>>(e->d_real[0].ptr, e->d_w[0].ptr, stride, n, n_real, e->d_partials.ptr, n_cols);
+        CU_TRY(cudaGetLastError());
+        ++launches;
+    }
+    if (n_int > 0) {
+        CU_TRY(launch_hist_all(e->compute, n_chunks, n_int, e->d_int[0].ptr, e->d_w[0].ptr, stride, n, hw, kBaseCols + 2 * n_real,
+                               e->d_partials.ptr, n_cols, &launches));
+    }
+    CU_TRY(cudaEventRecord(e->ev_end, e->compute));
+    double m_ref = 0.0;
+    CU_TRY(cudaMemcpyAsync(&m_ref, e->d_pilot.ptr, sizeof(double), cudaMemcpyDeviceToHost, e->compute));
+    CU_TRY(cudaStreamSynchronize(e->compute));
+    float ms1 = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms1, e->ev_begin, e->ev_end));
+    double ms2 = 0.0;
+    const int rc = merge_impl(e, e->d_partials.ptr, n_chunks, n_cols, n_real, n_int, hw, m_ref, n, out, &launches, &ms2);
+    if (rc < 0) return rc;
+    out->device_ms = ms1 + ms2;
+    out->kernel_launches = launches;
+    out->passes = 1;
+    e->launches += launches;
+    return 0;
+}
+
+// ---- device distribution layer -------------------------------------------------------------------
+namespace {
+int map_grid(const cpprob_sis_engine * e, uint64_t n)
+{
+    return static_cast<int>(std::max<uint64_t>(1, std::min<uint64_t>((n + kBlock - 1) / kBlock, static_cast<uint64_t>(e->sm_count) * 8)));
+}
+}  // namespace
+
+int cpprob_sis_logpdf(cpprob_sis_engine * e, int kind, const double * params, int n_params, const double * x, uint64_t n, double * out)
+{
+    if (!e || !params || !x || !out || n_params < 0 || n_params > 8) return fail(CPPROB_SIS_EINVAL, "bad argument");
+    if (n == 0) return 0;
+    if (int rc = use_device(e)) return rc;
+    CU_TRY(e->d_logw[0].reserve(n));
+    CU_TRY(e->d_w[0].reserve(n));
+    CU_TRY(cudaMemcpyAsync(e->d_logw[0].ptr, x, n * sizeof(double), cudaMemcpyHostToDevice, e->compute));
+    logpdf_op op;
+    op.kind = kind;
+    std::memset(&op.q, 0, sizeof op.q);
+    for (int i = 0; i < n_params; ++i) op.q.p[i] = params[i];
+    op.q.n = n_params;
+    op.x = e->d_logw[0].ptr;
+    op.out = e->d_w[0].ptr;
+    k_map<<<map_grid(e, n), kBlock, 0, e->compute>>>(n, op);
+    CU_TRY(cudaGetLastError());
+    ++e->launches;
+    CU_TRY(cudaMemcpyAsync(out, e->d_w[0].ptr, n * sizeof(double), cudaMemcpyDeviceToHost, e->compute));
+    CU_TRY(cudaStreamSynchronize(e->compute));
+    return 0;
+}
+
+int cpprob_sis_sample(cpprob_sis_engine * e, int kind, const double * params, int n_params, uint64_t seed, uint64_t first_particle,
+                      uint64_t n, double * out)
+{
+    if (!e || !params || !out || n_params < 0 || n_params > 8) return fail(CPPROB_SIS_EINVAL, "bad argument");
+    if (n == 0) return 0;
+    if (int rc = use_device(e)) return rc;
+    CU_TRY(e->d_w[0].reserve(n));
+    sample_op op;
+    op.kind = kind;
+    std::memset(&op.q, 0, sizeof op.q);
+    for (int i = 0; i < n_params; ++i) op.q.p[i] = params[i];
+    op.q.n = n_params;
+    op.seed = seed;
+    op.first = first_particle;
+    op.out = e->d_w[0].ptr;
+    k_map<<<map_grid(e, n), kBlock, 0, e->compute>>>(n, op);
+    CU_TRY(cudaGetLastError());
+    ++e->launches;
+    CU_TRY(cudaMemcpyAsync(out, e->d_w[0].ptr, n * sizeof(double), cudaMemcpyDeviceToHost, e->compute));
+    CU_TRY(cudaStreamSynchronize(e->compute));
+    return 0;
+}
+
+int cpprob_sis_philox(cpprob_sis_engine * e, const uint32_t * ctr, const uint32_t * key, uint64_t n, uint32_t * out)
+{
+    if (!e || !ctr || !key || !out) return fail(CPPROB_SIS_EINVAL, "bad argument");
+    if (n == 0) return 0;
+    if (int rc = use_device(e)) return rc;
+    // 4 + 2 + 4 words per block, staged in the double buffers (8-byte aligned)
+    CU_TRY(e->d_logw[0].reserve(n * 2));
+    CU_TRY(e->d_w[0].reserve(n * 2));
+    CU_TRY(e->d_real[0].reserve(n));
+    unsigned * d_ctr = reinterpret_cast<unsigned *>(e->d_logw[0].ptr);
+    unsigned * d_out = reinterpret_cast<unsigned *>(e->d_w[0].ptr);
+    unsigned * d_key = reinterpret_cast<unsigned *>(e->d_real[0].ptr);
+    CU_TRY(cudaMemcpyAsync(d_ctr, ctr, n * 4 * sizeof(unsigned), cudaMemcpyHostToDevice, e->compute));
+    CU_TRY(cudaMemcpyAsync(d_key, key, n * 2 * sizeof(unsigned), cudaMemcpyHostToDevice, e->compute));
+    philox_op op{d_ctr, d_key, d_out};
+    k_map<<<map_grid(e, n), kBlock, 0, e->compute>>>(n, op);
+    CU_TRY(cudaGetLastError());
+    ++e->launches;
+    CU_TRY(cudaMemcpyAsync(out, d_out, n * 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, e->compute));
+    CU_TRY(cudaStreamSynchronize(e->compute));
+    return 0;
+}
+
+int cpprob_sis_dmath(cpprob_sis_engine * e, int fn, const double * x, uint64_t n, double * out)
+{
+    if (!e || !x || !out) return fail(CPPROB_SIS_EINVAL, "bad argument");
+    if (n == 0) return 0;
+    if (int rc = use_device(e)) return rc;
+    const uint64_t n_in = fn == 5 ? 2 * n : n;
+    CU_TRY(e->d_logw[0].reserve(n_in));
+    CU_TRY(e->d_w[0].reserve(n));
+    CU_TRY(cudaMemcpyAsync(e->d_logw[0].ptr, x, n_in * sizeof(double), cudaMemcpyHostToDevice, e->compute));
+    dmath_op op{fn, e->d_logw[0].ptr, e->d_w[0].ptr};
+    k_map<<<map_grid(e, n), kBlock, 0, e->compute>>>(n, op);
+    CU_TRY(cudaGetLastError());
+    ++e->launches;
+    CU_TRY(cudaMemcpyAsync(out, e->d_w[0].ptr, n * sizeof(double), cudaMemcpyDeviceToHost, e->compute));
+    CU_TRY(cudaStreamSynchronize(e->compute));
+    return 0;
+}
+
+// ---- roofline denominators -------------------------------------------------------------------------
+int cpprob_sis_measure_dfma_peak(cpprob_sis_engine * e, double * tflops, double * sm_clock_mhz_est)
+{
+    if (!e || !tflops) return fail(CPPROB_SIS_EINVAL, "bad argument");
+    if (int rc = use_device(e)) return rc;
+    const int grid = e->sm_count * 8;
+    CU_TRY(e->d_w[0].reserve(static_cast<size_t>(grid) * kBlock));
+    const int iters = 4096;
+    double best_ms = 1e30;
+    for (int rep = 0; rep < 6; ++rep) {
+        CU_TRY(cudaEventRecord(e->ev_begin, e->compute));
+        k_dfma_peak<<<grid, kBlock, 0, e->compute>>>(e->d_w[0].ptr, iters, 0.999999, 1.0e-6);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaEventRecord(e->ev_end, e->compute));
+        CU_TRY(cudaStreamSynchronize(e->compute));
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));
+        if (rep > 0) best_ms = std::min<double>(best_ms, ms);
+        ++e->launches;
+    }
+    const double fmas = static_cast<double>(grid) * kBlock * iters * 32.0;
+    *tflops = 2.0 * fmas / (best_ms * 1e-3) / 1e12;
+    if (sm_clock_mhz_est) {
+        // 64 DFMA lanes per SM per clock
+        *sm_clock_mhz_est = fmas / (best_ms * 1e-3) / (64.0 * e->sm_count) / 1e6;
+    }
+    return 0;
+}
+
+int cpprob_sis_measure_store_peak(cpprob_sis_engine * e, double * gbytes_per_s)
+{
+    if (!e || !gbytes_per_s) return fail(CPPROB_SIS_EINVAL, "bad argument");
+    if (int rc = use_device(e)) return rc;
+    const size_t n = (1ull << 30) / sizeof(double);   // 1 GiB, well beyond L2
+    CU_TRY(e->d_real[0].reserve(n));
+    double best_ms = 1e30;
+    for (int rep = 0; rep < 6; ++rep) {
+        CU_TRY(cudaEventRecord(e->ev_begin, e->compute));
+        k_store_peak<<<e->sm_count * 16, kBlock, 0, e->compute>>>(reinterpret_cast<double2 *>(e->d_real[0].ptr), n / 2, 1.0 + rep);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaEventRecord(e->ev_end, e->compute));
+        CU_TRY(cudaStreamSynchronize(e->compute));
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));
+        if (rep > 0) best_ms = std::min<double>(best_ms, ms);
+        ++e->launches;
+    }
+    *gbytes_per_s = static_cast<double>(n * sizeof(double)) / (best_ms * 1e-3) / 1e9;
+    return 0;
+}
+
+// ---- posterior files ---------------------------------------------------------------------------------
+namespace {
+struct file_sink {
+    cpprob_sis_engine * e;
+    cpprob::text::posterior_writer * writer;
+};
+int file_sink_block(void * user, const cpprob_sis_block * blk)
+{
+    file_sink * fs = static_cast<file_sink *>(user);
+    return fs->writer->append(*blk) ? 0 : 1;
+}
+}  // namespace
+
+int cpprob_sis_infer_to_files(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs, uint64_t n_particles,
+                              const char * prefix, cpprob_sis_stats * out)
+{
+    if (!e || !out || !obs || !prefix) return fail(CPPROB_SIS_EINVAL, "null argument");
+    const cpprob_sis_model_vtable * vt = model_of(model_id);
+    if (!vt) return fail(CPPROB_SIS_ENOMODEL, "unknown model id");
+    if (int rc = probe_structure(e, vt, obs, n_obs)) return rc;
+    cpprob::text::posterior_writer writer(prefix, e->slots);
+    if (!writer.open()) return fail(CPPROB_SIS_EIO, std::string("cannot open posterior files for ") + prefix + ": " + std::strerror(errno));
+    file_sink fs{e, &writer};
+    shard_options so;
+    so.emit = CPPROB_SIS_EMIT_ALL;
+    so.on_block = &file_sink_block;
+    so.user = &fs;
+    const int rc = run_full(e, vt, obs, n_obs, n_particles, so, out);
+    if (rc != 0) return rc;
+    if (!writer.finish(e->structure.ids)) return fail(CPPROB_SIS_EIO, std::string("cannot write ") + prefix + ".ids");
+    if (!cpprob::text::write_stats_sidecar(prefix, *out, e->slots, e->structure.ids)) {
+        return fail(CPPROB_SIS_EIO, std::string("cannot write ") + prefix + ".stats");
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,453 @@
+// cpprob-b200: the SIS kernels (sm_100a).  One particle = one thread-iteration; all particle state
+// (Philox key/counter, log_w, staged predict values) is register-resident.
+//
+// What the reference does per particle (/root/reference: include/cpprob/cpprob.hpp:194-201):
+//     start_trace(); call_f_tuple(f, observes); finish_trace();
+// with finish_trace appending a text record to three files (src/cpprob/state.cpp:193-202), and a
+// later StatsPrinter pass re-reading the text to form self-normalised estimators
+// (include/cpprob/postprocess/stats_printer.hpp:88-120, empirical_distribution.hpp:52-81,117-143).
+// Here the model body, the weight exp(log_w - m_ref) and the estimator sums are one kernel.
+//
+// Determinism: particles are grouped in fixed CHUNKs of 2^15 consecutive global indices.  A chunk is
+// always reduced by one CTA with a fixed thread->particle map and a fixed shuffle/shared-memory
+// tree, so a chunk's partial sums are bit-identical whatever the grid size, schedule (chunks are
+// handed out through an atomic counter) or GPU count.  Chunk partials are then merged in chunk order
+// by k_merge_columns.  All weights are taken relative to one run-wide reference m_ref (max log_w of
+// a pilot over global particles [0, 4096), identical on every rank), so merging is plain addition.
+#ifndef CPPROB_B200_SIS_KERNELS_CUH
+#define CPPROB_B200_SIS_KERNELS_CUH
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "cpprob/particle.hpp"
+
+namespace cpprob {
+namespace engine {
+
+constexpr int kBlock = 256;                 // threads per CTA
+constexpr int kWarps = kBlock / 32;
+constexpr unsigned kChunk = 1u << 15;       // particles per deterministic reduction unit
+constexpr int kBaseCols = 8;                // partial columns every run has (see col:: below)
+constexpr int kPilot = 4096;                // pilot particles (global indices [0, kPilot))
+constexpr int kMomTile = 8;                 // real rows per k_row_moments CTA
+constexpr int kMaxFusedReal = 4;            // register-staged predict slots in the fused kernel
+
+namespace col {
+enum : int { max_lw = 0, s0 = 1, s00 = 2, n_neginf = 3, neg_imin = 4, imax = 5, int_oor = 6, n_nan = 7 };
+}
+// columns merged with max (all others with +)
+constexpr unsigned long long kMaxColsMask = (1ull << col::max_lw) | (1ull << col::neg_imin) | (1ull << col::imax);
+
+static_assert(kBlock == static_cast<int>(kPairStride), "one CTA row of threads per half stream tile");
+static_assert(kChunk % (2 * kPairStride) == 0, "chunks hold whole stream tiles");
+
+struct run_args {
+    philox_keys keys;                    // expanded Philox round keys of the run's seed
+    unsigned long long first_particle;   // global index of this launch's first particle (multiple of kChunk)
+    unsigned long long n_particles;      // particles in this launch
+    unsigned n_chunks;                   // ceil(n_particles / kChunk)
+    int n_obs;
+    const double * obs;                  // device
+    const double * m_ref;                // device scalar
+    unsigned * chunk_counter;            // device, zeroed before the launch
+    double * partials;                   // [n_chunks][n_cols]
+    int n_cols;
+    // SoA trace rows (row kernels only); column index = particle index within the launch
+    double * real_rows;                  // [n_real][row_stride]
+    int * int_rows;                      // [n_int][row_stride]
+    double * logw;                       // [row_stride]
+    double * w;                          // [row_stride]
+    unsigned long long row_stride;
+    // histogram window for int predicts (from the pilot)
+    long long hist_lo;
+    int hist_bins;
+};
+
+// ------------------------------------------------------------------------------------------------
+// CTA-wide reduction of N doubles with a fixed tree.  Slot i uses max if bit i of max_mask is set.
+// Result valid in threads [0, N) of the CTA (one value each).
+// ------------------------------------------------------------------------------------------------
+template<int N>
+__device__ __forceinline__ double block_reduce(double (&v)[N], unsigned long long max_mask, double * smem /*[kWarps][N]*/)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double x = v[i];
+        const bool is_max = (max_mask >> i) & 1ull;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double y = __shfl_xor_sync(0xffffffffu, x, off);
+            x = is_max ? fmax(x, y) : x + y;
+        }
+        if (lane == 0) smem[warp * N + i] = x;
+    }
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x < N) {
+        const bool is_max = (max_mask >> threadIdx.x) & 1ull;
+        r = smem[threadIdx.x];
+#pragma unroll
+        for (int wi = 1; wi < kWarps; ++wi) {
+            const double y = smem[wi * N + threadIdx.x];
+            r = is_max ? fmax(r, y) : r + y;
+        }
+    }
+    __syncthreads();
+    return r;
+}
+
+// special-value tests on the bit pattern (ALU pipe) instead of DSETP (FP64 pipe)
+__device__ __forceinline__ bool is_finite(double x)
+{
+    return (static_cast<unsigned>(__double2hiint(x)) & 0x7FF00000u) != 0x7FF00000u;
+}
+__device__ __forceinline__ bool is_neg_inf(double x)
+{
+    return __double2hiint(x) == static_cast<int>(0xFFF00000u) && __double2loint(x) == 0;
+}
+__device__ __forceinline__ bool is_nan(double x)
+{
+    const unsigned hi = static_cast<unsigned>(__double2hiint(x)) & 0x7FFFFFFFu;
+    return hi > 0x7FF00000u || (hi == 0x7FF00000u && __double2loint(x) != 0);
+}
+
+// Next chunk for this CTA (dynamic schedule; results do not depend on it).
+__device__ __forceinline__ unsigned fetch_chunk(unsigned * counter, unsigned * s_slot)
+{
+    if (threadIdx.x == 0) *s_slot = atomicAdd(counter, 1u);
+    __syncthreads();
+    const unsigned c = *s_slot;
+    __syncthreads();
+    return c;
+}
+
+// Runs body(rng, i) for the particles of [0, n_here) owned by this thread: in every tile of 512 the
+// thread owns local indices t and t + 256, which share one Philox stream (random/philox.hpp).
+// `global_base` is the global index of local particle 0 (a multiple of 512).
+template<class Body>
+__device__ __forceinline__ void for_each_owned_particle(const philox_keys & keys, unsigned long long global_base,
+                                                        unsigned n_here, Body && body)
+{
+    const unsigned n_tiles = (n_here + 2 * kPairStride - 1) / (2 * kPairStride);
+    const unsigned long long stream0 = stream_of_particle(global_base) + threadIdx.x;
+    for (unsigned tile = 0; tile < n_tiles; ++tile) {
+        const unsigned ia = tile * (2 * kPairStride) + threadIdx.x;
+        if (ia < n_here) {
+            philox_stream rng(keys, stream0 + static_cast<unsigned long long>(tile) * kPairStride);
+            body(rng, ia);
+            const unsigned ib = ia + kPairStride;
+            if (ib < n_here) body(rng, ib);
+        }
+    }
+}
+
+// Observations of scalar-argument models are read once into registers; array models read theirs
+// through the read-only path as they go (the same address in every lane: one L1 hit per warp).
+template<class Model, bool Scalars = (Model::n_scalar_obs >= 0)>
+struct obs_cache {
+    double v[Model::n_scalar_obs > 0 ? Model::n_scalar_obs : 1];
+    __device__ __forceinline__ obs_cache(const double * __restrict__ obs, int)
+    {
+#pragma unroll
+        for (int i = 0; i < Model::n_scalar_obs; ++i) v[i] = __ldg(obs + i);
+    }
+    __device__ __forceinline__ const double * data() const { return v; }
+};
+template<class Model>
+struct obs_cache<Model, false> {
+    const double * p;
+    __device__ __forceinline__ obs_cache(const double * __restrict__ obs, int) : p(obs) {}
+    __device__ __forceinline__ const double * data() const { return p; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Policies (see include/cpprob/particle.hpp)
+// ------------------------------------------------------------------------------------------------
+
+// Pilot / dry run: draw from the prior, drop predicts, remember the int range.
+struct null_policy {
+    long long imin, imax;
+    __device__ __forceinline__ null_policy() : imin(0x7fffffffffffffffLL), imax(-0x7fffffffffffffffLL - 1) {}
+    template<class D>
+    __device__ __forceinline__ typename D::result_type sample(const D & d, philox_stream & rng) { return d(rng); }
+    template<class S> __device__ __forceinline__ void predict_int(long long x, const S &)
+    {
+        imin = x < imin ? x : imin;
+        imax = x > imax ? x : imax;
+    }
+    template<class S> __device__ __forceinline__ void predict_real(double, const S &) {}
+};
+
+// Fused kernel: up to NR real predicts staged in registers.
+template<int NR>
+struct reg_policy {
+    double v[NR];
+    int k;
+    __device__ __forceinline__ reg_policy() : k(0)
+    {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) v[i] = 0.0;
+    }
+    template<class D>
+    __device__ __forceinline__ typename D::result_type sample(const D & d, philox_stream & rng) { return d(rng); }
+    template<class S> __device__ __forceinline__ void predict_int(long long, const S &) {}
+    template<class S> __device__ __forceinline__ void predict_real(double x, const S &)
+    {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) if (k == i) v[i] = x;
+        ++k;
+    }
+};
+
+// Row kernel: address-major SoA rows in HBM; consecutive threads own consecutive columns, so each
+// predict statement is one fully coalesced store per warp.
+struct row_policy {
+    double * real_col;
+    int * int_col;
+    unsigned long long stride;
+    long long hist_lo;
+    int hist_bins;
+    int oor;
+    long long imin, imax;
+    __device__ __forceinline__ row_policy(double * rc, int * ic, unsigned long long s, long long lo, int bins)
+        : real_col(rc), int_col(ic), stride(s), hist_lo(lo), hist_bins(bins), oor(0),
+          imin(0x7fffffffffffffffLL), imax(-0x7fffffffffffffffLL - 1) {}
+    template<class D>
+    __device__ __forceinline__ typename D::result_type sample(const D & d, philox_stream & rng) { return d(rng); }
+    template<class S> __device__ __forceinline__ void predict_int(long long x, const S &)
+    {
+        *int_col = static_cast<int>(x);
+        int_col += stride;
+        imin = x < imin ? x : imin;
+        imax = x > imax ? x : imax;
+        const long long b = x - hist_lo;
+        oor += (b < 0 || b >= hist_bins) ? 1 : 0;
+    }
+    template<class S> __device__ __forceinline__ void predict_real(double x, const S &)
+    {
+        *real_col = x;
+        real_col += stride;
+    }
+};
+
+// Replay: the k-th sample statement of a kind returns the k-th recorded predict of that kind.
+// Valid for models that predict every sampled value in program order (all three target models;
+// SURVEY.md §8c "Replay check feasibility").
+struct replay_policy {
+    const double * real_col;
+    const int * int_col;
+    unsigned long long stride;
+    __device__ __forceinline__ replay_policy(const double * rc, const int * ic, unsigned long long s)
+        : real_col(rc), int_col(ic), stride(s) {}
+    template<class D>
+    __device__ __forceinline__ typename D::result_type sample(const D &, philox_stream &)
+    {
+        return take(std::integral_constant<bool, std::is_integral<typename D::result_type>::value>(),
+                    static_cast<typename D::result_type *>(nullptr));
+    }
+    template<class S> __device__ __forceinline__ void predict_int(long long, const S &) {}
+    template<class S> __device__ __forceinline__ void predict_real(double, const S &) {}
+
+private:
+    template<class R>
+    __device__ __forceinline__ R take(std::true_type, R *)
+    {
+        const int x = __ldg(int_col);
+        int_col += stride;
+        return static_cast<R>(x);
+    }
+    template<class R>
+    __device__ __forceinline__ R take(std::false_type, R *)
+    {
+        const double x = __ldg(real_col);
+        real_col += stride;
+        return static_cast<R>(x);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// K_pilot: max log_w and int-predict range over global particles [0, n_pilot).  One CTA.
+// out[0] = m_ref (finite; 0 if every pilot weight is -inf / nan), out[1] = imin, out[2] = imax
+// (as doubles; imin > imax when the model has no int predicts).
+// ------------------------------------------------------------------------------------------------
+template<class Model>
+__global__ void __launch_bounds__(kBlock) k_pilot(const __grid_constant__ philox_keys keys, const double * __restrict__ obs,
+                                                  int n_obs, int n_pilot, double * __restrict__ out)
+{
+    __shared__ double smem[kWarps * 3];
+    const Model model{};
+    const obs_cache<Model> oc(obs, n_obs);
+    double v[3] = {dm::neg_inf(), dm::neg_inf(), dm::neg_inf()};   // max lw, max(-imin), max(imax)
+    for_each_owned_particle(keys, 0ull, static_cast<unsigned>(n_pilot), [&](philox_stream & rng, unsigned) {
+        null_policy pol;
+        particle<null_policy> p(rng, pol);
+        invoke_model(model, p, oc.data(), n_obs);
+        v[0] = fmax(v[0], p.log_w());
+        if (pol.imin <= pol.imax) {
+            v[1] = fmax(v[1], -static_cast<double>(pol.imin));
+            v[2] = fmax(v[2], static_cast<double>(pol.imax));
+        }
+    });
+    const double r = block_reduce<3>(v, 0x7ull, smem);
+    if (threadIdx.x == 0) out[0] = (r > -1.0e300 && r < 1.0e300) ? r : 0.0;
+    if (threadIdx.x == 1) out[1] = -r;
+    if (threadIdx.x == 2) out[2] = r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 k_sis_fused: model body + weight + estimator sums, no trace written.  Used when the model has
+// no int predicts and at most NR real predicts per trace and no trace emission was asked for.
+// Partial columns: kBaseCols then (S1, S2) per real predict slot.
+// ------------------------------------------------------------------------------------------------
+template<class Model, int NR>
+__global__ void __launch_bounds__(kBlock) k_sis_fused(const __grid_constant__ run_args a)
+{
+    constexpr int NV = kBaseCols + 2 * NR;
+    __shared__ double smem[kWarps * NV];
+    __shared__ unsigned s_chunk;
+    const Model model{};
+    const double m_ref = *a.m_ref;
+    const obs_cache<Model> oc(a.obs, a.n_obs);
+
+    for (;;) {
+        const unsigned c = fetch_chunk(a.chunk_counter, &s_chunk);
+        if (c >= a.n_chunks) break;
+        const unsigned long long base = static_cast<unsigned long long>(c) * kChunk;
+        const unsigned long long left = a.n_particles - base;
+        const unsigned n_here = left < kChunk ? static_cast<unsigned>(left) : kChunk;
+
+        double max_lw = dm::neg_inf(), s0 = 0.0, s00 = 0.0;
+        unsigned n_neginf = 0, n_nan = 0;
+        double s1[NR], s2[NR];
+#pragma unroll
+        for (int j = 0; j < NR; ++j) { s1[j] = 0.0; s2[j] = 0.0; }
+
+        for_each_owned_particle(a.keys, a.first_particle + base, n_here, [&](philox_stream & rng, unsigned) {
+            reg_policy<NR> pol;
+            particle<reg_policy<NR>> p(rng, pol);
+            invoke_model(model, p, oc.data(), a.n_obs);
+            const double lw = p.log_w();
+            const double w = dm::exp_weight(lw - m_ref);
+            max_lw = fmax(max_lw, lw);
+            if (!is_finite(lw)) {   // rare: keep the bookkeeping off the common path
+                n_neginf += is_neg_inf(lw) ? 1u : 0u;
+                n_nan += is_nan(lw) ? 1u : 0u;
+            }
+            s0 += w;
+            s00 = fma(w, w, s00);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                const double wx = w * pol.v[j];
+                s1[j] += wx;
+                s2[j] = fma(wx, pol.v[j], s2[j]);
+            }
+        });
+
+        double v[NV];
+        v[col::max_lw] = max_lw;
+        v[col::s0] = s0;
+        v[col::s00] = s00;
+        v[col::n_neginf] = static_cast<double>(n_neginf);
+        v[col::neg_imin] = dm::neg_inf();
+        v[col::imax] = dm::neg_inf();
+        v[col::int_oor] = 0.0;
+        v[col::n_nan] = static_cast<double>(n_nan);
+#pragma unroll
+        for (int j = 0; j < NR; ++j) { v[kBaseCols + 2 * j] = s1[j]; v[kBaseCols + 2 * j + 1] = s2[j]; }
+        const double r = block_reduce<NV>(v, kMaxColsMask, smem);
+        if (threadIdx.x < NV && threadIdx.x < a.n_cols) {
+            a.partials[static_cast<size_t>(c) * a.n_cols + threadIdx.x] = r;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 k_sis_rows: model body, SoA trace rows + logw + w written to HBM, base sums reduced.
+// The per-row estimator sums are formed afterwards by k_row_moments / k_row_hist.
+// ------------------------------------------------------------------------------------------------
+template<class Model>
+__global__ void __launch_bounds__(kBlock) k_sis_rows(const __grid_constant__ run_args a)
+{
+    __shared__ double smem[kWarps * kBaseCols];
+    __shared__ unsigned s_chunk;
+    const Model model{};
+    const double m_ref = *a.m_ref;
+    const obs_cache<Model> oc(a.obs, a.n_obs);
+
+    for (;;) {
+        const unsigned c = fetch_chunk(a.chunk_counter, &s_chunk);
+        if (c >= a.n_chunks) break;
+        const unsigned long long base = static_cast<unsigned long long>(c) * kChunk;
+        const unsigned long long left = a.n_particles - base;
+        const unsigned n_here = left < kChunk ? static_cast<unsigned>(left) : kChunk;
+
+        double max_lw = dm::neg_inf(), s0 = 0.0, s00 = 0.0;
+        unsigned n_neginf = 0, n_nan = 0, oor = 0;
+        long long imin = 0x7fffffffffffffffLL, imax = -0x7fffffffffffffffLL - 1;
+
+        for_each_owned_particle(a.keys, a.first_particle + base, n_here, [&](philox_stream & rng, unsigned i) {
+            const unsigned long long colidx = base + i;
+            row_policy pol(a.real_rows + colidx, a.int_rows + colidx, a.row_stride, a.hist_lo, a.hist_bins);
+            particle<row_policy> p(rng, pol);
+            invoke_model(model, p, oc.data(), a.n_obs);
+            const double lw = p.log_w();
+            const double w = dm::exp_weight(lw - m_ref);
+            a.logw[colidx] = lw;
+            a.w[colidx] = w;
+            max_lw = fmax(max_lw, lw);
+            if (!is_finite(lw)) {   // rare: keep the bookkeeping off the common path
+                n_neginf += is_neg_inf(lw) ? 1u : 0u;
+                n_nan += is_nan(lw) ? 1u : 0u;
+            }
+            s0 += w;
+            s00 = fma(w, w, s00);
+            oor += pol.oor;
+            imin = pol.imin < imin ? pol.imin : imin;
+            imax = pol.imax > imax ? pol.imax : imax;
+        });
+
+        double v[kBaseCols];
+        v[col::max_lw] = max_lw;
+        v[col::s0] = s0;
+        v[col::s00] = s00;
+        v[col::n_neginf] = static_cast<double>(n_neginf);
+        v[col::neg_imin] = imin <= imax ? -static_cast<double>(imin) : dm::neg_inf();
+        v[col::imax] = imin <= imax ? static_cast<double>(imax) : dm::neg_inf();
+        v[col::int_oor] = static_cast<double>(oor);
+        v[col::n_nan] = static_cast<double>(n_nan);
+        const double r = block_reduce<kBaseCols>(v, kMaxColsMask, smem);
+        if (threadIdx.x < kBaseCols) {
+            a.partials[static_cast<size_t>(c) * a.n_cols + threadIdx.x] = r;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5 k_replay: recompute log_w from a supplied SoA trace (parity gate: <= 1e-12 relative against
+// the reference/oracle log-weights).
+// ------------------------------------------------------------------------------------------------
+template<class Model>
+__global__ void __launch_bounds__(kBlock) k_replay(const double * __restrict__ obs, int n_obs,
+                                                   const double * __restrict__ real_rows, const int * __restrict__ int_rows,
+                                                   unsigned long long stride, unsigned long long n,
+                                                   double * __restrict__ logw_out)
+{
+    const Model model{};
+    const obs_cache<Model> oc(obs, n_obs);
+    const philox_keys keys(0u, 0u);   // never drawn from: every sample statement returns a recorded value
+    for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(kBlock) + threadIdx.x; i < n;
+         i += static_cast<unsigned long long>(gridDim.x) * kBlock) {
+        replay_policy pol(real_rows + i, int_rows + i, stride);
+        philox_stream rng(keys, i);
+        particle<replay_policy> p(rng, pol);
+        invoke_model(model, p, oc.data(), n_obs);
+        logw_out[i] = p.log_w();
+    }
+}
+
+}  // namespace engine
+}  // namespace cpprob
+#endif  // CPPROB_B200_SIS_KERNELS_CUH

@@ -1,0 +1,471 @@
+// cpprob-b200: device distribution layer — POD distribution types, fp64 samplers and log-pdfs.
+//
+// The reference takes its distribution *types* and *samplers* from Boost.Random (un-vendored,
+// pinned to 1.66 by CI) and supplies the log-densities itself as specialisations of
+// `cpprob::logpdf<D>` (/root/reference: include/cpprob/distributions/utils_base.hpp:27-28):
+//     normal           utils_normal_distribution.hpp:20-45
+//     uniform_real     utils_uniform_real.hpp:21-31
+//     uniform_smallint utils_uniform_smallint.hpp:17-27
+//     discrete         utils_discrete.hpp:17-27
+//     poisson          utils_poisson.hpp:17-36
+// Boost types are host-only (and Boost is absent from this image), so this header ships trivially
+// copyable types with the same accessor names (mean() sigma() a() b() min() max() probabilities()
+// result_type) that can live in registers, keeps `cpprob::logpdf<D>` as the customisation point and
+// evaluates every log-density in the reference's operation order.  gamma / beta have no reference
+// log-pdf; they follow the textbook densities in Boost's parametrisation.
+//
+// Samplers take a cpprob::philox_stream (see random/philox.hpp for the word-consumption rules).
+// The reference pins no sampler output (its RNG is seeded from random_device), so sampler parity is
+// distributional; tests/test_distributions_gpu.py checks moments / KS against scipy.
+#ifndef CPPROB_DISTRIBUTIONS_HPP
+#define CPPROB_DISTRIBUTIONS_HPP
+
+#include <cstddef>
+#include <cstdint>
+#include <initializer_list>
+#include <limits>
+
+#include "cpprob/hd.hpp"
+#include "cpprob/math/dmath.hpp"
+#include "cpprob/random/philox.hpp"
+
+namespace cpprob {
+
+// Customisation point, same name and shape as the reference's (utils_base.hpp:27-28).
+template<class Distribution> struct logpdf;
+
+// -------------------------------------------------------------------------------------------------
+// normal
+// -------------------------------------------------------------------------------------------------
+template<class RealType = double>
+class normal_distribution {
+public:
+    using result_type = RealType;
+    using input_type = RealType;
+
+    CPPROB_HD explicit normal_distribution(RealType mean = 0, RealType sigma = 1) : mean_(mean), sigma_(sigma) {}
+    CPPROB_HD RealType mean() const { return mean_; }
+    CPPROB_HD RealType sigma() const { return sigma_; }
+    CPPROB_HD RealType min() const { return -std::numeric_limits<RealType>::infinity(); }
+    CPPROB_HD RealType max() const { return std::numeric_limits<RealType>::infinity(); }
+
+    template<class Rng>
+    CPPROB_HD result_type operator()(Rng & rng) const
+    {
+        return static_cast<RealType>(rng.next_std_normal() * sigma_ + mean_);
+    }
+
+private:
+    RealType mean_, sigma_;
+};
+
+template<class RealType>
+struct logpdf<normal_distribution<RealType>> {
+    // Operation order of utils_normal_distribution.hpp:26-43 (needed for the 1e-12 replay gate).
+    CPPROB_HD RealType operator()(const normal_distribution<RealType> & distr, const RealType & x) const
+    {
+        const RealType mean = distr.mean();
+        const RealType std = distr.sigma();
+        if (std == 0) {
+            return x == mean ? RealType(0) : -std::numeric_limits<RealType>::infinity();
+        }
+        if (dm::fabs(x) == std::numeric_limits<RealType>::infinity()) {
+            return -std::numeric_limits<RealType>::infinity();
+        }
+        RealType result = (x - mean) / std;
+        result *= result;
+        result += dm::log(2 * dm::pi * std * std);
+        result *= -0.5;
+        return result;
+    }
+};
+
+// -------------------------------------------------------------------------------------------------
+// uniform_real
+// -------------------------------------------------------------------------------------------------
+template<class RealType = double>
+class uniform_real_distribution {
+public:
+    using result_type = RealType;
+    using input_type = RealType;
+
+    CPPROB_HD explicit uniform_real_distribution(RealType a = 0, RealType b = 1) : a_(a), b_(b) {}
+    CPPROB_HD RealType a() const { return a_; }
+    CPPROB_HD RealType b() const { return b_; }
+    CPPROB_HD RealType min() const { return a_; }
+    CPPROB_HD RealType max() const { return b_; }
+
+    template<class Rng>
+    CPPROB_HD result_type operator()(Rng & rng) const
+    {
+        return static_cast<RealType>(a_ + (b_ - a_) * rng.next_uniform());
+    }
+
+private:
+    RealType a_, b_;
+};
+
+template<class RealType>
+struct logpdf<uniform_real_distribution<RealType>> {
+    // utils_uniform_real.hpp:24-30
+    CPPROB_HD RealType operator()(const uniform_real_distribution<RealType> & distr, const RealType & x) const
+    {
+        if (x < distr.min() || x > distr.max()) {
+            return -std::numeric_limits<RealType>::infinity();
+        }
+        return -dm::log(distr.b() - distr.a());
+    }
+};
+
+// -------------------------------------------------------------------------------------------------
+// uniform_smallint
+// -------------------------------------------------------------------------------------------------
+template<class IntType = int>
+class uniform_smallint {
+public:
+    using result_type = IntType;
+    using input_type = IntType;
+
+    CPPROB_HD explicit uniform_smallint(IntType min = 0, IntType max = 9) : min_(min), max_(max) {}
+    CPPROB_HD IntType a() const { return min_; }
+    CPPROB_HD IntType b() const { return max_; }
+    CPPROB_HD IntType min() const { return min_; }
+    CPPROB_HD IntType max() const { return max_; }
+
+    template<class Rng>
+    CPPROB_HD result_type operator()(Rng & rng) const
+    {
+        // "small" range: one 32-bit word, multiply-shift (bias <= range * 2^-32, as for Boost's
+        // uniform_smallint, which is documented as only approximately uniform).
+        const std::uint32_t range = static_cast<std::uint32_t>(max_ - min_) + 1u;
+        const std::uint64_t prod = static_cast<std::uint64_t>(rng.next_u32()) * range;
+        return static_cast<IntType>(min_ + static_cast<IntType>(prod >> 32));
+    }
+
+private:
+    IntType min_, max_;
+};
+
+template<class IntType>
+struct logpdf<uniform_smallint<IntType>> {
+    // utils_uniform_smallint.hpp:20-26 (returns double whatever IntType is)
+    CPPROB_HD double operator()(const uniform_smallint<IntType> & distr, const IntType & x) const
+    {
+        if (x < distr.min() || x > distr.max()) {
+            return -std::numeric_limits<double>::infinity();
+        }
+        return -dm::log(distr.max() - distr.min() + 1.0);
+    }
+};
+
+// -------------------------------------------------------------------------------------------------
+// discrete (weights held inline, capacity MaxK; normalised on construction like Boost's)
+// -------------------------------------------------------------------------------------------------
+template<class WeightType, int MaxK>
+struct probability_array {
+    WeightType p[MaxK];
+    int n;
+    CPPROB_HD int size() const { return n; }
+    CPPROB_HD WeightType operator[](std::size_t i) const { return p[i]; }
+    CPPROB_HD const WeightType * begin() const { return p; }
+    CPPROB_HD const WeightType * end() const { return p + n; }
+};
+
+template<class IntType = int, class WeightType = double, int MaxK = 8>
+class discrete_distribution {
+public:
+    using result_type = IntType;
+    using input_type = WeightType;
+    static constexpr int capacity = MaxK;
+
+    CPPROB_HD discrete_distribution() { probs_.n = 1; probs_.p[0] = 1; for (int i = 1; i < MaxK; ++i) probs_.p[i] = 0; }
+
+    template<class Iter>
+    CPPROB_HD discrete_distribution(Iter first, Iter last) { init(first, last); }
+
+    CPPROB_HD discrete_distribution(std::initializer_list<WeightType> w) { init(w.begin(), w.end()); }
+
+    CPPROB_HD IntType min() const { return 0; }
+    CPPROB_HD IntType max() const { return static_cast<IntType>(probs_.n - 1); }
+    CPPROB_HD const probability_array<WeightType, MaxK> & probabilities() const { return probs_; }
+
+    template<class Rng>
+    CPPROB_HD result_type operator()(Rng & rng) const
+    {
+        // inverse CDF by linear scan; u in (0,1) with 32 random bits
+        const WeightType u = (static_cast<WeightType>(rng.next_u32()) + WeightType(0.5)) * WeightType(2.3283064365386962890625e-10);
+        WeightType acc = 0;
+        int r = probs_.n - 1;
+        bool found = false;   // the smallest i with u < p0 + ... + p_i wins
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int i = 0; i < MaxK; ++i) {
+            if (i < probs_.n - 1) {
+                acc += probs_.p[i];
+                if (!found && u < acc) { r = i; found = true; }
+            }
+        }
+        return static_cast<IntType>(r);
+    }
+
+private:
+    template<class Iter>
+    CPPROB_HD void init(Iter first, Iter last)
+    {
+        int n = 0;
+        WeightType sum = 0;
+        for (; first != last && n < MaxK; ++first, ++n) {
+            probs_.p[n] = *first;
+            sum += probs_.p[n];
+        }
+        probs_.n = n;
+        for (int i = 0; i < MaxK; ++i) {
+            probs_.p[i] = i < n ? probs_.p[i] / sum : WeightType(0);
+        }
+    }
+
+    probability_array<WeightType, MaxK> probs_;
+};
+
+template<class IntType, class WeightType, int MaxK>
+struct logpdf<discrete_distribution<IntType, WeightType, MaxK>> {
+    // utils_discrete.hpp:20-26
+    CPPROB_HD WeightType operator()(const discrete_distribution<IntType, WeightType, MaxK> & distr, const IntType & x) const
+    {
+        if (x < distr.min() || x > distr.max()) {
+            return -std::numeric_limits<WeightType>::infinity();
+        }
+        // select instead of a dynamically indexed register array
+        WeightType p = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int i = 0; i < MaxK; ++i) {
+            if (static_cast<IntType>(i) == x) p = distr.probabilities().p[i];
+        }
+        return dm::log(p);
+    }
+};
+
+// -------------------------------------------------------------------------------------------------
+// categorical: non-owning view of K probabilities (e.g. one row of a transition matrix).  Not in the
+// reference; north_star lists it next to `discrete`.  Probabilities are used as given (no
+// normalisation); log-pdf follows the discrete rule.
+// -------------------------------------------------------------------------------------------------
+template<class IntType = int, class WeightType = double>
+class categorical_distribution {
+public:
+    using result_type = IntType;
+    using input_type = WeightType;
+
+    CPPROB_HD categorical_distribution(const WeightType * probs, int k) : probs_(probs), k_(k) {}
+    CPPROB_HD IntType min() const { return 0; }
+    CPPROB_HD IntType max() const { return static_cast<IntType>(k_ - 1); }
+    CPPROB_HD const WeightType * probabilities() const { return probs_; }
+    CPPROB_HD int size() const { return k_; }
+
+    template<class Rng>
+    CPPROB_HD result_type operator()(Rng & rng) const
+    {
+        const WeightType u = (static_cast<WeightType>(rng.next_u32()) + WeightType(0.5)) * WeightType(2.3283064365386962890625e-10);
+        WeightType acc = 0;
+        int r = k_ - 1;
+        for (int i = 0; i < k_ - 1; ++i) {
+            acc += probs_[i];
+            if (u < acc) { r = i; break; }
+        }
+        return static_cast<IntType>(r);
+    }
+
+private:
+    const WeightType * probs_;
+    int k_;
+};
+
+template<class IntType, class WeightType>
+struct logpdf<categorical_distribution<IntType, WeightType>> {
+    CPPROB_HD WeightType operator()(const categorical_distribution<IntType, WeightType> & distr, const IntType & x) const
+    {
+        if (x < distr.min() || x > distr.max()) {
+            return -std::numeric_limits<WeightType>::infinity();
+        }
+        return dm::log(distr.probabilities()[static_cast<std::size_t>(x)]);
+    }
+};
+
+// -------------------------------------------------------------------------------------------------
+// poisson
+// -------------------------------------------------------------------------------------------------
+template<class IntType = int, class RealType = double>
+class poisson_distribution {
+public:
+    using result_type = IntType;
+    using input_type = RealType;
+
+    CPPROB_HD explicit poisson_distribution(RealType mean = 1) : mean_(mean) {}
+    CPPROB_HD RealType mean() const { return mean_; }
+    CPPROB_HD IntType min() const { return 0; }
+    CPPROB_HD IntType max() const { return std::numeric_limits<IntType>::max(); }
+
+    template<class Rng>
+    CPPROB_HD result_type operator()(Rng & rng) const
+    {
+        if (mean_ < RealType(10)) {
+            // inversion by sequential search on the CDF
+            const RealType u = rng.next_uniform();
+            RealType p = dm::exp(-mean_);
+            RealType F = p;
+            IntType x = 0;
+            while (u > F && x < 1000) {
+                ++x;
+                p *= mean_ / static_cast<RealType>(x);
+                F += p;
+            }
+            return x;
+        }
+        // PTRS, transformed rejection with squeeze (W. Hoermann 1993), valid for mean >= 10
+        const RealType slam = dm::sqrt(mean_);
+        const RealType loglam = dm::log(mean_);
+        const RealType b = RealType(0.931) + RealType(2.53) * slam;
+        const RealType a = RealType(-0.059) + RealType(0.02483) * b;
+        const RealType inv_alpha = RealType(1.1239) + RealType(1.1328) / (b - RealType(3.4));
+        const RealType vr = RealType(0.9277) - RealType(3.6224) / (b - RealType(2));
+        for (int it = 0; it < 1000; ++it) {
+            const RealType U = rng.next_uniform() - RealType(0.5);
+            const RealType V = rng.next_uniform();
+            const RealType us = RealType(0.5) - dm::fabs(U);
+            const RealType kf = dm::floor((RealType(2) * a / us + b) * U + mean_ + RealType(0.43));
+            if (us >= RealType(0.07) && V <= vr) return static_cast<IntType>(kf);
+            if (kf < 0 || (us < RealType(0.013) && V > us)) continue;
+            if (dm::log(V) + dm::log(inv_alpha) - dm::log(a / (us * us) + b)
+                <= -mean_ + kf * loglam - dm::lgamma(kf + RealType(1))) {
+                return static_cast<IntType>(kf);
+            }
+        }
+        return static_cast<IntType>(mean_);
+    }
+
+private:
+    RealType mean_;
+};
+
+template<class IntType, class RealType>
+struct logpdf<poisson_distribution<IntType, RealType>> {
+    // utils_poisson.hpp:20-35: explicit sum of logs, not lgamma
+    CPPROB_HD RealType operator()(const poisson_distribution<IntType, RealType> & distr, const IntType & x) const
+    {
+        const RealType l = distr.mean();
+        if (l == RealType(0)) {
+            return -std::numeric_limits<RealType>::infinity();
+        }
+        RealType ret = x * dm::log(l) - l;
+        for (int i = 1; i <= x; ++i) {
+            ret -= dm::log(static_cast<RealType>(i));
+        }
+        return ret;
+    }
+};
+
+// -------------------------------------------------------------------------------------------------
+// gamma (shape alpha, scale beta — Boost.Random's parametrisation)
+// -------------------------------------------------------------------------------------------------
+template<class RealType = double>
+class gamma_distribution {
+public:
+    using result_type = RealType;
+    using input_type = RealType;
+
+    CPPROB_HD explicit gamma_distribution(RealType alpha = 1, RealType beta = 1) : alpha_(alpha), beta_(beta) {}
+    CPPROB_HD RealType alpha() const { return alpha_; }
+    CPPROB_HD RealType beta() const { return beta_; }
+    CPPROB_HD RealType min() const { return 0; }
+    CPPROB_HD RealType max() const { return std::numeric_limits<RealType>::infinity(); }
+
+    template<class Rng>
+    CPPROB_HD result_type operator()(Rng & rng) const
+    {
+        // Marsaglia & Tsang (2000); shape < 1 boosted with U^(1/alpha)
+        const bool small = alpha_ < RealType(1);
+        const RealType a = small ? alpha_ + RealType(1) : alpha_;
+        const RealType d = a - RealType(1) / RealType(3);
+        const RealType c = RealType(1) / dm::sqrt(RealType(9) * d);
+        RealType g = d;
+        for (int it = 0; it < 1000; ++it) {
+            const RealType x = rng.next_std_normal();
+            RealType v = RealType(1) + c * x;
+            if (v <= RealType(0)) continue;
+            v = v * v * v;
+            const RealType u = rng.next_uniform();
+            if (dm::log(u) < RealType(0.5) * x * x + d - d * v + d * dm::log(v)) { g = d * v; break; }
+        }
+        if (small) {
+            g *= dm::pow(rng.next_uniform(), RealType(1) / alpha_);
+        }
+        return g * beta_;
+    }
+
+private:
+    RealType alpha_, beta_;
+};
+
+template<class RealType>
+struct logpdf<gamma_distribution<RealType>> {
+    CPPROB_HD RealType operator()(const gamma_distribution<RealType> & distr, const RealType & x) const
+    {
+        const RealType k = distr.alpha();
+        const RealType theta = distr.beta();
+        if (x < RealType(0)) return -std::numeric_limits<RealType>::infinity();
+        if (x == RealType(0)) {
+            if (k == RealType(1)) return -dm::log(theta);
+            return k < RealType(1) ? std::numeric_limits<RealType>::infinity()
+                                   : -std::numeric_limits<RealType>::infinity();
+        }
+        return (k - RealType(1)) * dm::log(x) - x / theta - dm::lgamma(k) - k * dm::log(theta);
+    }
+};
+
+// -------------------------------------------------------------------------------------------------
+// beta
+// -------------------------------------------------------------------------------------------------
+template<class RealType = double>
+class beta_distribution {
+public:
+    using result_type = RealType;
+    using input_type = RealType;
+
+    CPPROB_HD explicit beta_distribution(RealType alpha = 1, RealType beta = 1) : alpha_(alpha), beta_(beta) {}
+    CPPROB_HD RealType alpha() const { return alpha_; }
+    CPPROB_HD RealType beta() const { return beta_; }
+    CPPROB_HD RealType min() const { return 0; }
+    CPPROB_HD RealType max() const { return 1; }
+
+    template<class Rng>
+    CPPROB_HD result_type operator()(Rng & rng) const
+    {
+        const RealType x = gamma_distribution<RealType>(alpha_, 1)(rng);
+        const RealType y = gamma_distribution<RealType>(beta_, 1)(rng);
+        return x / (x + y);
+    }
+
+private:
+    RealType alpha_, beta_;
+};
+
+template<class RealType>
+struct logpdf<beta_distribution<RealType>> {
+    CPPROB_HD RealType operator()(const beta_distribution<RealType> & distr, const RealType & x) const
+    {
+        const RealType a = distr.alpha();
+        const RealType b = distr.beta();
+        if (x < RealType(0) || x > RealType(1)) return -std::numeric_limits<RealType>::infinity();
+        const RealType log_b = dm::lgamma(a) + dm::lgamma(b) - dm::lgamma(a + b);
+        // xlogy-style edges: 0 * log 0 = 0
+        const RealType t1 = (a == RealType(1)) ? RealType(0) : (a - RealType(1)) * dm::log(x);
+        const RealType t2 = (b == RealType(1)) ? RealType(0) : (b - RealType(1)) * dm::log(RealType(1) - x);
+        return t1 + t2 - log_b;
+    }
+};
+
+}  // namespace cpprob
+#endif  // CPPROB_DISTRIBUTIONS_HPP

@@ -1,0 +1,270 @@
+// cpprob-b200: fp64 elementary functions used by the samplers, log-pdfs and the weight reduction.
+//
+// On the device the hot ones (log of a unit-interval uniform, sqrt, sin/cos of 2*pi*u, exp of a
+// shifted log-weight) are branch-free DFMA chains: the SIS kernels are bound by the FP64 pipe
+// (64 lanes/SM, one warp instruction per 2 cycles per SM sub-partition), so every instruction that
+// is not an FP64-pipe instruction competes with it only for issue slots, and every FP64 instruction
+// that can be avoided is time saved.  Polynomial coefficients are near-minimax (tools/gen_poly.py)
+// and live in __constant__ memory so that they reach the DFMAs as uniform-register operands instead
+// of two immediate moves each.  Everything has a host twin (libm) used only by the structure probe /
+// dry run.
+//
+// Accuracy (checked on the GPU in tests/test_dmath_gpu.py against numpy/mpmath):
+//   log_unit, log     <= 2 ulp
+//   sqrt_pos          <= 1 ulp (Newton from the hardware seed + exact residual step)
+//   sincos_2pi, cos_2pi  abs error <= 2^-52
+//   exp_weight        <= 2 ulp on (-708, 708); exactly 0 at or below -708 (and for -inf); +inf at or above 708
+#ifndef CPPROB_MATH_DMATH_HPP
+#define CPPROB_MATH_DMATH_HPP
+
+#include <cmath>
+#include <cstdint>
+#include <limits>
+
+#include "cpprob/hd.hpp"
+
+namespace cpprob {
+namespace dm {
+
+constexpr double pi      = 3.141592653589793238462643383279502884;
+constexpr double two_pi  = 6.283185307179586476925286766559005768;
+
+CPPROB_HD double neg_inf() { return -std::numeric_limits<double>::infinity(); }
+
+#if defined(__CUDACC__)
+namespace tbl {
+// atanh(s)/s = 1 + z*P(z), z = s^2 <= 0.02944; degree 6, error 2^-57.6 (gen_poly.py "LOG_P")
+static __constant__ double log_p[7] = {
+    0x1.5555555555558p-2, 0x1.99999999952e2p-3, 0x1.2492492df148dp-3, 0x1.c71c62e5800a1p-4,
+    0x1.7462b4ab2ef6bp-4, 0x1.39fe606542ddep-4, 0x1.2b584aae78a57p-4};
+// exp(r) = 1 + r + r^2 Q(r), |r| <= ln2/2; degree 9, error 2^-56 (gen_poly.py "EXP_Q")
+static __constant__ double exp_q[10] = {
+    0x1.0000000000001p-1, 0x1.5555555555556p-3, 0x1.5555555553d63p-5, 0x1.11111111109b3p-7,
+    0x1.6c16c1788bd90p-10, 0x1.a01a01a7c41d5p-13, 0x1.a019b90d2ae7ap-16, 0x1.71de0dae63bb3p-19,
+    0x1.289185613a3d6p-22, 0x1.af38a9b0ec855p-26};
+// sinpi(r) = r*pi + r*z*S(z), cospi(r) = 1 + z*C(z), z = r^2, |r| <= 1/4 (gen_poly.py)
+// laid out as pairs {S_i, C_i}, S padded with a zero top coefficient, so one Horner chain serves both
+static __constant__ double sincos_sc[7][2] = {
+    {-0x1.4abbce625be52p+2, -0x1.3bd3cc9be45dep+2},
+    {0x1.466bc6775a476p+1, 0x1.03c1f081b5ac0p+2},
+    {-0x1.32d2cce500387p-1, -0x1.55d3c7e3cb241p+0},
+    {0x1.50783208843ebp-4, 0x1.e1f5068688d5bp-3},
+    {-0x1.e3027dea82bd7p-8, -0x1.a6d1eef479be1p-6},
+    {0x1.e4a9d9166f052p-12, 0x1.f9ce245cada0bp-10},
+    {0.0, -0x1.b2f3eb054afcdp-14}};
+// scalar constants, kept next to the tables so that they too arrive as uniform-register operands
+static __constant__ double k_ln2_hi = 6.93147180369123816490e-01;   // 32 trailing zero bits: e*ln2_hi exact
+static __constant__ double k_ln2_lo = 1.90821492927058770002e-10;
+static __constant__ double k_log2e = 1.4426950408889634074;
+static __constant__ double k_round_magic = 6755399441055744.0;      // 2^52 + 2^51: x + magic rounds x to an integer
+static __constant__ double k_pi = 3.141592653589793238462643383279502884;
+}  // namespace tbl
+#endif
+
+#if CPPROB_ON_DEVICE
+// ---------------------------------------------------------------------------------------------
+// Device implementations.
+// ---------------------------------------------------------------------------------------------
+namespace detail {
+
+// log(m) + e*ln2 given s = (m-1)/(m+1)
+__device__ __forceinline__ double log_tail(double s, int e)
+{
+    const double z = s * s;
+    double p = tbl::log_p[6];
+    p = fma(p, z, tbl::log_p[5]);
+    p = fma(p, z, tbl::log_p[4]);
+    p = fma(p, z, tbl::log_p[3]);
+    p = fma(p, z, tbl::log_p[2]);
+    p = fma(p, z, tbl::log_p[1]);
+    p = fma(p, z, tbl::log_p[0]);
+    const double s2 = s + s;
+    const double t = s2 * z;
+    const double de = static_cast<double>(e);
+    const double inner = fma(t, p, fma(de, tbl::k_ln2_lo, s2));
+    return fma(de, tbl::k_ln2_hi, inner);
+}
+}  // namespace detail
+
+// Natural log of a normal, finite, positive argument (no zero / denormal / inf / nan handling):
+// the sampler's log of a unit-interval uniform.  m in [sqrt(1/2), sqrt(2)), log x = e ln2 + 2 atanh(s).
+__device__ __forceinline__ double log_unit(double x)
+{
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    const int e = (hi - 0x3FE6A09F) >> 20;          // arithmetic shift = floor
+    hi -= e << 20;
+    const double m = __hiloint2double(hi, lo);
+    const double num = m - 1.0;
+    const double den = m + 1.0;
+    // 1/den, den in [1.7, 2.42): hardware seed on the high word (~2^-20) + 2 Newton steps
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
+    double t = fma(-den, y, 1.0);
+    y = fma(y, t, y);
+    t = fma(-den, y, 1.0);
+    y = fma(y, t, y);
+    double s = num * y;
+    s = fma(fma(-den, s, num), y, s);               // residual step: s = num/den to < 1 ulp
+    return detail::log_tail(s, e);
+}
+
+// General natural log, IEEE special cases included, written without opaque intrinsics so that the
+// compiler folds it for constant arguments and hoists it for loop-invariant ones (the log-pdf
+// normalisers: log(2 pi sigma^2), log(b-a), log(lambda) ...).
+__device__ __forceinline__ double log(double x)
+{
+    const bool tiny = x < 2.2250738585072014e-308;                 // denormal, zero or negative
+    const double xs = tiny ? x * 18014398509481984.0 : x;          // * 2^54
+    long long bits = __double_as_longlong(xs);
+    int hi = static_cast<int>(bits >> 32);
+    const int e = (hi - 0x3FE6A09F) >> 20;
+    hi -= e << 20;
+    bits = (static_cast<long long>(hi) << 32) | (bits & 0xffffffffLL);
+    const double m = __longlong_as_double(bits);
+    const double s = (m - 1.0) / (m + 1.0);
+    double r = detail::log_tail(s, tiny ? e - 54 : e);
+    r = (x == 0.0) ? neg_inf() : r;
+    r = (x < 0.0) ? __longlong_as_double(0x7ff8000000000000LL) : r;
+    r = (x == std::numeric_limits<double>::infinity()) ? x : r;
+    r = (x != x) ? x : r;
+    return r;
+}
+
+// sqrt of a positive normal number (no zero / denormal / inf / negative handling).
+__device__ __forceinline__ double sqrt_pos(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));        // ~2^-20 on the high word
+    const double e = fma(x, -(y * y), 1.0);
+    const double p = fma(e, 0.375, 0.5);
+    y = fma(p, y * e, y);                                           // third-order step: ~2^-58
+    const double g = x * y;
+    const double h = 0.5 * y;
+    return fma(fma(g, -g, x), h, g);                                // exact-residual correction
+}
+
+__device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+
+namespace detail {
+// quarter-turn reduction of the angle 2*pi*u, u in [0,1]: k = rint(4u) in {0..4}, r in [-1/4, 1/4]
+// with 2*pi*u = (pi/2) k + pi r.  Both steps are exact.
+__device__ __forceinline__ void reduce_2pi(double u, int & k, double & r)
+{
+    const double magic = tbl::k_round_magic;
+    const double km = fma(u, 4.0, magic);
+    k = __double2loint(km);
+    const double kf = km - magic;
+    r = fma(kf, -0.5, u + u);
+}
+}  // namespace detail
+
+// sin(2*pi*u) and cos(2*pi*u), u in [0,1].
+__device__ __forceinline__ void sincos_2pi(double u, double & s, double & c)
+{
+    int k;
+    double r;
+    detail::reduce_2pi(u, k, r);
+    const double z = r * r;
+    double ps = tbl::sincos_sc[5][0], pc = tbl::sincos_sc[6][1];
+    pc = fma(pc, z, tbl::sincos_sc[5][1]);
+#pragma unroll
+    for (int i = 4; i >= 0; --i) {
+        ps = fma(ps, z, tbl::sincos_sc[i][0]);
+        pc = fma(pc, z, tbl::sincos_sc[i][1]);
+    }
+    const double sv = fma(r * z, ps, r * tbl::k_pi);
+    const double cv = fma(z, pc, 1.0);
+    // k: 0 -> (s, c) = (sv, cv); 1 -> (cv, -sv); 2 -> (-sv, -cv); 3 -> (-cv, sv); 4 == 0
+    double so = (k & 1) ? cv : sv;
+    double co = (k & 1) ? sv : cv;
+    const int s_neg = (k >> 1) & 1;
+    const int c_neg = ((k + 1) >> 1) & 1;
+    so = __hiloint2double(__double2hiint(so) ^ (s_neg << 31), __double2loint(so));
+    co = __hiloint2double(__double2hiint(co) ^ (c_neg << 31), __double2loint(co));
+    s = so;
+    c = co;
+}
+
+// One of sin / cos of 2*pi*u through a single Horner chain with per-lane selected coefficients:
+// the selects go to the ALU pipe, the FP64 pipe sees one polynomial instead of two.
+template<bool WantCos>
+__device__ __forceinline__ double sin_or_cos_2pi(double u)
+{
+    int k;
+    double r;
+    detail::reduce_2pi(u, k, r);
+    const double z = r * r;
+    const bool use_cos_poly = WantCos ? !(k & 1) : (k & 1);
+    const int neg = WantCos ? (((k + 1) >> 1) & 1) : ((k >> 1) & 1);
+    double p = use_cos_poly ? tbl::sincos_sc[6][1] : tbl::sincos_sc[6][0];
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        const double ci = use_cos_poly ? tbl::sincos_sc[i][1] : tbl::sincos_sc[i][0];
+        p = fma(p, z, ci);
+    }
+    const double head = use_cos_poly ? 1.0 : r * tbl::k_pi;
+    const double tail = use_cos_poly ? z : r * z;
+    const double v = fma(tail, p, head);
+    return __hiloint2double(__double2hiint(v) ^ (neg << 31), __double2loint(v));
+}
+__device__ __forceinline__ double cos_2pi(double u) { return sin_or_cos_2pi<true>(u); }
+__device__ __forceinline__ double sin_2pi(double u) { return sin_or_cos_2pi<false>(u); }
+
+__device__ __forceinline__ double exp(double x) { return ::exp(x); }
+
+// exp(log_w - m_ref).  Anything at or below -708 (including -inf) gives exactly 0, anything at or
+// above 708 gives +inf, NaN gives NaN.  The range test is done on the bit pattern (ALU pipe); inside
+// (-708, 708) the result is a normal number and 2^k is applied through the exponent field.
+__device__ __forceinline__ double exp_weight(double x)
+{
+    const double magic = tbl::k_round_magic;
+    const double t = fma(x, tbl::k_log2e, magic);
+    const int k = __double2loint(t);
+    const double kf = t - magic;
+    double r = fma(kf, -tbl::k_ln2_hi, x);
+    r = fma(kf, -tbl::k_ln2_lo, r);
+    double q = tbl::exp_q[9];
+#pragma unroll
+    for (int i = 8; i >= 0; --i) q = fma(q, r, tbl::exp_q[i]);
+    const double e = fma(r * r, q, r) + 1.0;                        // in [0.70, 1.42]
+    const int hi = __double2hiint(e) + (k << 20);
+    double w = __hiloint2double(hi, __double2loint(e));
+    const int xhi = __double2hiint(x);
+    if ((static_cast<unsigned>(xhi) & 0x7FFFFFFFu) >= 0x40862000u) {  // |x| >= 708, inf or nan: rare
+        w = (x != x) ? x : (xhi < 0 ? 0.0 : std::numeric_limits<double>::infinity());
+    }
+    return w;
+}
+
+__device__ __forceinline__ double lgamma(double x) { return ::lgamma(x); }
+__device__ __forceinline__ double pow(double a, double b) { return ::pow(a, b); }
+__device__ __forceinline__ double floor(double x) { return ::floor(x); }
+__device__ __forceinline__ double fabs(double x) { return ::fabs(x); }
+
+#else
+// ---------------------------------------------------------------------------------------------
+// Host twins (structure probe / dry run only).
+// ---------------------------------------------------------------------------------------------
+inline double log_unit(double u) { return std::log(u); }
+inline double log(double x) { return std::log(x); }
+inline double sqrt_pos(double x) { return std::sqrt(x); }
+inline double sqrt(double x) { return std::sqrt(x); }
+inline void sincos_2pi(double u, double & s, double & c)
+{
+    s = std::sin(two_pi * u);
+    c = std::cos(two_pi * u);
+}
+inline double cos_2pi(double u) { return std::cos(two_pi * u); }
+inline double sin_2pi(double u) { return std::sin(two_pi * u); }
+inline double exp(double x) { return std::exp(x); }
+inline double exp_weight(double x) { return x != x ? 0.0 : std::exp(x); }
+inline double lgamma(double x) { return std::lgamma(x); }
+inline double pow(double a, double b) { return std::pow(a, b); }
+inline double floor(double x) { return std::floor(x); }
+inline double fabs(double x) { return std::fabs(x); }
+#endif
+
+}  // namespace dm
+}  // namespace cpprob
+#endif  // CPPROB_MATH_DMATH_HPP

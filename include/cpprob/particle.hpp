@@ -1,0 +1,223 @@
+// cpprob-b200: the per-particle execution context — what `sample`, `observe` and `predict` act on.
+//
+// In the reference the three statements are free function templates that mutate process-global
+// statics (/root/reference: include/cpprob/cpprob.hpp:68-76 sample, :79-90 observe, :92-98 predict;
+// state behind them in src/cpprob/state.cpp:188-223 and include/cpprob/state.hpp:312-349).  Device
+// code has no such statics, so a model is a functor whose first parameter is a `particle<Policy>&`
+// and the statements are calls on it:
+//
+//     struct my_model {
+//         template<class P> CPPROB_HD void operator()(P & cpprob, double x1, double x2) const {
+//             cpprob::normal_distribution<> prior{1, 1.5};
+//             const double mu = cpprob.sample(prior, true);          // was cpprob::sample(prior, true)
+//             cpprob.observe(cpprob::normal_distribution<>{mu, 2}, x1);
+//             cpprob.predict(mu, "Mean");
+//         }
+//     };
+//
+// (free-function spellings cpprob::sample(p, d, control) etc. are provided too).  SIS semantics are
+// the reference's: sample = prior draw, adds nothing to log_w (cpprob.hpp:72-74); observe =
+// `log_w += logpdf<D>()(d, x)` accumulated in program order from 0.0 (cpprob.hpp:87-89,
+// state.cpp:221, trace.hpp:59); predict = record (address id, value), integral values and floating
+// values routed to separate record lists (state.hpp:312-326).
+//
+// The Policy decides where sampled values come from and where predicted values go; the engine
+// instantiates each model with the policies in cpprob_b200/csrc/sis_kernels.cuh (register staging,
+// SoA rows in HBM, replay from SoA rows) and, on the host, with `probe_policy` below.
+#ifndef CPPROB_PARTICLE_HPP
+#define CPPROB_PARTICLE_HPP
+
+#include <cstddef>
+#include <cstdint>
+#include <type_traits>
+#include <utility>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "cpprob/hd.hpp"
+#include "cpprob/distributions/distributions.hpp"
+#include "cpprob/random/philox.hpp"
+
+namespace cpprob {
+
+// View of the observation array handed to array-style models (`std::array<double, N>` in the
+// reference, models.hpp:67-68,114-115; here N is a run-time value).
+template<class T>
+struct obs_span {
+    const T * ptr;
+    int n;
+    CPPROB_HD const T * begin() const { return ptr; }
+    CPPROB_HD const T * end() const { return ptr + n; }
+    CPPROB_HD int size() const { return n; }
+    CPPROB_HD const T & operator[](int i) const { return ptr[i]; }
+};
+
+template<class Policy>
+class particle {
+public:
+    // `rng` is the stream this particle draws from; the two particles of a stream pair are run one
+    // after the other on the same stream object (random/philox.hpp, "particle -> stream map").
+    CPPROB_HD particle(philox_stream & rng, Policy & policy) : rng_(rng), log_w_(0.0), policy_(policy) {}
+
+    // cpprob::sample(distr, control) — cpprob.hpp:68-76.  `control` is accepted and, as in the
+    // reference's SIS branch (:72), has no effect.
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+    template<class Distribution>
+    CPPROB_HD typename Distribution::result_type sample(const Distribution & distr, bool control = false)
+    {
+        (void)control;
+        return policy_.sample(distr, rng_);
+    }
+
+    // cpprob::sample(distr, control, address) — cpprob.hpp:28-35; the address is unused in SIS.
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+    template<class Distribution, class String>
+    CPPROB_HD typename Distribution::result_type sample(const Distribution & distr, bool control, const String &)
+    {
+        (void)control;
+        return policy_.sample(distr, rng_);
+    }
+
+    // cpprob::observe(distr, x) — cpprob.hpp:79-90 -> StateInfer::increment_log_prob, state.cpp:221.
+    template<class Distribution>
+    CPPROB_HD void observe(const Distribution & distr, const typename Distribution::result_type & x)
+    {
+        log_w_ += logpdf<Distribution>()(distr, x);
+    }
+
+    // cpprob::predict(x, addr) — cpprob.hpp:92-98 -> StateInfer::add_predict, state.hpp:312-326.
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+    template<class T, class String,
+             typename std::enable_if<std::is_integral<T>::value, int>::type = 0>
+    CPPROB_HD void predict(T x, const String & addr)
+    {
+        policy_.predict_int(static_cast<long long>(x), addr);
+    }
+
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+    template<class T, class String,
+             typename std::enable_if<std::is_floating_point<T>::value, int>::type = 0>
+    CPPROB_HD void predict(T x, const String & addr)
+    {
+        policy_.predict_real(static_cast<double>(x), addr);
+    }
+
+    CPPROB_HD double log_w() const { return log_w_; }
+    CPPROB_HD philox_stream & rng() { return rng_; }
+
+private:
+    philox_stream & rng_;
+    double log_w_;
+    Policy & policy_;
+};
+
+// Free-function spellings.
+template<class P, class D>
+CPPROB_HD typename D::result_type sample(particle<P> & p, const D & d, bool control = false) { return p.sample(d, control); }
+template<class P, class D>
+CPPROB_HD void observe(particle<P> & p, const D & d, const typename D::result_type & x) { p.observe(d, x); }
+template<class P, class T, class S>
+CPPROB_HD void predict(particle<P> & p, T x, const S & addr) { p.predict(x, addr); }
+
+// -------------------------------------------------------------------------------------------------
+// Model invocation: unpack the observation array the way call_f_tuple does for the observation
+// tuple (/root/reference: include/cpprob/call_function.hpp:56-65,75-80).
+//   Model::n_scalar_obs >= 0 : f(p, obs[0], ..., obs[n-1])      (e.g. gaussian_unknown_mean(x1, x2))
+//   Model::n_scalar_obs == -1: f(p, obs_span<double>{obs, n})   (e.g. hmm<N>, linear_gaussian_1d<N>)
+// -------------------------------------------------------------------------------------------------
+namespace detail {
+template<class Model, class P, std::size_t... I>
+CPPROB_HD void invoke_scalars(const Model & m, P & p, const double * obs, std::index_sequence<I...>)
+{
+    m(p, obs[I]...);
+}
+template<class Model, class P>
+CPPROB_HD void invoke_model_impl(const Model & m, P & p, const double * obs, int, std::true_type /*scalars*/)
+{
+    invoke_scalars(m, p, obs, std::make_index_sequence<static_cast<std::size_t>(Model::n_scalar_obs)>());
+}
+template<class Model, class P>
+CPPROB_HD void invoke_model_impl(const Model & m, P & p, const double * obs, int n, std::false_type)
+{
+    m(p, obs_span<double>{obs, n});
+}
+}  // namespace detail
+
+template<class Model, class P>
+CPPROB_HD void invoke_model(const Model & m, P & p, const double * obs, int n_obs)
+{
+    detail::invoke_model_impl(m, p, obs, n_obs, std::integral_constant<bool, (Model::n_scalar_obs >= 0)>());
+}
+
+// -------------------------------------------------------------------------------------------------
+// Host-side structure probe: one execution of the model that records, in program order, the kind
+// and address of every predict statement.  Address ids are handed out in first-seen order exactly
+// like TraceInfer::register_addr_predict (/root/reference: include/cpprob/trace.hpp:37-41).
+// The engine uses the result to lay out the SoA trace rows and to write `<out>.ids`.
+// -------------------------------------------------------------------------------------------------
+struct predict_slot {
+    bool is_int;          // routed to the .int (true) or .real (false) record list
+    std::size_t id;       // address id
+    std::size_t k;        // occurrence index of this id within the trace (StatsPrinter key)
+    std::size_t row;      // row index inside the int / real SoA block
+};
+
+struct model_structure {
+    std::vector<std::string> ids;          // address strings, index = id
+    std::vector<predict_slot> slots;       // program order
+    std::size_t n_real = 0, n_int = 0;     // number of real / int predict statements per trace
+    std::size_t n_samples = 0;             // number of sample statements per trace
+};
+
+class probe_policy {
+public:
+    explicit probe_policy(model_structure & out) : out_(out) {}
+
+    template<class D>
+    typename D::result_type sample(const D & d, philox_stream & rng)
+    {
+        ++out_.n_samples;
+        return d(rng);
+    }
+    template<class S> void predict_int(long long, const S & addr) { add(true, std::string(addr)); }
+    template<class S> void predict_real(double, const S & addr) { add(false, std::string(addr)); }
+
+private:
+    void add(bool is_int, std::string addr)
+    {
+        auto it = index_.emplace(addr, out_.ids.size());
+        if (it.second) out_.ids.push_back(addr);
+        const std::size_t id = it.first->second;
+        std::size_t k = 0;
+        for (const auto & s : out_.slots) if (s.id == id) ++k;
+        const std::size_t row = is_int ? out_.n_int++ : out_.n_real++;
+        out_.slots.push_back(predict_slot{is_int, id, k, row});
+    }
+
+    model_structure & out_;
+    std::unordered_map<std::string, std::size_t> index_;
+};
+
+template<class Model>
+model_structure probe_model(const Model & m, const double * obs, int n_obs, std::uint64_t seed = 0)
+{
+    model_structure st;
+    probe_policy pol(st);
+    const philox_keys keys(seed);
+    philox_stream rng(keys, 0);
+    particle<probe_policy> p(rng, pol);
+    invoke_model(m, p, obs, n_obs);
+    return st;
+}
+}  // namespace cpprob
+#endif  // CPPROB_PARTICLE_HPP

@@ -1,0 +1,220 @@
+/* cpprob-b200: C ABI of the B200 sequential-importance-sampling engine (libcpprob_sis.so).
+ *
+ * CPProb has no FFI of its own: its boundary for this path is the header-only C++ template API
+ * (/root/reference: include/cpprob/cpprob.hpp:173-203 `cpprob::inference`, :68-106 sample/observe/
+ * predict; include/cpprob/postprocess/stats_printer.hpp:22-121).  The C++14 mirror of that API in
+ * include/cpprob/cpprob.hpp is a thin header layer over the entry points declared here; each entry
+ * point names the reference code whose work it takes over.  Plain pointers and sizes only, no
+ * exceptions cross this boundary: every call returns 0 on success or a negative CPPROB_SIS_E* code,
+ * and cpprob_sis_last_error() returns the message for the calling thread.
+ *
+ * There is no CPU fallback: if no CUDA device is usable cpprob_sis_create fails.
+ */
+#ifndef CPPROB_SIS_H
+#define CPPROB_SIS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPPROB_SIS_ABI_VERSION 1
+
+enum {
+    CPPROB_SIS_OK = 0,
+    CPPROB_SIS_EINVAL = -1,    /* bad argument */
+    CPPROB_SIS_ECUDA = -2,     /* CUDA runtime error (message has the details) */
+    CPPROB_SIS_ENOMODEL = -3,  /* unknown model id / name */
+    CPPROB_SIS_EIO = -4,       /* posterior file could not be written */
+    CPPROB_SIS_ERANGE = -5,    /* int predict window too wide for the on-device histogram */
+    CPPROB_SIS_ENOMEM = -6
+};
+
+typedef struct cpprob_sis_engine cpprob_sis_engine;
+
+typedef struct cpprob_sis_config {
+    int device;              /* CUDA device ordinal */
+    uint64_t seed;           /* Philox key; the reference seeds mt19937 from random_device
+                                (src/cpprob/utils.cpp:16-20), so it has no counterpart */
+    uint64_t max_batch;      /* particles per trace batch when rows are materialised (0 = default) */
+    int blocks_per_sm;       /* persistent grid = blocks_per_sm x SM count (0 = default) */
+} cpprob_sis_config;
+
+/* ---- engine lifetime ------------------------------------------------------------------------ */
+int cpprob_sis_abi_version(void);
+const char * cpprob_sis_last_error(void);
+int cpprob_sis_create(const cpprob_sis_config * cfg, cpprob_sis_engine ** out);
+void cpprob_sis_destroy(cpprob_sis_engine * e);
+
+/* ---- model registry --------------------------------------------------------------------------
+ * A model is a device functor (include/models/models.hpp) compiled into a set of kernel
+ * instantiations; the registry pairs a name with their launchers.  Built-in: the models of
+ * /root/reference include/models/models.hpp:22-35,67-80,114-141 and src/models/gaussian.cpp:6-17.
+ * Plugins (user .cu files using CPPROB_SIS_REGISTER_MODEL) add theirs at load time. */
+struct cpprob_sis_model_vtable;
+int cpprob_sis_register_model(const struct cpprob_sis_model_vtable * vt);
+int cpprob_sis_model_count(void);
+const char * cpprob_sis_model_name(int model_id);
+int cpprob_sis_find_model(const char * name);     /* id >= 0, or CPPROB_SIS_ENOMODEL */
+
+/* ---- trace structure -------------------------------------------------------------------------
+ * Takes over TraceInfer::register_addr_predict (include/cpprob/trace.hpp:37-41) and the
+ * int/real routing of StateInfer::add_predict (include/cpprob/state.hpp:312-326): one host-side
+ * probe execution records, in program order, the address id and kind of every predict statement. */
+typedef struct cpprob_sis_slot {
+    int is_int;      /* 1: value goes to <out>.int, 0: to <out>.real */
+    int id;          /* address id = line number in <out>.ids */
+    int k;           /* occurrence index of this id within one trace (StatsPrinter's key) */
+    int row;         /* row inside the int / real SoA block */
+} cpprob_sis_slot;
+
+typedef struct cpprob_sis_structure {
+    int n_ids;
+    int n_slots;
+    int n_real;
+    int n_int;
+    int n_samples;
+    const char * const * ids;          /* [n_ids], engine-owned, valid until the next describe/run */
+    const cpprob_sis_slot * slots;     /* [n_slots], program order */
+} cpprob_sis_structure;
+
+int cpprob_sis_describe(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs,
+                        cpprob_sis_structure * out);
+
+/* ---- inference --------------------------------------------------------------------------------
+ * Posterior estimators.  Everything StatsPrinter prints (mean / variance per real (id,k);
+ * distribution / MAP / num points per int (id,k)) plus max log-weight, log-sum-exp, log-evidence
+ * and ESS, which the reference does not compute (north_star additions).  Pointers are engine-owned
+ * and stay valid until the next call on the same engine. */
+typedef struct cpprob_sis_stats {
+    uint64_t n_particles;
+    uint64_t n_neg_inf;          /* particles with log_w == -inf */
+    uint64_t n_nan;
+    double m_ref;                /* reference log-weight the sums are relative to */
+    double max_log_w;
+    double log_sum_exp;          /* log sum_i exp(log_w_i)  (empirical_distribution.hpp:117-143) */
+    double log_evidence;         /* log_sum_exp - log n */
+    double ess;                  /* (sum w)^2 / sum w^2 */
+    int n_real;
+    int n_int;
+    const double * real_mean;    /* [n_real]  sum w~ x            (empirical_distribution.hpp:52-71) */
+    const double * real_var;     /* [n_real]  sum w~ x^2 - mean^2 (:78-81) */
+    long long int_lo;            /* first histogram bin value */
+    int int_bins;
+    const double * int_prob;     /* [n_int][int_bins]  sum w~ [x == int_lo + b]   (:30-40) */
+    const long long * int_map;   /* [n_int] argmax (first maximum, as std::max_element :47-50) */
+    int n_cols;
+    const double * sums;         /* [n_cols] merged raw sums (kBaseCols, then S1,S2 per real row, then bins) */
+    double device_ms;            /* CUDA-event time of the particle + reduction kernels of this call */
+    uint64_t kernel_launches;    /* kernels launched by this call */
+    int passes;                  /* 1, or 2 if m_ref had to be re-based */
+} cpprob_sis_stats;
+
+enum {
+    CPPROB_SIS_EMIT_NONE = 0,    /* estimators only: no trace leaves the GPU */
+    CPPROB_SIS_EMIT_ALL = 1      /* every particle's record is delivered / written */
+};
+
+typedef struct cpprob_sis_block {
+    uint64_t first_particle;     /* global index of column 0 */
+    uint64_t n;                  /* particles (columns) in this block */
+    uint64_t stride;             /* elements between consecutive rows */
+    int n_real, n_int;
+    const double * real_rows;    /* [n_real][stride], pinned host memory */
+    const int32_t * int_rows;    /* [n_int][stride] */
+    const double * log_w;        /* [n] */
+} cpprob_sis_block;
+
+/* Called on the calling thread, once per trace block, in particle order.  Non-zero aborts the run. */
+typedef int (*cpprob_sis_block_fn)(void * user, const cpprob_sis_block * blk);
+
+typedef struct cpprob_sis_run_options {
+    int emit;                    /* CPPROB_SIS_EMIT_* */
+    int force_rows;              /* 1: use the row (SoA) path even when the fused kernel applies */
+    cpprob_sis_block_fn on_block;/* receives the SoA trace blocks when emit == EMIT_ALL (may be NULL) */
+    void * user;
+} cpprob_sis_run_options;
+
+/* Takes over the loop of cpprob::inference (cpprob.hpp:194-201) and the estimator pass of
+ * StatsPrinter: runs n_particles weighted executions of the model on the engine's GPU. */
+int cpprob_sis_run(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs,
+                   uint64_t n_particles, const cpprob_sis_run_options * opt, cpprob_sis_stats * out);
+
+/* Same, and writes the reference's posterior files: one `([(id v) ...] logw)` line per particle to
+ * <prefix>.real / <prefix>.int (StateInfer::finish_trace + dump_predicts, src/cpprob/state.cpp:
+ * 193-202,262-267, grammar include/cpprob/serialization.hpp:41-46,71-98, scientific/precision 15),
+ * <prefix>.ids (dump_ids, state.cpp:250-260) and removes the kinds that stayed empty
+ * (finish_infer, state.cpp:164-180).  Files are appended to, as in the reference (ios::app).
+ * Also writes <prefix>.stats with the on-device estimators. */
+int cpprob_sis_infer_to_files(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs,
+                              uint64_t n_particles, const char * prefix, cpprob_sis_stats * out);
+
+/* ---- multi-GPU: shard / gather / merge ---------------------------------------------------------
+ * Particles are i.i.d. (cpprob.hpp:194-201 has no inter-particle dependence), so rank r of `world`
+ * takes the chunk range [r*C/world, (r+1)*C/world) of the C = ceil(n/32768) chunks and no data-path
+ * collective is needed.  Each rank returns its per-chunk partial sums in DEVICE memory; the caller
+ * all-gathers them in rank order (NCCL) and hands the concatenation to cpprob_sis_merge, which is
+ * bit-identical on every rank and for every world size. */
+typedef struct cpprob_sis_partials {
+    double * device_ptr;         /* [n_chunks_local][n_cols], engine-owned */
+    uint32_t n_chunks_local;
+    uint32_t n_chunks_total;
+    uint32_t chunk_first;
+    int n_cols;
+    double m_ref;
+    double device_ms;
+    uint64_t kernel_launches;
+} cpprob_sis_partials;
+
+int cpprob_sis_run_shard(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs,
+                         uint64_t n_particles_total, int rank, int world,
+                         const double * m_ref_override /* NULL: pilot */,
+                         cpprob_sis_partials * out);
+
+/* gathered: DEVICE pointer to [n_chunks_total][n_cols].  Returns 1 (not an error) if the weights
+ * have to be re-based: call run_shard again with *m_ref_override = out->max_log_w. */
+int cpprob_sis_merge(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs,
+                     const double * gathered, uint32_t n_chunks_total, int n_cols, double m_ref,
+                     uint64_t n_particles_total, cpprob_sis_stats * out);
+
+/* ---- replay ------------------------------------------------------------------------------------
+ * Recomputes log_w for n recorded traces (host SoA rows as in cpprob_sis_block) by re-running the
+ * model with every sample statement returning the recorded value.  Parity gate for
+ * cpprob::observe / logpdf<> (cpprob.hpp:87-89): must match the reference's log-weights to 1e-12. */
+int cpprob_sis_replay(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs,
+                      const double * real_rows, const int32_t * int_rows, uint64_t stride, uint64_t n,
+                      double * logw_out);
+
+/* Estimators from externally supplied records (e.g. parsed posterior files): the device twin of
+ * StatsPrinter::load_distr + operator<< (stats_printer.hpp:42-120). */
+int cpprob_sis_reduce_records(cpprob_sis_engine * e, const double * real_rows, int n_real,
+                              const int32_t * int_rows, int n_int, const double * log_w,
+                              uint64_t stride, uint64_t n, cpprob_sis_stats * out);
+
+/* ---- device distribution layer, exposed for testing and for callers that only need densities ----
+ * kind: see CPPROB_SIS_DIST_*; params: up to 8 doubles (mean,sigma | a,b | min,max | p0..p7 |
+ * mean | alpha(shape),beta(scale) | alpha,beta). */
+enum {
+    CPPROB_SIS_DIST_NORMAL = 0, CPPROB_SIS_DIST_UNIFORM_REAL = 1, CPPROB_SIS_DIST_UNIFORM_SMALLINT = 2,
+    CPPROB_SIS_DIST_DISCRETE = 3, CPPROB_SIS_DIST_POISSON = 4, CPPROB_SIS_DIST_GAMMA = 5,
+    CPPROB_SIS_DIST_BETA = 6
+};
+int cpprob_sis_logpdf(cpprob_sis_engine * e, int kind, const double * params, int n_params,
+                      const double * x, uint64_t n, double * out);
+int cpprob_sis_sample(cpprob_sis_engine * e, int kind, const double * params, int n_params,
+                      uint64_t seed, uint64_t first_particle, uint64_t n, double * out);
+/* raw Philox4x32-10 blocks: out[4*i..] = block(counter = ctr[4*i..], key = key[2*i..]) */
+int cpprob_sis_philox(cpprob_sis_engine * e, const uint32_t * ctr, const uint32_t * key, uint64_t n, uint32_t * out);
+/* fp64 elementary functions of include/cpprob/math/dmath.hpp: 0 log_unit 1 exp_weight 2 sin2pi 3 cos2pi (joint) 4 sqrt_pos 5 Box-Muller z0 from (u1,u2) packed as x[2i],x[2i+1] 6 log 7 cos_2pi 8 sin_2pi (single chain) */
+int cpprob_sis_dmath(cpprob_sis_engine * e, int fn, const double * x, uint64_t n, double * out);
+
+/* ---- roofline denominators ----------------------------------------------------------------------*/
+int cpprob_sis_measure_dfma_peak(cpprob_sis_engine * e, double * tflops, double * sm_clock_mhz_est);
+int cpprob_sis_measure_store_peak(cpprob_sis_engine * e, double * gbytes_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPPROB_SIS_H */

@@ -1,0 +1,72 @@
+#!/usr/bin/env python3
+"""Instruction mix of one kernel's SASS (static count), grouped by issue pipe.
+
+usage: tools/sass_mix.py <lib.so|.o|.cubin> <kernel-name-substring> [--dump] [--range 0xLO 0xHI]
+The FP64 pipe share of the particle loop is the static proxy for the ncu metric
+sm__inst_executed_pipe_fp64 ("K1 instruction budget").
+"""
+import collections
+import re
+import subprocess
+import sys
+
+
+def kernel_sass(path, needle):
+    out = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout
+    blocks = re.split(r"\n\s*Function : ", out)
+    for b in blocks[1:]:
+        name = b.split("\n", 1)[0].strip()
+        if needle in name:
+            return name, b
+    raise SystemExit(f"no kernel matching {needle!r}")
+
+
+def classify(op):
+    base = op.split(".")[0]
+    if base in ("DFMA", "DADD", "DMUL", "DSETP", "DMNMX"):
+        return "fp64"
+    if base in ("MUFU",):
+        return "xu"
+    if base in ("IMAD", "FFMA", "FMUL", "FADD", "HFMA2", "IMUL"):
+        return "fma"
+    if base in ("LDG", "STG", "LDS", "STS", "LDC", "LDL", "STL", "ATOMG", "ATOMS", "RED", "LDCU"):
+        return "lsu"
+    if base in ("BRA", "EXIT", "BAR", "BSSY", "BSYNC", "CALL", "RET", "WARPSYNC", "NOP", "BREAK", "YIELD"):
+        return "ctrl"
+    if base in ("F2F", "I2F", "F2I", "I2I", "FRND", "DSETP"):
+        return "conv"
+    return "alu"
+
+
+def main():
+    path, needle = sys.argv[1], sys.argv[2]
+    name, body = kernel_sass(path, needle)
+    ops = collections.Counter()
+    classes = collections.Counter()
+    lines = []
+    lo_addr, hi_addr = 0, 1 << 62
+    if "--range" in sys.argv:
+        i = sys.argv.index("--range")
+        lo_addr, hi_addr = int(sys.argv[i + 1], 16), int(sys.argv[i + 2], 16)
+    for line in body.splitlines():
+        m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", line)
+        if not m:
+            continue
+        if not (lo_addr <= int(m.group(1), 16) <= hi_addr):
+            continue
+        op = m.group(2)
+        lines.append(line.rstrip())
+        ops[op.split(".")[0]] += 1
+        classes[classify(op)] += 1
+    total = sum(classes.values())
+    print(name)
+    print(f"total {total}")
+    for k, v in classes.most_common():
+        print(f"  {k:5s} {v:5d}  {100.0 * v / total:5.1f}%")
+    print("top opcodes:", ", ".join(f"{k}:{v}" for k, v in ops.most_common(24)))
+    if "--dump" in sys.argv:
+        print("\n".join(lines))
+
+
+if __name__ == "__main__":
+    main()
