@@ -1,0 +1,317 @@
+#!/usr/bin/env python3
+"""Headline benchmark: SIS particles/sec on the README model (BASELINE.json configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA path (N>1 under torchrun)
+  python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU SIS (restated oracle)
+
+One "step" = one complete inference pass: every particle of the workload is generated, weighted and
+folded into the posterior estimators (pilot + particle kernel + chunk merge [+ NCCL all-gather]).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "SIS particles/sec (device-timed)"
+MODEL = "gaussian_unknown_mean"
+OBS = [3.0, 4.0]
+SEED = 0x5EED
+
+# FP64-pipe thread instructions per particle of k_sis_fused<gaussian_unknown_mean_model, 1>, counted in
+# the SASS of the particle loop (tools/sass_mix.py; tests/test_sass_budget.py keeps this in step with the
+# binary).  One loop trip = one stream tile pair = 2 particles.  "flop" counts DFMA as 2, DADD/DMUL as 1.
+FP64_PIPE_INSTR_PER_PARTICLE = 62.5
+FP64_FLOP_PER_PARTICLE = 96.0
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        busy = sorted(sm)[len(sm) // 2:] if sm else []          # the upper half of the samples = under load
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU SIS (oracle restatement, faithful flavour) on all host cores
+# ---------------------------------------------------------------------------------------------------
+def oracle_binary():
+    exe = os.path.join(ROOT, "oracle", "oracle_sis")
+    if not os.path.exists(exe):
+        subprocess.run(["make"], cwd=os.path.join(ROOT, "oracle"), check=True, stdout=subprocess.DEVNULL)
+    return exe
+
+
+def scratch_dir():
+    return "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+
+
+def cpu_sis_step(n_procs, particles_each, flavour="faithful"):
+    """One bounded sample: n_procs independent single-threaded runs (the reference is single-threaded,
+    SURVEY.md §5), each writing its own posterior files.  Returns wall seconds."""
+    exe = oracle_binary()
+    with tempfile.TemporaryDirectory(dir=scratch_dir()) as d:
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen([exe, MODEL, str(particles_each), os.path.join(d, f"p{i}"), flavour, "3", "4"],
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for i in range(n_procs)]
+        for p in procs:
+            if p.wait() != 0:
+                raise RuntimeError("oracle_sis failed")
+        return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    each = args.ref_particles
+    for _ in range(args.warmup):
+        cpu_sis_step(cores, each)
+    times = [cpu_sis_step(cores, each) for _ in range(args.steps)]
+    total = sum(times)
+    value = cores * each * args.steps / total
+    sample = f"{cores} processes x {each} particles per step, faithful flavour (3 file appends per trace + StatsPrinter), files on {scratch_dir()}"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "particles/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "gaussian_unknown_mean x=(3,4), reference CPU SIS (oracle restatement of cpprob::inference + StatsPrinter; "
+                               "the reference itself needs Boost/ZeroMQ/FlatBuffers and cannot be built in this image)",
+                   "particles_per_step": cores * each},
+        "cpu_baseline": {"value": value, "unit": "particles/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+class _DeviceArray:
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cpprob_b200 import Engine, capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the SIS engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    engine = Engine(device=local_rank, seed=SEED)
+    per_gpu = args.particles
+    total = per_gpu * world
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    gathered_buf = {}
+
+    def step():
+        """One inference pass of `total` particles over `world` GPUs.  Returns (stats, kernel_ms, launches)."""
+        m_ref = None
+        for _attempt in range(3):
+            p = engine.run_shard(MODEL, OBS, total, rank, world, m_ref=m_ref)
+            kernel_ms, launches = p.device_ms, p.kernel_launches
+            if world == 1:
+                ptr, n_chunks = p.device_ptr, p.n_chunks_total
+            else:
+                # all-gather the per-chunk partial sums in rank order (NCCL over NVLink); shards differ by at most one chunk
+                max_local = -(-p.n_chunks_total // world)
+                key = (max_local, p.n_cols)
+                if key not in gathered_buf:
+                    gathered_buf[key] = (torch.zeros((max_local, p.n_cols), dtype=torch.float64, device="cuda"),
+                                         torch.empty((world, max_local, p.n_cols), dtype=torch.float64, device="cuda"))
+                local, allbuf = gathered_buf[key]
+                if p.n_chunks_local:
+                    local[:p.n_chunks_local].copy_(torch.as_tensor(_DeviceArray(p.device_ptr, (p.n_chunks_local, p.n_cols)), device="cuda"))
+                dist.all_gather_into_tensor(allbuf, local)
+                pieces = []
+                for r in range(world):
+                    _, ncl, _, _, _ = capi.plan_shard(total, r, world)
+                    pieces.append(allbuf[r, :ncl])
+                g = torch.cat(pieces).contiguous()
+                torch.cuda.synchronize()
+                ptr, n_chunks = g.data_ptr(), g.shape[0]
+            st, rebase = engine.merge(MODEL, OBS, ptr, n_chunks, p.n_cols, p.m_ref, total)
+            kernel_ms += st["device_ms"]
+            launches += st["kernel_launches"]
+            if not rebase:
+                return st, kernel_ms, launches
+            m_ref = st["max_log_w"]
+        raise RuntimeError("weights could not be re-based")
+
+    for _ in range(args.warmup):
+        step()
+        flush.fill_(1)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    kernel_ms_total, launches_total, last = 0.0, 0, None
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)                 # L2 flush between steps (outside the timed brackets)
+        torch.cuda.synchronize()
+        ev0[i].record()
+        last, kms, nl = step()
+        ev1[i].record()
+        kernel_ms_total += kms
+        launches_total += nl
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    t = torch.tensor([step_ms, kernel_ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms, kernel_ms_total = t.tolist()
+
+    # end to end through the public call with host buffers (cpprob_sis_run / run_shard+merge): wall clock,
+    # includes the H2D of the observations, every launch and sync, and the D2H of the estimators
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        if world == 1:
+            st_e2e = engine.run(MODEL, OBS, total)
+        else:
+            st_e2e, _, _ = step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = te.item()
+
+    if rank == 0:
+        value = total * args.steps / (step_ms * 1e-3)
+        n_cols = last["n_cols"]
+        line = {
+            "metric": METRIC, "value": value, "unit": "particles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"gaussian_unknown_mean x=(3,4), {per_gpu:.3g} particles per GPU (BASELINE.json configs[1])",
+                       "particles_per_gpu": per_gpu, "total_particles": total, "seed": SEED, "parallelism": f"particle shards x{world}",
+                       "l2": "256 MiB written between steps (flush); the path's only input is 16 B of observations"},
+            "e2e": {"value": total * e2e_steps / e2e_s, "unit": "particles/s", "h2d_bytes_per_step": 8 * len(OBS),
+                    "d2h_bytes_per_step": 24 + 8 * n_cols},
+            "gpu_launches": int(launches_total),
+            "clocks": clocks,
+            "posterior": {"mean": float(last["real_mean"][0]), "variance": float(last["real_var"][0]), "log_evidence": last["log_evidence"],
+                          "ess": last["ess"], "analytic_mean": 2.323529411764706, "analytic_variance": 1.0588235294117647,
+                          "mean_err_in_mc_se": abs(float(last["real_mean"][0]) - 2.323529411764706) / (1.2973 / math.sqrt(total))},
+            "kernel_ms_per_step": kernel_ms_total / args.steps,
+        }
+        if world == 1:
+            peak_tflops, est_mhz = engine.dfma_peak()
+            k_s = kernel_ms_total * 1e-3 / args.steps
+            achieved = FP64_FLOP_PER_PARTICLE * per_gpu / k_s / 1e12
+            line["roofline"] = {
+                "bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+                "traffic": None,
+                "note": "dominant kernel k_sis_fused is FP64-pipe bound (no dense contraction, no HBM stream): peak = DFMA chain "
+                        "micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry); achieved counts DFMA as 2 flop",
+                "fp64_pipe_util": FP64_PIPE_INSTR_PER_PARTICLE * per_gpu / k_s / (peak_tflops * 1e12 / 2.0),
+                "fp64_pipe_instr_per_particle": FP64_PIPE_INSTR_PER_PARTICLE, "flop_per_particle": FP64_FLOP_PER_PARTICLE,
+                "dfma_peak_sm_mhz_equiv": est_mhz,
+            }
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line), flush=True)
+    engine.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args):
+    """The reference's CPU SIS (single thread, as the reference is) on a bounded sample of the same workload."""
+    n = args.cpu_particles
+    s = cpu_sis_step(1, n, "faithful")
+    s_fast = cpu_sis_step(1, n, "fast")
+    return {"value": n / s, "unit": "particles/s", "cores": 1, "kind": "port",
+            "sample": f"{n} particles of gaussian_unknown_mean x=(3,4): restated cpprob::inference (3 file appends per trace) + StatsPrinter, "
+                      f"-O2, files on {scratch_dir()}",
+            "fast_flavour_value": n / s_fast}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles", type=int, default=1_000_000_000, help="particles per GPU per step")
+    ap.add_argument("--cpu-particles", type=int, default=1_000_000, help="particles of the cpu_baseline sample")
+    ap.add_argument("--ref-particles", type=int, default=50_000, help="particles per process per step of --impl reference")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

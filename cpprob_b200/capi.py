@@ -25,7 +25,7 @@ SYMBOLS = [
     "cpprob_sis_describe", "cpprob_sis_run", "cpprob_sis_infer_to_files", "cpprob_sis_run_shard",
     "cpprob_sis_merge", "cpprob_sis_replay", "cpprob_sis_reduce_records", "cpprob_sis_logpdf",
     "cpprob_sis_sample", "cpprob_sis_philox", "cpprob_sis_dmath", "cpprob_sis_measure_dfma_peak",
-    "cpprob_sis_measure_store_peak",
+    "cpprob_sis_measure_store_peak", "cpprob_sis_plan_shard",
 ]
 
 
@@ -110,8 +110,18 @@ def lib():
         L.cpprob_sis_dmath.argtypes = [C.c_void_p, C.c_int, dp, u64, dp]
         L.cpprob_sis_measure_dfma_peak.argtypes = [C.c_void_p, dp, dp]
         L.cpprob_sis_measure_store_peak.argtypes = [C.c_void_p, dp]
+        L.cpprob_sis_plan_shard.argtypes = [u64, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                            C.POINTER(u64), C.POINTER(u64)]
         _lib = L
         return L
+
+
+def plan_shard(n_total, rank, world):
+    """(chunk_first, n_chunks_local, n_chunks_total, first_particle, n_local) of `rank` — host arithmetic only."""
+    cf, ncl, nct = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    fp, nl = C.c_uint64(), C.c_uint64()
+    _check(lib().cpprob_sis_plan_shard(int(n_total), rank, world, C.byref(cf), C.byref(ncl), C.byref(nct), C.byref(fp), C.byref(nl)))
+    return cf.value, ncl.value, nct.value, fp.value, nl.value
 
 
 class SisError(RuntimeError):

@@ -264,8 +264,10 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     CU_TRY(e->d_counter.reserve(1));
     CU_TRY(cudaMemcpyAsync(e->d_obs.ptr, obs, n_obs * sizeof(double), cudaMemcpyHostToDevice, e->compute));
 
-    // pilot: m_ref and the int window, identical on every rank
+    // pilot: m_ref and the int window, identical on every rank.  The device-timed region of a run
+    // starts here: it covers the pilot, the particle kernel(s) and the row reductions.
     const philox_keys keys(e->seed);
+    CU_TRY(cudaEventRecord(e->ev_begin, e->compute));
     const int n_pilot = static_cast<int>(std::min<uint64_t>(n_total, kPilot));
     double pilot[3] = {0, 0, 0};
     CU_TRY(vt->launch_pilot(e->compute, &keys, e->d_obs.ptr, static_cast<int>(n_obs), n_pilot, e->d_pilot.ptr));
@@ -321,7 +323,6 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         a.n_chunks = plan.n_chunks_local;
         a.partials = e->d_partials.ptr;
         CU_TRY(cudaMemsetAsync(e->d_counter.ptr, 0, sizeof(unsigned), e->compute));
-        CU_TRY(cudaEventRecord(e->ev_begin, e->compute));
         CU_TRY(vt->launch_fused(e->compute, grid, nr, &a));
         CU_TRY(cudaEventRecord(e->ev_end, e->compute));
         ++res->launches;
@@ -380,7 +381,6 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         return 0;
     };
 
-    if (!emit) CU_TRY(cudaEventRecord(e->ev_begin, e->compute));
     for (uint64_t b = 0; b < n_batches; ++b) {
         const int buf = emit ? static_cast<int>(b & 1) : 0;
         const uint64_t off = b * cap;
@@ -622,6 +622,19 @@ int cpprob_sis_find_model(const char * name)
         if (std::strcmp(registry()[i]->name, name) == 0) return static_cast<int>(i);
     }
     return fail(CPPROB_SIS_ENOMODEL, std::string("no device model named '") + name + "' is registered");
+}
+
+int cpprob_sis_plan_shard(uint64_t n_particles_total, int rank, int world, uint32_t * chunk_first, uint32_t * n_chunks_local,
+                          uint32_t * n_chunks_total, uint64_t * first_particle, uint64_t * n_local)
+{
+    if (world <= 0 || rank < 0 || rank >= world || n_particles_total == 0) return fail(CPPROB_SIS_EINVAL, "bad rank / world / n");
+    const shard_plan p = plan_shard(n_particles_total, rank, world);
+    if (chunk_first) *chunk_first = p.chunk_first;
+    if (n_chunks_local) *n_chunks_local = p.n_chunks_local;
+    if (n_chunks_total) *n_chunks_total = p.n_chunks_total;
+    if (first_particle) *first_particle = p.first_particle;
+    if (n_local) *n_local = p.n_local;
+    return 0;
 }
 
 int cpprob_sis_create(const cpprob_sis_config * cfg, cpprob_sis_engine ** out)

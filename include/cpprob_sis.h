@@ -168,6 +168,11 @@ typedef struct cpprob_sis_partials {
     uint64_t kernel_launches;
 } cpprob_sis_partials;
 
+/* The shard of `rank`: pure host arithmetic, usable without a GPU. */
+int cpprob_sis_plan_shard(uint64_t n_particles_total, int rank, int world, uint32_t * chunk_first,
+                          uint32_t * n_chunks_local, uint32_t * n_chunks_total, uint64_t * first_particle,
+                          uint64_t * n_local);
+
 int cpprob_sis_run_shard(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs,
                          uint64_t n_particles_total, int rank, int world,
                          const double * m_ref_override /* NULL: pilot */,
