@@ -11,6 +11,7 @@ import analytic
 
 pytestmark = pytest.mark.gpu
 G = analytic.golden()
+mpmath.mp.dps = 40
 
 
 def ulp_err(got, exact):
