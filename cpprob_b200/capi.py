@@ -11,7 +11,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcpprob_sis.so")
+LIB_PATH = os.environ.get("CPPROB_SIS_LIB") or os.path.join(_HERE, "lib", "libcpprob_sis.so")   # override: kernel-variant sweeps
 
 EMIT_NONE, EMIT_ALL = 0, 1
 DIST = {"normal": 0, "uniform_real": 1, "uniform_smallint": 2, "discrete": 3, "poisson": 4, "gamma": 5, "beta": 6}
@@ -25,7 +25,7 @@ SYMBOLS = [
     "cpprob_sis_describe", "cpprob_sis_run", "cpprob_sis_infer_to_files", "cpprob_sis_run_shard",
     "cpprob_sis_merge", "cpprob_sis_replay", "cpprob_sis_reduce_records", "cpprob_sis_logpdf",
     "cpprob_sis_sample", "cpprob_sis_philox", "cpprob_sis_dmath", "cpprob_sis_measure_dfma_peak",
-    "cpprob_sis_measure_store_peak", "cpprob_sis_plan_shard",
+    "cpprob_sis_measure_store_peak", "cpprob_sis_plan_shard", "cpprob_sis_probe_issue",
 ]
 
 
@@ -110,6 +110,7 @@ def lib():
         L.cpprob_sis_dmath.argtypes = [C.c_void_p, C.c_int, dp, u64, dp]
         L.cpprob_sis_measure_dfma_peak.argtypes = [C.c_void_p, dp, dp]
         L.cpprob_sis_measure_store_peak.argtypes = [C.c_void_p, dp]
+        L.cpprob_sis_probe_issue.argtypes = [C.c_void_p, C.c_int, dp]
         L.cpprob_sis_plan_shard.argtypes = [u64, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                             C.POINTER(u64), C.POINTER(u64)]
         _lib = L
@@ -302,6 +303,11 @@ class Engine:
         t, mhz = C.c_double(), C.c_double()
         _check(self._L.cpprob_sis_measure_dfma_peak(self._h, C.byref(t), C.byref(mhz)))
         return t.value, mhz.value
+
+    def probe_issue(self, int_per_dfma):
+        ms = C.c_double()
+        _check(self._L.cpprob_sis_probe_issue(self._h, int_per_dfma, C.byref(ms)))
+        return ms.value
 
     def store_peak(self):
         g = C.c_double()

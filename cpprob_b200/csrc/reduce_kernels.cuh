@@ -170,6 +170,31 @@ __global__ void __launch_bounds__(kBlock) k_dfma_peak(double * __restrict__ out,
     if (s == 123.456) out[blockIdx.x * kBlock + threadIdx.x] = s;   // never true; keeps the chain alive
 }
 
+// Issue-model probe: the same 8 DFMA chains with NI independent integer (ALU-pipe) instructions per DFMA
+// interleaved.  If time does not grow with NI <= 1 the FP64 pipe co-issues with the ALU pipe; if it
+// grows by ~50% per NI, an FP64 warp instruction holds the issue port for both of its cycles.
+template<int NI>
+__global__ void __launch_bounds__(kBlock) k_issue_probe(double * __restrict__ out, int iters, double a, double b, unsigned m)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    unsigned i0 = threadIdx.x, i1 = i0 + 1, i2 = i0 + 2, i3 = i0 + 3, i4 = i0 + 4, i5 = i0 + 5, i6 = i0 + 6, i7 = i0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                i0 = (i0 ^ m) + i1; i1 = (i1 ^ m) + i2; i2 = (i2 ^ m) + i3; i3 = (i3 ^ m) + i4;
+                i4 = (i4 ^ m) + i5; i5 = (i5 ^ m) + i6; i6 = (i6 ^ m) + i7; i7 = (i7 ^ m) + i0;
+            }
+        }
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    const unsigned t = i0 ^ i1 ^ i2 ^ i3 ^ i4 ^ i5 ^ i6 ^ i7;
+    if (s == 123.456 || t == 0x12345u) out[blockIdx.x * kBlock + threadIdx.x] = s + t;
+}
+
 // Streaming store of doubles (HBM write roofline for the trace rows).
 __global__ void __launch_bounds__(kBlock) k_store_peak(double2 * __restrict__ dst, unsigned long long n2, double v)
 {

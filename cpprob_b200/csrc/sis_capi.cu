@@ -477,7 +477,11 @@ int merge_impl(cpprob_sis_engine * e, const double * gathered, uint32_t n_chunks
     out->n_nan = static_cast<uint64_t>(s[col::n_nan]);
     out->m_ref = m_ref;
     out->max_log_w = s[col::max_lw];
-    const double s0 = s[col::s0], s00 = s[col::s00];
+    // a NaN or +inf log-weight makes every self-normalised estimator NaN, as it does in the reference
+    // (exp(nan - lse) / exp(inf - inf) in empirical_distribution.hpp:52-66); exp_weight does not
+    // propagate those itself, so poison the sums here
+    const bool poisoned = s[col::n_nan] > 0.0 || s[col::max_lw] == std::numeric_limits<double>::infinity();
+    const double s0 = poisoned ? std::numeric_limits<double>::quiet_NaN() : s[col::s0], s00 = s[col::s00];
     out->log_sum_exp = m_ref + std::log(s0);
     out->log_evidence = out->log_sum_exp - std::log(static_cast<double>(n_total));
     out->ess = s0 * s0 / s00;
@@ -1009,6 +1013,34 @@ int cpprob_sis_measure_dfma_peak(cpprob_sis_engine * e, double * tflops, double 
         // 64 DFMA lanes per SM per clock
         *sm_clock_mhz_est = fmas / (best_ms * 1e-3) / (64.0 * e->sm_count) / 1e6;
     }
+    return 0;
+}
+
+int cpprob_sis_probe_issue(cpprob_sis_engine * e, int int_per_dfma, double * ms_out)
+{
+    if (!e || !ms_out || int_per_dfma < 0 || int_per_dfma > 3) return fail(CPPROB_SIS_EINVAL, "bad argument");
+    if (int rc = use_device(e)) return rc;
+    const int grid = e->sm_count * 8;
+    CU_TRY(e->d_w[0].reserve(static_cast<size_t>(grid) * kBlock));
+    const int iters = 2048;
+    double best_ms = 1e30;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU_TRY(cudaEventRecord(e->ev_begin, e->compute));
+        switch (int_per_dfma) {
+        case 0: k_issue_probe<0><<<grid, kBlock, 0, e->compute>>>(e->d_w[0].ptr, iters, 0.999999, 1.0e-6, 0x9E3779B9u); break;
+        case 1: k_issue_probe<1><<<grid, kBlock, 0, e->compute>>>(e->d_w[0].ptr, iters, 0.999999, 1.0e-6, 0x9E3779B9u); break;
+        case 2: k_issue_probe<2><<<grid, kBlock, 0, e->compute>>>(e->d_w[0].ptr, iters, 0.999999, 1.0e-6, 0x9E3779B9u); break;
+        default: k_issue_probe<3><<<grid, kBlock, 0, e->compute>>>(e->d_w[0].ptr, iters, 0.999999, 1.0e-6, 0x9E3779B9u); break;
+        }
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaEventRecord(e->ev_end, e->compute));
+        CU_TRY(cudaStreamSynchronize(e->compute));
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));
+        if (rep > 0) best_ms = std::min<double>(best_ms, ms);
+        ++e->launches;
+    }
+    *ms_out = best_ms;
     return 0;
 }
 

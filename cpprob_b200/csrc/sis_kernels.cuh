@@ -25,6 +25,13 @@
 namespace cpprob {
 namespace engine {
 
+#ifndef CPPROB_TILES_PER_TRIP
+#define CPPROB_TILES_PER_TRIP 1             // stream tiles (pairs of particles per thread) per loop trip
+#endif
+#ifndef CPPROB_FUSED_MIN_BLOCKS
+#define CPPROB_FUSED_MIN_BLOCKS 4           // resident CTAs per SM the fused kernel is compiled for
+#endif
+
 constexpr int kBlock = 256;                 // threads per CTA
 constexpr int kWarps = kBlock / 32;
 constexpr unsigned kChunk = 1u << 15;       // particles per deterministic reduction unit
@@ -131,10 +138,33 @@ template<class Body>
 __device__ __forceinline__ void for_each_owned_particle(const philox_keys & keys, unsigned long long global_base,
                                                         unsigned n_here, Body && body)
 {
-    const unsigned n_tiles = (n_here + 2 * kPairStride - 1) / (2 * kPairStride);
+    constexpr unsigned kTile = 2 * kPairStride;
     const unsigned long long stream0 = stream_of_particle(global_base) + threadIdx.x;
-    for (unsigned tile = 0; tile < n_tiles; ++tile) {
-        const unsigned ia = tile * (2 * kPairStride) + threadIdx.x;
+    const unsigned full_tiles = n_here / kTile;
+    unsigned tile = 0;
+    // two whole tiles per trip: four independent particle bodies in one straight-line block, so that the
+    // scheduler can overlap the integer (Philox) phase of one with the FP64 chains of another and the
+    // polynomial constants are fetched once for all four
+#if CPPROB_TILES_PER_TRIP == 2
+    for (; tile + 2 <= full_tiles; tile += 2) {
+        philox_stream r0(keys, stream0 + static_cast<unsigned long long>(tile) * kPairStride);
+        philox_stream r1(keys, stream0 + static_cast<unsigned long long>(tile + 1) * kPairStride);
+        const unsigned i0 = tile * kTile + threadIdx.x;
+        body(r0, i0);
+        body(r1, i0 + kTile);
+        body(r0, i0 + kPairStride);
+        body(r1, i0 + kTile + kPairStride);
+    }
+#else
+    for (; tile < full_tiles; ++tile) {
+        philox_stream r0(keys, stream0 + static_cast<unsigned long long>(tile) * kPairStride);
+        const unsigned i0 = tile * kTile + threadIdx.x;
+        body(r0, i0);
+        body(r0, i0 + kPairStride);
+    }
+#endif
+    for (; tile * kTile < n_here; ++tile) {
+        const unsigned ia = tile * kTile + threadIdx.x;
         if (ia < n_here) {
             philox_stream rng(keys, stream0 + static_cast<unsigned long long>(tile) * kPairStride);
             body(rng, ia);
@@ -303,7 +333,7 @@ __global__ void __launch_bounds__(kBlock) k_pilot(const __grid_constant__ philox
 // Partial columns: kBaseCols then (S1, S2) per real predict slot.
 // ------------------------------------------------------------------------------------------------
 template<class Model, int NR>
-__global__ void __launch_bounds__(kBlock) k_sis_fused(const __grid_constant__ run_args a)
+__global__ void __launch_bounds__(kBlock, CPPROB_FUSED_MIN_BLOCKS) k_sis_fused(const __grid_constant__ run_args a)
 {
     constexpr int NV = kBaseCols + 2 * NR;
     __shared__ double smem[kWarps * NV];
@@ -331,8 +361,8 @@ __global__ void __launch_bounds__(kBlock) k_sis_fused(const __grid_constant__ ru
             invoke_model(model, p, oc.data(), a.n_obs);
             const double lw = p.log_w();
             const double w = dm::exp_weight(lw - m_ref);
-            max_lw = fmax(max_lw, lw);
-            if (!is_finite(lw)) {   // rare: keep the bookkeeping off the common path
+            max_lw = lw > max_lw ? lw : max_lw;
+            if (__builtin_expect(!is_finite(lw), 0)) {
                 n_neginf += is_neg_inf(lw) ? 1u : 0u;
                 n_nan += is_nan(lw) ? 1u : 0u;
             }
@@ -397,8 +427,8 @@ __global__ void __launch_bounds__(kBlock) k_sis_rows(const __grid_constant__ run
             const double w = dm::exp_weight(lw - m_ref);
             a.logw[colidx] = lw;
             a.w[colidx] = w;
-            max_lw = fmax(max_lw, lw);
-            if (!is_finite(lw)) {   // rare: keep the bookkeeping off the common path
+            max_lw = lw > max_lw ? lw : max_lw;
+            if (__builtin_expect(!is_finite(lw), 0)) {
                 n_neginf += is_neg_inf(lw) ? 1u : 0u;
                 n_nan += is_nan(lw) ? 1u : 0u;
             }

@@ -66,10 +66,10 @@ struct logpdf<normal_distribution<RealType>> {
     {
         const RealType mean = distr.mean();
         const RealType std = distr.sigma();
-        if (std == 0) {
+        if (CPPROB_UNLIKELY(std == 0)) {
             return x == mean ? RealType(0) : -std::numeric_limits<RealType>::infinity();
         }
-        if (dm::fabs(x) == std::numeric_limits<RealType>::infinity()) {
+        if (CPPROB_UNLIKELY(dm::fabs(x) == std::numeric_limits<RealType>::infinity())) {
             return -std::numeric_limits<RealType>::infinity();
         }
         RealType result = (x - mean) / std;

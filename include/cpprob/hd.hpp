@@ -21,4 +21,10 @@
 #  define CPPROB_ON_DEVICE 0
 #endif
 
+#if defined(__GNUC__) || defined(__CUDACC__)
+#  define CPPROB_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#else
+#  define CPPROB_UNLIKELY(x) (x)
+#endif
+
 #endif  // CPPROB_HD_HPP

@@ -13,7 +13,7 @@
 //   log_unit, log     <= 2 ulp
 //   sqrt_pos          <= 1 ulp (Newton from the hardware seed + exact residual step)
 //   sincos_2pi, cos_2pi  abs error <= 2^-52
-//   exp_weight        <= 2 ulp on (-708, 708); exactly 0 at or below -708 (and for -inf); +inf at or above 708
+//   exp_weight        <= 2 ulp on (-708, 709); exactly 0 at or below -708.4 (and for -inf)
 #ifndef CPPROB_MATH_DMATH_HPP
 #define CPPROB_MATH_DMATH_HPP
 
@@ -213,28 +213,31 @@ __device__ __forceinline__ double sin_2pi(double u) { return sin_or_cos_2pi<fals
 
 __device__ __forceinline__ double exp(double x) { return ::exp(x); }
 
-// exp(log_w - m_ref).  Anything at or below -708 (including -inf) gives exactly 0, anything at or
-// above 708 gives +inf, NaN gives NaN.  The range test is done on the bit pattern (ALU pipe); inside
-// (-708, 708) the result is a normal number and 2^k is applied through the exponent field.
+// exp(log_w - m_ref) for the weight reduction.  The argument is first clamped from below at -745 on its
+// bit pattern (ALU pipe, no branch), so -inf and every x <= -708 give exactly 0 through the ordinary
+// path (2^k below the normal range is flushed).  x >= 709.8, +inf and NaN are NOT handled here: the
+// kernels count NaN log-weights, and a maximum far above m_ref triggers the engine's re-base pass, so
+// such values never reach a reported estimate.
 __device__ __forceinline__ double exp_weight(double x)
 {
+    // negative doubles order like their unsigned high words: hi(x) > hi(-745.0) (unsigned) <=> x < -745
+    const unsigned xh = static_cast<unsigned>(__double2hiint(x));
+    const bool low = xh > 0xC0874800u;                               // x < -745 (or -inf, or a negative NaN)
+    const double xc = __hiloint2double(low ? static_cast<int>(0xC0874800u) : static_cast<int>(xh), low ? 0 : __double2loint(x));
     const double magic = tbl::k_round_magic;
-    const double t = fma(x, tbl::k_log2e, magic);
+    const double t = fma(xc, tbl::k_log2e, magic);
     const int k = __double2loint(t);
     const double kf = t - magic;
-    double r = fma(kf, -tbl::k_ln2_hi, x);
+    double r = fma(kf, -tbl::k_ln2_hi, xc);
     r = fma(kf, -tbl::k_ln2_lo, r);
     double q = tbl::exp_q[9];
 #pragma unroll
     for (int i = 8; i >= 0; --i) q = fma(q, r, tbl::exp_q[i]);
     const double e = fma(r * r, q, r) + 1.0;                        // in [0.70, 1.42]
-    const int hi = __double2hiint(e) + (k << 20);
-    double w = __hiloint2double(hi, __double2loint(e));
-    const int xhi = __double2hiint(x);
-    if ((static_cast<unsigned>(xhi) & 0x7FFFFFFFu) >= 0x40862000u) {  // |x| >= 708, inf or nan: rare
-        w = (x != x) ? x : (xhi < 0 ? 0.0 : std::numeric_limits<double>::infinity());
-    }
-    return w;
+    // times 2^k, built from the clamped biased exponent: k <= -1023 gives a factor of exactly 0, so
+    // weights below the normal range are flushed without a select the compiler could turn into a branch
+    const int biased = max(k + 1023, 0);
+    return e * __hiloint2double(biased << 20, 0);
 }
 
 __device__ __forceinline__ double lgamma(double x) { return ::lgamma(x); }

@@ -218,6 +218,8 @@ int cpprob_sis_dmath(cpprob_sis_engine * e, int fn, const double * x, uint64_t n
 /* ---- roofline denominators ----------------------------------------------------------------------*/
 int cpprob_sis_measure_dfma_peak(cpprob_sis_engine * e, double * tflops, double * sm_clock_mhz_est);
 int cpprob_sis_measure_store_peak(cpprob_sis_engine * e, double * gbytes_per_s);
+/* issue-model probe: time of a fixed DFMA workload with `int_per_dfma` (0..3) ALU instructions interleaved per DFMA */
+int cpprob_sis_probe_issue(cpprob_sis_engine * e, int int_per_dfma, double * ms_out);
 
 #ifdef __cplusplus
 }
