@@ -28,57 +28,64 @@ MODEL = "gaussian_unknown_mean"
 OBS = [3.0, 4.0]
 SEED = 0x5EED
 
-# FP64-pipe thread instructions per particle of k_sis_fused<gaussian_unknown_mean_model, 1>, counted in
-# the SASS of the particle loop (tools/sass_mix.py; tests/test_sass_budget.py keeps this in step with the
-# binary).  One loop trip = one stream tile pair = 2 particles.  "flop" counts DFMA as 2, DADD/DMUL as 1.
-FP64_PIPE_INSTR_PER_PARTICLE = 62.5
-FP64_FLOP_PER_PARTICLE = 96.0
+
+
+def sass_budget():
+    """FP64-pipe thread instructions and flops per particle of k_sis_fused<gaussian_unknown_mean_model, 1>, counted in
+    the SASS of the particle loop when the library was built (cpprob_b200/build.py, tools/sass_mix.py).  One loop
+    trip = one stream tile pair = 2 particles.  "flop" counts DFMA as 2, DADD / DMUL as 1, DSETP as 0."""
+    with open(os.path.join(ROOT, "cpprob_b200", "lib", "sass_budget.json")) as f:
+        b = json.load(f)
+    per = b["particles_per_trip"]
+    return {"fp64_instr": b["fp64"] / per, "flop": (2 * b["dfma"] + b["dadd"] + b["dmul"]) / per, "loop_instr": b["total"] / per}
 
 
 # ---------------------------------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons through NVML every few ms while the timed region runs
+    (nvidia-smi -lms cannot start fast enough for a region of a few hundred ms)."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
-        self.proc = None
+        self.sm, self.power, self.mask = [], [], 0
+        self.max_mhz = None
+        self.stop_flag = threading.Event()
+        self.thread = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                self.mask |= nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=5)
-            except subprocess.TimeoutExpired:
-                self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
-        busy = sorted(sm)[len(sm) // 2:] if sm else []          # the upper half of the samples = under load
-        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=2)
+        reasons = sorted(k for k, bit in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -146,7 +153,8 @@ class _DeviceArray:
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from cpprob_b200 import Engine, capi
+    from cpprob_b200 import Engine
+    from cpprob_b200.dist import gather_partials
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -178,21 +186,10 @@ def run_ours(args):
             if world == 1:
                 ptr, n_chunks = p.device_ptr, p.n_chunks_total
             else:
-                # all-gather the per-chunk partial sums in rank order (NCCL over NVLink); shards differ by at most one chunk
-                max_local = -(-p.n_chunks_total // world)
-                key = (max_local, p.n_cols)
-                if key not in gathered_buf:
-                    gathered_buf[key] = (torch.zeros((max_local, p.n_cols), dtype=torch.float64, device="cuda"),
-                                         torch.empty((world, max_local, p.n_cols), dtype=torch.float64, device="cuda"))
-                local, allbuf = gathered_buf[key]
-                if p.n_chunks_local:
-                    local[:p.n_chunks_local].copy_(torch.as_tensor(_DeviceArray(p.device_ptr, (p.n_chunks_local, p.n_cols)), device="cuda"))
-                dist.all_gather_into_tensor(allbuf, local)
-                pieces = []
-                for r in range(world):
-                    _, ncl, _, _, _ = capi.plan_shard(total, r, world)
-                    pieces.append(allbuf[r, :ncl])
-                g = torch.cat(pieces).contiguous()
+                # the one collective of the path: all-gather of the per-chunk partial sums in rank order (NCCL over NVLink)
+                local = (torch.as_tensor(_DeviceArray(p.device_ptr, (p.n_chunks_local, p.n_cols)), device="cuda") if p.n_chunks_local
+                         else torch.empty((0, p.n_cols), dtype=torch.float64, device="cuda"))
+                g = gather_partials(local, total, world, gathered_buf.get("scratch"))
                 torch.cuda.synchronize()
                 ptr, n_chunks = g.data_ptr(), g.shape[0]
             st, rebase = engine.merge(MODEL, OBS, ptr, n_chunks, p.n_cols, p.m_ref, total)
@@ -209,6 +206,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.02)
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     kernel_ms_total, launches_total, last = 0.0, 0, None
@@ -267,15 +265,17 @@ def run_ours(args):
         }
         if world == 1:
             peak_tflops, est_mhz = engine.dfma_peak()
+            budget = sass_budget()
             k_s = kernel_ms_total * 1e-3 / args.steps
-            achieved = FP64_FLOP_PER_PARTICLE * per_gpu / k_s / 1e12
+            achieved = budget["flop"] * per_gpu / k_s / 1e12
             line["roofline"] = {
                 "bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                 "traffic": None,
                 "note": "dominant kernel k_sis_fused is FP64-pipe bound (no dense contraction, no HBM stream): peak = DFMA chain "
                         "micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry); achieved counts DFMA as 2 flop",
-                "fp64_pipe_util": FP64_PIPE_INSTR_PER_PARTICLE * per_gpu / k_s / (peak_tflops * 1e12 / 2.0),
-                "fp64_pipe_instr_per_particle": FP64_PIPE_INSTR_PER_PARTICLE, "flop_per_particle": FP64_FLOP_PER_PARTICLE,
+                "fp64_pipe_util": budget["fp64_instr"] * per_gpu / k_s / (peak_tflops * 1e12 / 2.0),
+                "fp64_pipe_instr_per_particle": budget["fp64_instr"], "flop_per_particle": budget["flop"],
+                "loop_instr_per_particle": budget["loop_instr"],
                 "dfma_peak_sm_mhz_equiv": est_mhz,
             }
             line["cpu_baseline"] = cpu_baseline(args)

@@ -13,9 +13,29 @@ def _make(directory, *targets):
     subprocess.run(["make", "-j4", *targets], cwd=directory, check=True, env=env)
 
 
+HEADLINE_KERNEL = "k_sis_fusedIN6models27gaussian_unknown_mean_modelELi1"
+
+
+def write_sass_budget(lib):
+    """Static instruction budget of the headline kernel's particle loop (one trip = 2 particles), read from
+    the SASS of the library just built; bench.py turns it into the roofline's flop / instruction counts."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_mix
+    b = sass_mix.loop_budget(lib, HEADLINE_KERNEL)
+    b["particles_per_trip"] = 2
+    b["kernel"] = HEADLINE_KERNEL
+    with open(os.path.join(os.path.dirname(lib), "sass_budget.json"), "w") as f:
+        json.dump(b, f)
+    return b
+
+
 def build_engine():
     _make(os.path.join(ROOT, "cpprob_b200", "csrc"))
-    return os.path.join(ROOT, "cpprob_b200", "lib", "libcpprob_sis.so")
+    lib = os.path.join(ROOT, "cpprob_b200", "lib", "libcpprob_sis.so")
+    write_sass_budget(lib)
+    return lib
 
 
 def build_oracle():

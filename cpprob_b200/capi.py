@@ -98,7 +98,7 @@ def lib():
         L.cpprob_sis_find_model.argtypes = [C.c_char_p]
         L.cpprob_sis_describe.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t, C.POINTER(Structure)]
         L.cpprob_sis_run.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t, u64, C.POINTER(RunOptions), C.POINTER(Stats)]
-        L.cpprob_sis_infer_to_files.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t, u64, C.c_char_p, C.POINTER(Stats)]
+        L.cpprob_sis_infer_to_files.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t, u64, C.c_char_p, C.c_int, C.POINTER(Stats)]
         L.cpprob_sis_run_shard.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t, u64, C.c_int, C.c_int, dp, C.POINTER(Partials)]
         L.cpprob_sis_merge.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t, C.c_void_p, C.c_uint32, C.c_int, C.c_double, u64,
                                        C.POINTER(Stats)]
@@ -225,10 +225,11 @@ class Engine:
             out["log_w"] = np.concatenate([b[3] for b in blocks])
         return out
 
-    def infer_to_files(self, model, obs, n, prefix):
+    def infer_to_files(self, model, obs, n, prefix, emit=EMIT_ALL):
         obs = _f64(obs)
         st = Stats()
-        _check(self._L.cpprob_sis_infer_to_files(self._h, self.model_id(model), _dptr(obs), obs.size, int(n), prefix.encode(), C.byref(st)))
+        _check(self._L.cpprob_sis_infer_to_files(self._h, self.model_id(model), _dptr(obs), obs.size, int(n), prefix.encode(), emit,
+                                                 C.byref(st)))
         return stats_to_dict(st)
 
     def run_shard(self, model, obs, n_total, rank, world, m_ref=None):

@@ -54,6 +54,18 @@ inline char * format_int(char * p, long long v)
     return r.ptr;
 }
 
+// dump_ids (state.cpp:250-260): one address per line, line index = id; the file is truncated
+inline bool write_ids(const std::string & prefix, const std::vector<std::string> & ids)
+{
+    std::FILE * f = std::fopen((prefix + ".ids").c_str(), "wb");
+    if (!f) return false;
+    for (const auto & s : ids) {
+        std::fputs(s.c_str(), f);
+        std::fputc('\n', f);
+    }
+    return std::fclose(f) == 0;
+}
+
 class posterior_writer {
 public:
     posterior_writer(const std::string & prefix, const std::vector<cpprob_sis_slot> & slots) : prefix_(prefix)
@@ -157,13 +169,7 @@ public:
         bool ok = true;
         if (f_real_) { ok = std::fclose(f_real_) == 0 && ok; f_real_ = nullptr; }
         if (f_int_) { ok = std::fclose(f_int_) == 0 && ok; f_int_ = nullptr; }
-        std::FILE * f = std::fopen((prefix_ + ".ids").c_str(), "wb");
-        if (!f) return false;
-        for (const auto & s : ids) {
-            std::fputs(s.c_str(), f);
-            std::fputc('\n', f);
-        }
-        ok = std::fclose(f) == 0 && ok;
+        ok = write_ids(prefix_, ids) && ok;
         if (int_ids_.empty()) std::remove((prefix_ + ".int").c_str());
         if (real_ids_.empty()) std::remove((prefix_ + ".real").c_str());
         std::remove((prefix_ + ".any").c_str());   // no any-typed predicts exist on the device path

@@ -1080,12 +1080,21 @@ int file_sink_block(void * user, const cpprob_sis_block * blk)
 }  // namespace
 
 int cpprob_sis_infer_to_files(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs, uint64_t n_particles,
-                              const char * prefix, cpprob_sis_stats * out)
+                              const char * prefix, int emit, cpprob_sis_stats * out)
 {
     if (!e || !out || !obs || !prefix) return fail(CPPROB_SIS_EINVAL, "null argument");
     const cpprob_sis_model_vtable * vt = model_of(model_id);
     if (!vt) return fail(CPPROB_SIS_ENOMODEL, "unknown model id");
     if (int rc = probe_structure(e, vt, obs, n_obs)) return rc;
+    if (emit == CPPROB_SIS_EMIT_NONE) {
+        shard_options none;
+        if (int rc = run_full(e, vt, obs, n_obs, n_particles, none, out)) return rc;
+        if (!cpprob::text::write_ids(prefix, e->structure.ids)) return fail(CPPROB_SIS_EIO, std::string("cannot write ") + prefix + ".ids");
+        if (!cpprob::text::write_stats_sidecar(prefix, *out, e->slots, e->structure.ids)) {
+            return fail(CPPROB_SIS_EIO, std::string("cannot write ") + prefix + ".stats");
+        }
+        return 0;
+    }
     cpprob::text::posterior_writer writer(prefix, e->slots);
     if (!writer.open()) return fail(CPPROB_SIS_EIO, std::string("cannot open posterior files for ") + prefix + ": " + std::strerror(errno));
     file_sink fs{e, &writer};

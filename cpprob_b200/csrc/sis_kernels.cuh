@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kBlock) k_pilot(const __grid_constant__ philox
 // Partial columns: kBaseCols then (S1, S2) per real predict slot.
 // ------------------------------------------------------------------------------------------------
 template<class Model, int NR>
-__global__ void __launch_bounds__(kBlock, CPPROB_FUSED_MIN_BLOCKS) k_sis_fused(const __grid_constant__ run_args a)
+__global__ void __launch_bounds__(kBlock, NR == 1 ? CPPROB_FUSED_MIN_BLOCKS : 1) k_sis_fused(const __grid_constant__ run_args a)
 {
     constexpr int NV = kBaseCols + 2 * NR;
     __shared__ double smem[kWarps * NV];

@@ -147,9 +147,12 @@ int cpprob_sis_run(cpprob_sis_engine * e, int model_id, const double * obs, size
  * 193-202,262-267, grammar include/cpprob/serialization.hpp:41-46,71-98, scientific/precision 15),
  * <prefix>.ids (dump_ids, state.cpp:250-260) and removes the kinds that stayed empty
  * (finish_infer, state.cpp:164-180).  Files are appended to, as in the reference (ios::app).
- * Also writes <prefix>.stats with the on-device estimators. */
+ * Also writes <prefix>.stats with the on-device estimators.  With emit == CPPROB_SIS_EMIT_NONE the
+ * per-particle records are not produced at all (no trace leaves the GPU): only <prefix>.ids and
+ * <prefix>.stats are written. */
 int cpprob_sis_infer_to_files(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs,
-                              uint64_t n_particles, const char * prefix, cpprob_sis_stats * out);
+                              uint64_t n_particles, const char * prefix, int emit /* CPPROB_SIS_EMIT_* */,
+                              cpprob_sis_stats * out);
 
 /* ---- multi-GPU: shard / gather / merge ---------------------------------------------------------
  * Particles are i.i.d. (cpprob.hpp:194-201 has no inter-particle dependence), so rank r of `world`

@@ -38,9 +38,51 @@ def classify(op):
     return "alu"
 
 
+def particle_loop(body, marker="MUFU.RSQ64H"):
+    """(lo, hi) addresses of the innermost loop (backward branch span) that contains `marker`:
+    the steady-state particle loop of the SIS kernels (the sampler's sqrt seed is only issued there)."""
+    instr = []
+    for line in body.splitlines():
+        m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", line)
+        if m:
+            instr.append((int(m.group(1), 16), m.group(2)))
+    marks = [a for a, t in instr if marker in t]
+    best = None
+    for a, t in instr:
+        m = re.search(r"\bBRA\s+(?:\w+,\s*)?0x([0-9a-f]+)", t)
+        if not m:
+            continue
+        tgt = int(m.group(1), 16)
+        if tgt < a and any(tgt <= x <= a for x in marks):
+            if best is None or (a - tgt) < (best[1] - best[0]):
+                best = (tgt, a)
+    return best
+
+
+def loop_budget(path, needle):
+    """opcode counts of the particle loop: dict(total=, fp64=, dfma=, dadd=, dmul=, dsetp=)"""
+    name, body = kernel_sass(path, needle)
+    lo, hi = particle_loop(body)
+    c = collections.Counter()
+    for line in body.splitlines():
+        m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", line)
+        if m and lo <= int(m.group(1), 16) <= hi:
+            c["total"] += 1
+            base = m.group(2).split(".")[0]
+            if classify(m.group(2)) == "fp64":
+                c["fp64"] += 1
+            if base in ("DFMA", "DADD", "DMUL", "DSETP"):
+                c[base.lower()] += 1
+    return dict(c)
+
+
 def main():
     path, needle = sys.argv[1], sys.argv[2]
     name, body = kernel_sass(path, needle)
+    if "--loop" in sys.argv:
+        lo, hi = particle_loop(body)
+        sys.argv += ["--range", hex(lo), hex(hi)]
+        print(f"particle loop {hex(lo)}..{hex(hi)}")
     ops = collections.Counter()
     classes = collections.Counter()
     lines = []
