@@ -69,7 +69,7 @@ class RunOptions(C.Structure):
 
 class Partials(C.Structure):
     _fields_ = [("device_ptr", C.c_void_p), ("n_chunks_local", C.c_uint32), ("n_chunks_total", C.c_uint32),
-                ("chunk_first", C.c_uint32), ("n_cols", C.c_int), ("m_ref", C.c_double),
+                ("chunk_first", C.c_uint32), ("rows_per_chunk", C.c_uint32), ("n_cols", C.c_int), ("m_ref", C.c_double),
                 ("device_ms", C.c_double), ("kernel_launches", C.c_uint64)]
 
 

@@ -11,6 +11,12 @@
 namespace cpprob {
 namespace engine {
 
+__global__ void __launch_bounds__(kBlock) k_init_int_extra(int_extra * __restrict__ x, unsigned n)
+{
+    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+    if (i < n) x[i] = int_extra{0x7fffffff, static_cast<int>(0x80000000u), 0u, 0u};
+}
+
 // ------------------------------------------------------------------------------------------------
 // K4a k_row_moments: S1 = sum w x, S2 = sum w x^2 for kMomTile real rows of one chunk.
 // grid = (n_chunks, ceil(n_real / kMomTile)).  Each row element is read once (coalesced 8 B/lane);
@@ -18,15 +24,15 @@ namespace engine {
 // Output: partials[chunk][kBaseCols + 2*row + {0,1}].
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_row_moments(const double * __restrict__ real_rows, const double * __restrict__ w,
-                                                        unsigned long long stride, unsigned long long n_particles,
+                                                        unsigned long long stride, unsigned long long n_particles, unsigned chunk,
                                                         int n_real, double * __restrict__ partials, int n_cols)
 {
     __shared__ double smem[kWarps * 2 * kMomTile];
     const unsigned c = blockIdx.x;
     const int row0 = blockIdx.y * kMomTile;
-    const unsigned long long base = static_cast<unsigned long long>(c) * kChunk;
+    const unsigned long long base = static_cast<unsigned long long>(c) * chunk;
     const unsigned long long left = n_particles - base;
-    const unsigned n_here = left < kChunk ? static_cast<unsigned>(left) : kChunk;
+    const unsigned n_here = left < chunk ? static_cast<unsigned>(left) : chunk;
 
     double acc[2 * kMomTile];
 #pragma unroll
@@ -59,16 +65,16 @@ __global__ void __launch_bounds__(kBlock) k_row_moments(const double * __restric
 // ------------------------------------------------------------------------------------------------
 template<int V>
 __global__ void __launch_bounds__(kBlock) k_row_hist(const int * __restrict__ int_rows, const double * __restrict__ w,
-                                                     unsigned long long stride, unsigned long long n_particles,
+                                                     unsigned long long stride, unsigned long long n_particles, unsigned chunk,
                                                      long long lo, int bin_offset, int hist_bins, int hist_col0,
                                                      double * __restrict__ partials, int n_cols)
 {
     __shared__ double smem[kWarps * V];
     const unsigned c = blockIdx.x;
     const int row = blockIdx.y;
-    const unsigned long long base = static_cast<unsigned long long>(c) * kChunk;
+    const unsigned long long base = static_cast<unsigned long long>(c) * chunk;
     const unsigned long long left = n_particles - base;
-    const unsigned n_here = left < kChunk ? static_cast<unsigned>(left) : kChunk;
+    const unsigned n_here = left < chunk ? static_cast<unsigned>(left) : chunk;
     const int * __restrict__ src = int_rows + static_cast<unsigned long long>(row) * stride + base;
     const double * __restrict__ wsrc = w + base;
 
@@ -110,18 +116,21 @@ __global__ void __launch_bounds__(kBlock) k_merge_columns(const double * __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3 k_reduce_logw: base sums from a log-weight array alone (used by replay / external traces).
+// K3 k_row_base: weights w = exp(log_w - m_ref) and the base sums of one sub-chunk from its log_w
+// column (16 B of HBM traffic per particle).  Used after k_sis_rows and for externally supplied
+// records (replay / StatsPrinter-on-device).  `extras` (may be null) carries the int bookkeeping that
+// k_sis_rows accumulated for the sub-chunk.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_reduce_logw(const double * __restrict__ logw, unsigned long long n_particles,
-                                                        const double * __restrict__ m_ref_ptr, double * __restrict__ w_out,
-                                                        double * __restrict__ partials, int n_cols)
+__global__ void __launch_bounds__(kBlock) k_row_base(const double * __restrict__ logw, unsigned long long n_particles, unsigned chunk,
+                                                     const double * __restrict__ m_ref_ptr, double * __restrict__ w_out,
+                                                     const int_extra * __restrict__ extras, double * __restrict__ partials, int n_cols)
 {
     __shared__ double smem[kWarps * kBaseCols];
     const unsigned c = blockIdx.x;
     const double m_ref = *m_ref_ptr;
-    const unsigned long long base = static_cast<unsigned long long>(c) * kChunk;
+    const unsigned long long base = static_cast<unsigned long long>(c) * chunk;
     const unsigned long long left = n_particles - base;
-    const unsigned n_here = left < kChunk ? static_cast<unsigned>(left) : kChunk;
+    const unsigned n_here = left < chunk ? static_cast<unsigned>(left) : chunk;
     double v[kBaseCols];
 #pragma unroll
     for (int j = 0; j < kBaseCols; ++j) v[j] = 0.0;
@@ -131,14 +140,20 @@ __global__ void __launch_bounds__(kBlock) k_reduce_logw(const double * __restric
     for (unsigned i = threadIdx.x; i < n_here; i += kBlock) {
         const double lw = logw[base + i];
         const double wi = dm::exp_weight(lw - m_ref);
-        if (w_out) w_out[base + i] = wi;
-        v[col::max_lw] = fmax(v[col::max_lw], lw);
+        w_out[base + i] = wi;
+        v[col::max_lw] = lw > v[col::max_lw] ? lw : v[col::max_lw];
         v[col::s0] += wi;
         v[col::s00] = fma(wi, wi, v[col::s00]);
-        v[col::n_neginf] += (lw == dm::neg_inf()) ? 1.0 : 0.0;
-        v[col::n_nan] += (lw != lw) ? 1.0 : 0.0;
+        v[col::n_neginf] += is_neg_inf(lw) ? 1.0 : 0.0;
+        v[col::n_nan] += is_nan(lw) ? 1.0 : 0.0;
     }
-    const double r = block_reduce<kBaseCols>(v, kMaxColsMask, smem);
+    double r = block_reduce<kBaseCols>(v, kMaxColsMask, smem);
+    if (extras != nullptr) {
+        const int_extra x = extras[c];
+        if (threadIdx.x == col::neg_imin) r = x.vmin <= x.vmax ? -static_cast<double>(x.vmin) : dm::neg_inf();
+        if (threadIdx.x == col::imax) r = x.vmin <= x.vmax ? static_cast<double>(x.vmax) : dm::neg_inf();
+        if (threadIdx.x == col::int_oor) r = static_cast<double>(x.oor);
+    }
     if (threadIdx.x < kBaseCols) partials[static_cast<size_t>(c) * n_cols + threadIdx.x] = r;
 }
 

@@ -120,6 +120,7 @@ struct cpprob_sis_engine {
     device_buffer<double> d_obs, d_pilot, d_partials, d_merged, d_w[2], d_logw[2], d_real[2], d_gather;
     device_buffer<int> d_int[2];
     device_buffer<unsigned> d_counter;
+    device_buffer<int_extra> d_int_extra;
     pinned_buffer<double> h_real[2], h_logw[2], h_merged;
     pinned_buffer<int> h_int[2];
 
@@ -193,15 +194,15 @@ struct hist_window {
 };
 
 template<int V>
-cudaError_t launch_hist(cudaStream_t s, dim3 grid, const int * rows, const double * w, unsigned long long stride,
+cudaError_t launch_hist(cudaStream_t s, dim3 grid, unsigned chunk, const int * rows, const double * w, unsigned long long stride,
                         unsigned long long n, long long lo, int off, int bins, int col0, double * partials, int n_cols)
 {
-    k_row_hist<V><<<grid, kBlock, 0, s>>>(rows, w, stride, n, lo, off, bins, col0, partials, n_cols);
+    k_row_hist<V><<<grid, kBlock, 0, s>>>(rows, w, stride, n, chunk, lo, off, bins, col0, partials, n_cols);
     return cudaGetLastError();
 }
 
 // all histogram passes for one batch; returns number of launches through *launches
-cudaError_t launch_hist_all(cudaStream_t s, unsigned n_chunks, int n_int, const int * rows, const double * w,
+cudaError_t launch_hist_all(cudaStream_t s, unsigned n_chunks, unsigned chunk, int n_int, const int * rows, const double * w,
                             unsigned long long stride, unsigned long long n, hist_window hw, int col0,
                             double * partials, int n_cols, uint64_t * launches)
 {
@@ -211,14 +212,14 @@ cudaError_t launch_hist_all(cudaStream_t s, unsigned n_chunks, int n_int, const 
         cudaError_t err;
         const long long lo = hw.lo + off;
         switch (left >= 8 ? 8 : left) {
-        case 1: err = launch_hist<1>(s, grid, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        case 2: err = launch_hist<2>(s, grid, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        case 3: err = launch_hist<3>(s, grid, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        case 4: err = launch_hist<4>(s, grid, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        case 5: err = launch_hist<5>(s, grid, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        case 6: err = launch_hist<6>(s, grid, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        case 7: err = launch_hist<7>(s, grid, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        default: err = launch_hist<8>(s, grid, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        case 1: err = launch_hist<1>(s, grid, chunk, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        case 2: err = launch_hist<2>(s, grid, chunk, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        case 3: err = launch_hist<3>(s, grid, chunk, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        case 4: err = launch_hist<4>(s, grid, chunk, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        case 5: err = launch_hist<5>(s, grid, chunk, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        case 6: err = launch_hist<6>(s, grid, chunk, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        case 7: err = launch_hist<7>(s, grid, chunk, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        default: err = launch_hist<8>(s, grid, chunk, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
         }
         if (err != cudaSuccess) return err;
         ++*launches;
@@ -235,6 +236,8 @@ struct shard_options {
 
 struct shard_result {
     shard_plan plan;
+    uint32_t rows_per_chunk = 1;       // partial rows per kChunk particles: 1 (fused) or kChunk / kSubChunk (row path)
+    uint32_t n_rows_local = 0, n_rows_total = 0, row_first = 0;
     int n_cols = 0;
     hist_window hw;
     double m_ref = 0.0;
@@ -296,10 +299,15 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     res->m_ref = m_ref;
     const int n_cols = kBaseCols + 2 * n_real + n_int * hw.bins;
     res->n_cols = n_cols;
-    if (plan.n_chunks_local == 0) return 0;
-    CU_TRY(e->d_partials.reserve(static_cast<size_t>(plan.n_chunks_local) * n_cols));
-
     const bool fused = !opt.force_rows && opt.emit == CPPROB_SIS_EMIT_NONE && n_int == 0 && n_real <= kMaxFusedReal;
+    // partial-sum rows: one per chunk on the fused path, one per sub-chunk on the row path (same on every rank)
+    const unsigned row_particles = fused ? kChunk : kSubChunk;
+    res->rows_per_chunk = kChunk / row_particles;
+    res->n_rows_total = static_cast<uint32_t>((n_total + row_particles - 1) / row_particles);
+    res->row_first = plan.chunk_first * res->rows_per_chunk;
+    res->n_rows_local = static_cast<uint32_t>((plan.n_local + row_particles - 1) / row_particles);
+    if (plan.n_chunks_local == 0) return 0;
+    CU_TRY(e->d_partials.reserve(static_cast<size_t>(res->n_rows_local) * n_cols));
 
     run_args a;
     std::memset(&a, 0, sizeof a);
@@ -336,7 +344,7 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     // ---- row path: batches of whole chunks ------------------------------------------------------
     const bool emit = opt.emit == CPPROB_SIS_EMIT_ALL;
     const uint64_t bytes_per_particle = 8ull * n_real + 4ull * n_int + 16ull;
-    const uint64_t budget = emit ? (256ull << 20) : (4096ull << 20);
+    const uint64_t budget = emit ? (512ull << 20) : (8192ull << 20);
     uint64_t cap = e->max_batch ? e->max_batch : budget / bytes_per_particle;
     cap = std::max<uint64_t>(kChunk, cap / kChunk * kChunk);
     cap = std::min<uint64_t>(cap, static_cast<uint64_t>(plan.n_chunks_local) * kChunk);
@@ -352,6 +360,7 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
             CU_TRY(e->h_logw[b].reserve(cap));
         }
     }
+    if (n_int > 0) CU_TRY(e->d_int_extra.reserve(static_cast<size_t>(cap / kSubChunk)));
     int occ = vt->occupancy(3);
     if (occ <= 0) occ = 1;
     if (e->blocks_per_sm > 0) occ = std::min(occ, e->blocks_per_sm);
@@ -385,7 +394,7 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         const int buf = emit ? static_cast<int>(b & 1) : 0;
         const uint64_t off = b * cap;
         const uint64_t n_here = std::min<uint64_t>(cap, plan.n_local - off);
-        const unsigned chunks_here = static_cast<unsigned>((n_here + kChunk - 1) / kChunk);
+        const unsigned subs_here = static_cast<unsigned>((n_here + kSubChunk - 1) / kSubChunk);
         if (emit) {
             // the previous user of this buffer pair (batch b-2) must have been handed to the consumer
             if (int rc = deliver(buf)) return rc;
@@ -395,25 +404,35 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         }
         a.first_particle = plan.first_particle + off;
         a.n_particles = n_here;
-        a.n_chunks = chunks_here;
-        a.partials = e->d_partials.ptr + (off / kChunk) * n_cols;
+        a.n_chunks = subs_here;
+        a.chunk = kSubChunk;
+        a.partials = e->d_partials.ptr + (off / kSubChunk) * n_cols;
         a.real_rows = e->d_real[buf].ptr;
         a.int_rows = e->d_int[buf].ptr;
         a.logw = e->d_logw[buf].ptr;
         a.w = e->d_w[buf].ptr;
         a.row_stride = cap;
-        const int grid = static_cast<int>(std::min<uint64_t>(chunks_here, static_cast<uint64_t>(e->sm_count) * occ));
-        CU_TRY(cudaMemsetAsync(e->d_counter.ptr, 0, sizeof(unsigned), e->compute));
+        a.int_extras = n_int > 0 ? e->d_int_extra.ptr : nullptr;
+        if (n_int > 0) {
+            k_init_int_extra<<<(subs_here + kBlock - 1) / kBlock, kBlock, 0, e->compute>>>(e->d_int_extra.ptr, subs_here);
+            CU_TRY(cudaGetLastError());
+            ++res->launches;
+        }
+        const uint64_t n_tiles = (n_here + 2 * kPairStride - 1) / (2 * kPairStride);
+        const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(e->sm_count) * occ));
         CU_TRY(vt->launch_rows(e->compute, grid, &a));
         ++res->launches;
+        k_row_base<<<subs_here, kBlock, 0, e->compute>>>(a.logw, n_here, kSubChunk, e->d_pilot.ptr, a.w, a.int_extras, a.partials, n_cols);
+        CU_TRY(cudaGetLastError());
+        ++res->launches;
         if (n_real > 0) {
-            const dim3 g(chunks_here, static_cast<unsigned>((n_real + kMomTile - 1) / kMomTile));
-            k_row_moments<<<g, kBlock, 0, e->compute>>>(a.real_rows, a.w, cap, n_here, n_real, a.partials, n_cols);
+            const dim3 g(subs_here, static_cast<unsigned>((n_real + kMomTile - 1) / kMomTile));
+            k_row_moments<<<g, kBlock, 0, e->compute>>>(a.real_rows, a.w, cap, n_here, kSubChunk, n_real, a.partials, n_cols);
             CU_TRY(cudaGetLastError());
             ++res->launches;
         }
         if (n_int > 0) {
-            CU_TRY(launch_hist_all(e->compute, chunks_here, n_int, a.int_rows, a.w, cap, n_here, hw, kBaseCols + 2 * n_real,
+            CU_TRY(launch_hist_all(e->compute, subs_here, kSubChunk, n_int, a.int_rows, a.w, cap, n_here, hw, kBaseCols + 2 * n_real,
                                    a.partials, n_cols, &res->launches));
         }
         if (emit) {
@@ -551,7 +570,7 @@ int run_full(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, const do
         total_ms += res.device_ms;
         launches += res.launches;
         double merge_ms = 0.0;
-        const int rc = merge_impl(e, e->d_partials.ptr, res.plan.n_chunks_total, res.n_cols, static_cast<int>(e->structure.n_real),
+        const int rc = merge_impl(e, e->d_partials.ptr, res.n_rows_total, res.n_cols, static_cast<int>(e->structure.n_real),
                                   static_cast<int>(e->structure.n_int), res.hw, res.m_ref, n, out, &launches, &merge_ms);
         if (rc < 0) return rc;
         total_ms += merge_ms;
@@ -690,7 +709,7 @@ void cpprob_sis_destroy(cpprob_sis_engine * e)
     if (e->compute) cudaStreamSynchronize(e->compute);
     if (e->copy) cudaStreamSynchronize(e->copy);
     e->d_obs.release(); e->d_pilot.release(); e->d_partials.release(); e->d_merged.release(); e->d_gather.release();
-    e->d_counter.release(); e->h_merged.release();
+    e->d_counter.release(); e->d_int_extra.release(); e->h_merged.release();
     for (int i = 0; i < 2; ++i) {
         e->d_w[i].release(); e->d_logw[i].release(); e->d_real[i].release(); e->d_int[i].release();
         e->h_real[i].release(); e->h_logw[i].release(); e->h_int[i].release();
@@ -747,9 +766,10 @@ int cpprob_sis_run_shard(cpprob_sis_engine * e, int model_id, const double * obs
     shard_options so;
     if (int rc = run_shard_impl(e, vt, obs, n_obs, n_particles_total, rank, world, m_ref_override, nullptr, so, &res)) return rc;
     out->device_ptr = e->d_partials.ptr;
-    out->n_chunks_local = res.plan.n_chunks_local;
-    out->n_chunks_total = res.plan.n_chunks_total;
-    out->chunk_first = res.plan.chunk_first;
+    out->n_chunks_local = res.n_rows_local;
+    out->n_chunks_total = res.n_rows_total;
+    out->chunk_first = res.row_first;
+    out->rows_per_chunk = res.rows_per_chunk;
     out->n_cols = res.n_cols;
     out->m_ref = res.m_ref;
     out->device_ms = res.device_ms;
@@ -849,7 +869,7 @@ int cpprob_sis_reduce_records(cpprob_sis_engine * e, const double * real_rows, i
         hw.bins = static_cast<int>(span);
     }
     const int n_cols = kBaseCols + 2 * n_real + n_int * hw.bins;
-    const unsigned n_chunks = static_cast<unsigned>((n + kChunk - 1) / kChunk);
+    const unsigned n_chunks = static_cast<unsigned>((n + kSubChunk - 1) / kSubChunk);
     CU_TRY(e->d_real[0].reserve(std::max<size_t>(1, static_cast<size_t>(n_real) * stride)));
     CU_TRY(e->d_int[0].reserve(std::max<size_t>(1, static_cast<size_t>(n_int) * stride)));
     CU_TRY(e->d_logw[0].reserve(n));
@@ -863,17 +883,17 @@ int cpprob_sis_reduce_records(cpprob_sis_engine * e, const double * real_rows, i
     CU_TRY(cudaEventRecord(e->ev_begin, e->compute));
     k_max_array<<<1, kBlock, 0, e->compute>>>(e->d_logw[0].ptr, n, e->d_pilot.ptr);
     CU_TRY(cudaGetLastError());
-    k_reduce_logw<<<n_chunks, kBlock, 0, e->compute>>>(e->d_logw[0].ptr, n, e->d_pilot.ptr, e->d_w[0].ptr, e->d_partials.ptr, n_cols);
+    k_row_base<<<n_chunks, kBlock, 0, e->compute>>>(e->d_logw[0].ptr, n, kSubChunk, e->d_pilot.ptr, e->d_w[0].ptr, nullptr, e->d_partials.ptr, n_cols);
     CU_TRY(cudaGetLastError());
     launches += 2;
     if (n_real > 0) {
         const dim3 g(n_chunks, static_cast<unsigned>((n_real + kMomTile - 1) / kMomTile));
-        k_row_moments<<<g, kBlock, 0, e->compute>>>(e->d_real[0].ptr, e->d_w[0].ptr, stride, n, n_real, e->d_partials.ptr, n_cols);
+        k_row_moments<<<g, kBlock, 0, e->compute>>>(e->d_real[0].ptr, e->d_w[0].ptr, stride, n, kSubChunk, n_real, e->d_partials.ptr, n_cols);
         CU_TRY(cudaGetLastError());
         ++launches;
     }
     if (n_int > 0) {
-        CU_TRY(launch_hist_all(e->compute, n_chunks, n_int, e->d_int[0].ptr, e->d_w[0].ptr, stride, n, hw, kBaseCols + 2 * n_real,
+        CU_TRY(launch_hist_all(e->compute, n_chunks, kSubChunk, n_int, e->d_int[0].ptr, e->d_w[0].ptr, stride, n, hw, kBaseCols + 2 * n_real,
                                e->d_partials.ptr, n_cols, &launches));
     }
     CU_TRY(cudaEventRecord(e->ev_end, e->compute));

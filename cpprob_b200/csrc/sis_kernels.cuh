@@ -34,7 +34,8 @@ namespace engine {
 
 constexpr int kBlock = 256;                 // threads per CTA
 constexpr int kWarps = kBlock / 32;
-constexpr unsigned kChunk = 1u << 15;       // particles per deterministic reduction unit
+constexpr unsigned kChunk = 1u << 15;       // particles per deterministic reduction unit (fused kernel, shard granularity)
+constexpr unsigned kSubChunk = 1u << 12;    // particles per partial row on the row (SoA) path; kChunk / kSubChunk rows per chunk
 constexpr int kBaseCols = 8;                // partial columns every run has (see col:: below)
 constexpr int kPilot = 4096;                // pilot particles (global indices [0, kPilot))
 constexpr int kMomTile = 8;                 // real rows per k_row_moments CTA
@@ -48,6 +49,8 @@ constexpr unsigned long long kMaxColsMask = (1ull << col::max_lw) | (1ull << col
 
 static_assert(kBlock == static_cast<int>(kPairStride), "one CTA row of threads per half stream tile");
 static_assert(kChunk % (2 * kPairStride) == 0, "chunks hold whole stream tiles");
+
+struct int_extra;
 
 struct run_args {
     philox_keys keys;                    // expanded Philox round keys of the run's seed
@@ -69,6 +72,9 @@ struct run_args {
     // histogram window for int predicts (from the pilot)
     long long hist_lo;
     int hist_bins;
+    // row path: particles per partial row (sub-chunk) and the per-sub-chunk int bookkeeping
+    unsigned chunk;
+    struct int_extra * int_extras;       // [n_sub_chunks] or nullptr when the model has no int predicts
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -395,62 +401,61 @@ __global__ void __launch_bounds__(kBlock, NR == 1 ? CPPROB_FUSED_MIN_BLOCKS : 1)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2 k_sis_rows: model body, SoA trace rows + logw + w written to HBM, base sums reduced.
-// The per-row estimator sums are formed afterwards by k_row_moments / k_row_hist.
+// K2 k_sis_rows: model body -> SoA trace rows + log_w in HBM.  No reduction happens here, so the work
+// unit is one stream tile (512 particles, two per thread) and tiles are spread over the grid with a
+// plain stride: a batch of long traces (hmm<1000>: 4 KB per particle) still fills every SM even when
+// it holds only a handful of reduction chunks.  The int range / out-of-window bookkeeping is folded
+// into per-sub-chunk integers with order-independent integer atomics (deterministic).
+// The weights, the base sums and the per-row estimator sums are formed afterwards by k_row_base,
+// k_row_moments and k_row_hist, which stream the rows back (HBM/L2-bound, FP64 pipe nearly idle).
 // ------------------------------------------------------------------------------------------------
+struct int_extra { int vmin, vmax; unsigned oor, pad; };
+
 template<class Model>
 __global__ void __launch_bounds__(kBlock) k_sis_rows(const __grid_constant__ run_args a)
 {
-    __shared__ double smem[kWarps * kBaseCols];
-    __shared__ unsigned s_chunk;
+    constexpr unsigned kTile = 2 * kPairStride;
     const Model model{};
-    const double m_ref = *a.m_ref;
     const obs_cache<Model> oc(a.obs, a.n_obs);
+    const unsigned n_tiles = static_cast<unsigned>((a.n_particles + kTile - 1) / kTile);
+    const unsigned long long stream0 = stream_of_particle(a.first_particle) + threadIdx.x;
 
-    for (;;) {
-        const unsigned c = fetch_chunk(a.chunk_counter, &s_chunk);
-        if (c >= a.n_chunks) break;
-        const unsigned long long base = static_cast<unsigned long long>(c) * kChunk;
+    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const unsigned long long base = static_cast<unsigned long long>(tile) * kTile;
         const unsigned long long left = a.n_particles - base;
-        const unsigned n_here = left < kChunk ? static_cast<unsigned>(left) : kChunk;
-
-        double max_lw = dm::neg_inf(), s0 = 0.0, s00 = 0.0;
-        unsigned n_neginf = 0, n_nan = 0, oor = 0;
-        long long imin = 0x7fffffffffffffffLL, imax = -0x7fffffffffffffffLL - 1;
-
-        for_each_owned_particle(a.keys, a.first_particle + base, n_here, [&](philox_stream & rng, unsigned i) {
-            const unsigned long long colidx = base + i;
-            row_policy pol(a.real_rows + colidx, a.int_rows + colidx, a.row_stride, a.hist_lo, a.hist_bins);
-            particle<row_policy> p(rng, pol);
-            invoke_model(model, p, oc.data(), a.n_obs);
-            const double lw = p.log_w();
-            const double w = dm::exp_weight(lw - m_ref);
-            a.logw[colidx] = lw;
-            a.w[colidx] = w;
-            max_lw = lw > max_lw ? lw : max_lw;
-            if (__builtin_expect(!is_finite(lw), 0)) {
-                n_neginf += is_neg_inf(lw) ? 1u : 0u;
-                n_nan += is_nan(lw) ? 1u : 0u;
+        const unsigned n_here = left < kTile ? static_cast<unsigned>(left) : kTile;
+        int vmin = 0x7fffffff, vmax = static_cast<int>(0x80000000u);
+        unsigned oor = 0;
+        if (threadIdx.x < n_here) {
+            philox_stream rng(a.keys, stream0 + static_cast<unsigned long long>(tile) * kPairStride);
+#pragma unroll 1
+            for (unsigned turn = 0; turn < 2; ++turn) {
+                const unsigned i = threadIdx.x + turn * kPairStride;
+                if (i < n_here) {
+                    const unsigned long long colidx = base + i;
+                    row_policy pol(a.real_rows + colidx, a.int_rows + colidx, a.row_stride, a.hist_lo, a.hist_bins);
+                    particle<row_policy> p(rng, pol);
+                    invoke_model(model, p, oc.data(), a.n_obs);
+                    a.logw[colidx] = p.log_w();
+                    oor += pol.oor;
+                    vmin = pol.imin < vmin ? static_cast<int>(pol.imin) : vmin;
+                    vmax = pol.imax > vmax ? static_cast<int>(pol.imax) : vmax;
+                }
             }
-            s0 += w;
-            s00 = fma(w, w, s00);
-            oor += pol.oor;
-            imin = pol.imin < imin ? pol.imin : imin;
-            imax = pol.imax > imax ? pol.imax : imax;
-        });
-
-        double v[kBaseCols];
-        v[col::max_lw] = max_lw;
-        v[col::s0] = s0;
-        v[col::s00] = s00;
-        v[col::n_neginf] = static_cast<double>(n_neginf);
-        v[col::neg_imin] = imin <= imax ? -static_cast<double>(imin) : dm::neg_inf();
-        v[col::imax] = imin <= imax ? static_cast<double>(imax) : dm::neg_inf();
-        v[col::int_oor] = static_cast<double>(oor);
-        v[col::n_nan] = static_cast<double>(n_nan);
-        const double r = block_reduce<kBaseCols>(v, kMaxColsMask, smem);
-        if (threadIdx.x < kBaseCols) {
-            a.partials[static_cast<size_t>(c) * a.n_cols + threadIdx.x] = r;
+        }
+        if (a.int_extras != nullptr) {
+            // a tile never straddles a sub-chunk (sub-chunk sizes are multiples of 512)
+            vmin = __reduce_min_sync(0xffffffffu, vmin);
+            vmax = __reduce_max_sync(0xffffffffu, vmax);
+            oor = __reduce_add_sync(0xffffffffu, oor);
+            if ((threadIdx.x & 31) == 0) {
+                int_extra * x = a.int_extras + base / a.chunk;
+                if (vmin <= vmax) {
+                    atomicMin(&x->vmin, vmin);
+                    atomicMax(&x->vmax, vmax);
+                }
+                if (oor) atomicAdd(&x->oor, oor);
+            }
         }
     }
 }

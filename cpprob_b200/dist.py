@@ -9,16 +9,18 @@ import torch.distributed as dist
 from . import capi
 
 
-def shard_sizes(n_total, world):
-    """n_chunks_local of every rank (host arithmetic of cpprob_sis_plan_shard)."""
-    return [capi.plan_shard(n_total, r, world)[1] for r in range(world)]
+def shard_sizes(n_total, world, rows_per_chunk=1):
+    """partial rows of every rank (host arithmetic of cpprob_sis_plan_shard); a rank's rows are
+    ceil(n_local / (CHUNK / rows_per_chunk))."""
+    row_particles = capi.CHUNK // rows_per_chunk
+    return [-(-capi.plan_shard(n_total, r, world)[4] // row_particles) for r in range(world)]
 
 
-def gather_partials(local, n_total, world, scratch=None):
+def gather_partials(local, n_total, world, scratch=None, rows_per_chunk=1):
     """local: [n_chunks_local, n_cols] float64 tensor of this rank.  Returns [n_chunks_total, n_cols] with
     every rank's rows in chunk order.  Shards differ by at most one chunk, so rows are padded to the
     largest shard for a single all_gather_into_tensor."""
-    sizes = shard_sizes(n_total, world)
+    sizes = shard_sizes(n_total, world, rows_per_chunk)
     if world == 1:
         return local
     max_local = max(sizes)

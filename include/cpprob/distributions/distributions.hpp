@@ -161,6 +161,24 @@ struct logpdf<uniform_smallint<IntType>> {
 // -------------------------------------------------------------------------------------------------
 // discrete (weights held inline, capacity MaxK; normalised on construction like Boost's)
 // -------------------------------------------------------------------------------------------------
+// Small constant table held in registers; operator[] is a select chain, so a per-lane index costs
+// neither local memory nor a divergent constant-bank load.
+template<class T, int N>
+struct reg_table {
+    T v[N];
+    CPPROB_HD T operator[](std::size_t i) const
+    {
+        T r = v[0];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int j = 1; j < N; ++j) if (i == static_cast<std::size_t>(j)) r = v[j];
+        return r;
+    }
+    CPPROB_HD const T * begin() const { return v; }
+    CPPROB_HD const T * end() const { return v + N; }
+};
+
 template<class WeightType, int MaxK>
 struct probability_array {
     WeightType p[MaxK];
@@ -184,6 +202,29 @@ public:
     CPPROB_HD discrete_distribution(Iter first, Iter last) { init(first, last); }
 
     CPPROB_HD discrete_distribution(std::initializer_list<WeightType> w) { init(w.begin(), w.end()); }
+
+    // from a register table: no pointer into the table is formed, so it never leaves the register file
+    template<int N>
+    CPPROB_HD discrete_distribution(const reg_table<WeightType, N> & w)
+    {
+        static_assert(N <= MaxK, "table larger than the distribution's capacity");
+        WeightType sum = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int i = 0; i < N; ++i) sum += w.v[i];
+        probs_.n = N;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int i = 0; i < MaxK; ++i) probs_.p[i] = i < N ? w.v[i] : WeightType(0);
+        if (sum != WeightType(1)) {          // x / 1 == x exactly: skip the divisions when already normalised
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+            for (int i = 0; i < N; ++i) probs_.p[i] = w.v[i] / sum;
+        }
+    }
 
     CPPROB_HD IntType min() const { return 0; }
     CPPROB_HD IntType max() const { return static_cast<IntType>(probs_.n - 1); }
@@ -220,8 +261,9 @@ private:
             sum += probs_.p[n];
         }
         probs_.n = n;
-        for (int i = 0; i < MaxK; ++i) {
-            probs_.p[i] = i < n ? probs_.p[i] / sum : WeightType(0);
+        for (int i = n; i < MaxK; ++i) probs_.p[i] = WeightType(0);
+        if (sum != WeightType(1)) {          // x / 1 == x exactly: skip the divisions when already normalised
+            for (int i = 0; i < n; ++i) probs_.p[i] /= sum;
         }
     }
 

@@ -162,9 +162,10 @@ int cpprob_sis_infer_to_files(cpprob_sis_engine * e, int model_id, const double 
  * bit-identical on every rank and for every world size. */
 typedef struct cpprob_sis_partials {
     double * device_ptr;         /* [n_chunks_local][n_cols], engine-owned */
-    uint32_t n_chunks_local;
-    uint32_t n_chunks_total;
-    uint32_t chunk_first;
+    uint32_t n_chunks_local;     /* partial rows of this rank ... */
+    uint32_t n_chunks_total;     /* ... of the whole run ... */
+    uint32_t chunk_first;        /* ... and the index of this rank's first row */
+    uint32_t rows_per_chunk;     /* partial rows per 32768-particle chunk: 1 (fused kernel) or 8 (row path) */
     int n_cols;
     double m_ref;
     double device_ms;

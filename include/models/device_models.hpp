@@ -22,26 +22,6 @@
 #include "cpprob/model_binding.hpp"
 #include "cpprob/particle.hpp"
 
-namespace cpprob {
-// Small constant table held in registers; operator[] is a select chain, so a per-lane index costs
-// neither local memory nor a divergent constant-bank load.
-template<class T, int N>
-struct reg_table {
-    T v[N];
-    CPPROB_HD T operator[](std::size_t i) const
-    {
-        T r = v[0];
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-        for (int j = 1; j < N; ++j) if (i == static_cast<std::size_t>(j)) r = v[j];
-        return r;
-    }
-    CPPROB_HD const T * begin() const { return v; }
-    CPPROB_HD const T * end() const { return v + N; }
-};
-}  // namespace cpprob
-
 namespace models {
 
 // -------------------------------------------------------------------------------------------------
@@ -141,8 +121,7 @@ struct hmm_model {
         ++obs_it;
 
         for (; obs_it != observed_states.end(); ++obs_it) {
-            const auto row = T[state];
-            const ::cpprob::discrete_distribution<std::size_t, double, k> transition_distr{row.begin(), row.end()};
+            const ::cpprob::discrete_distribution<std::size_t, double, k> transition_distr{T[state]};   // {T[state].begin(), T[state].end()}
             state = cpprob.sample(transition_distr, true);
             cpprob.predict(state, "State");
             likelihood = ::cpprob::normal_distribution<>{state_mean[state], 1};
