@@ -47,7 +47,7 @@ struct model_launchers {
     }
     static cudaError_t pilot(cudaStream_t s, const philox_keys * keys, const double * obs, int n_obs, int n_pilot, double * out)
     {
-        k_pilot<Model><<<1, kBlock, 0, s>>>(*keys, obs, n_obs, n_pilot, out);
+        k_pilot<Model><<<(n_pilot + 511) / 512, kBlock, 0, s>>>(*keys, obs, n_obs, n_pilot, out);
         return cudaGetLastError();
     }
     static cudaError_t fused(cudaStream_t s, int grid, int nr, const run_args * a)

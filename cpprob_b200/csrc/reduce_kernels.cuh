@@ -19,20 +19,21 @@ __global__ void __launch_bounds__(kBlock) k_init_int_extra(int_extra * __restric
 
 // ------------------------------------------------------------------------------------------------
 // K4a k_row_moments: S1 = sum w x, S2 = sum w x^2 for kMomTile real rows of one chunk.
-// grid = (n_chunks, ceil(n_real / kMomTile)).  Each row element is read once (coalesced 8 B/lane);
-// w is re-read once per tile (L2-resident: a chunk of w is 256 KB).
+// 1-D grid of n_sub_chunks * ceil(n_real / kMomTile) CTAs, tile index fastest.  Each row element is
+// read once (coalesced 8 B/lane); w is re-read once per tile from L2 (a sub-chunk of w is 32 KB).
 // Output: partials[chunk][kBaseCols + 2*row + {0,1}].
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_row_moments(const double * __restrict__ real_rows, const double * __restrict__ w,
-                                                        unsigned long long stride, unsigned long long n_particles, unsigned chunk,
+                                                        unsigned long long stride, unsigned long long n_particles,
                                                         int n_real, double * __restrict__ partials, int n_cols)
 {
     __shared__ double smem[kWarps * 2 * kMomTile];
-    const unsigned c = blockIdx.x;
-    const int row0 = blockIdx.y * kMomTile;
-    const unsigned long long base = static_cast<unsigned long long>(c) * chunk;
+    const unsigned n_tiles = static_cast<unsigned>((n_real + kMomTile - 1) / kMomTile);
+    const unsigned c = blockIdx.x / n_tiles;
+    const int row0 = static_cast<int>(blockIdx.x % n_tiles) * kMomTile;
+    const unsigned long long base = static_cast<unsigned long long>(c) * kSubChunk;
     const unsigned long long left = n_particles - base;
-    const unsigned n_here = left < chunk ? static_cast<unsigned>(left) : chunk;
+    const unsigned n_here = left < kSubChunk ? static_cast<unsigned>(left) : kSubChunk;
 
     double acc[2 * kMomTile];
 #pragma unroll
@@ -59,22 +60,24 @@ __global__ void __launch_bounds__(kBlock) k_row_moments(const double * __restric
 
 // ------------------------------------------------------------------------------------------------
 // K4b k_row_hist<V>: weighted histogram sum_i w_i [x_i == lo + b], b < V, for one int row of one
-// chunk.  grid = (n_chunks, n_int).  V <= 8 bins live in registers; wider windows are covered by
-// several launches with shifted `lo` (bin_offset selects the output columns).
-// Output: partials[chunk][hist_col0 + row*hist_bins + bin_offset + b].
+// sub-chunk.  1-D grid of n_sub_chunks * n_int CTAs with the row index fastest, so the CTAs that share
+// a sub-chunk's weights run together and w (32 KB) is served by L2: DRAM sees each int once.
+// V <= 8 bins live in registers; wider windows are covered by several launches with shifted `lo`
+// (bin_offset selects the output columns).
+// Output: partials[sub_chunk][hist_col0 + row*hist_bins + bin_offset + b].
 // ------------------------------------------------------------------------------------------------
 template<int V>
 __global__ void __launch_bounds__(kBlock) k_row_hist(const int * __restrict__ int_rows, const double * __restrict__ w,
-                                                     unsigned long long stride, unsigned long long n_particles, unsigned chunk,
+                                                     unsigned long long stride, unsigned long long n_particles, int n_int,
                                                      long long lo, int bin_offset, int hist_bins, int hist_col0,
                                                      double * __restrict__ partials, int n_cols)
 {
     __shared__ double smem[kWarps * V];
-    const unsigned c = blockIdx.x;
-    const int row = blockIdx.y;
-    const unsigned long long base = static_cast<unsigned long long>(c) * chunk;
+    const unsigned c = blockIdx.x / static_cast<unsigned>(n_int);
+    const int row = static_cast<int>(blockIdx.x % static_cast<unsigned>(n_int));
+    const unsigned long long base = static_cast<unsigned long long>(c) * kSubChunk;
     const unsigned long long left = n_particles - base;
-    const unsigned n_here = left < chunk ? static_cast<unsigned>(left) : chunk;
+    const unsigned n_here = left < kSubChunk ? static_cast<unsigned>(left) : kSubChunk;
     const int * __restrict__ src = int_rows + static_cast<unsigned long long>(row) * stride + base;
     const double * __restrict__ wsrc = w + base;
 

@@ -194,37 +194,66 @@ struct hist_window {
 };
 
 template<int V>
-cudaError_t launch_hist(cudaStream_t s, dim3 grid, unsigned chunk, const int * rows, const double * w, unsigned long long stride,
+cudaError_t launch_hist(cudaStream_t s, unsigned grid, int n_int, const int * rows, const double * w, unsigned long long stride,
                         unsigned long long n, long long lo, int off, int bins, int col0, double * partials, int n_cols)
 {
-    k_row_hist<V><<<grid, kBlock, 0, s>>>(rows, w, stride, n, chunk, lo, off, bins, col0, partials, n_cols);
+    k_row_hist<V><<<grid, kBlock, 0, s>>>(rows, w, stride, n, n_int, lo, off, bins, col0, partials, n_cols);
     return cudaGetLastError();
 }
 
 // all histogram passes for one batch; returns number of launches through *launches
-cudaError_t launch_hist_all(cudaStream_t s, unsigned n_chunks, unsigned chunk, int n_int, const int * rows, const double * w,
+cudaError_t launch_hist_all(cudaStream_t s, unsigned n_chunks, int n_int, const int * rows, const double * w,
                             unsigned long long stride, unsigned long long n, hist_window hw, int col0,
                             double * partials, int n_cols, uint64_t * launches)
 {
-    const dim3 grid(n_chunks, static_cast<unsigned>(n_int));
+    const unsigned grid = n_chunks * static_cast<unsigned>(n_int);
     for (int off = 0; off < hw.bins; off += 8) {
         const int left = hw.bins - off;
         cudaError_t err;
         const long long lo = hw.lo + off;
         switch (left >= 8 ? 8 : left) {
-        case 1: err = launch_hist<1>(s, grid, chunk, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        case 2: err = launch_hist<2>(s, grid, chunk, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        case 3: err = launch_hist<3>(s, grid, chunk, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        case 4: err = launch_hist<4>(s, grid, chunk, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        case 5: err = launch_hist<5>(s, grid, chunk, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        case 6: err = launch_hist<6>(s, grid, chunk, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        case 7: err = launch_hist<7>(s, grid, chunk, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        default: err = launch_hist<8>(s, grid, chunk, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        case 1: err = launch_hist<1>(s, grid, n_int, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        case 2: err = launch_hist<2>(s, grid, n_int, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        case 3: err = launch_hist<3>(s, grid, n_int, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        case 4: err = launch_hist<4>(s, grid, n_int, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        case 5: err = launch_hist<5>(s, grid, n_int, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        case 6: err = launch_hist<6>(s, grid, n_int, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        case 7: err = launch_hist<7>(s, grid, n_int, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
+        default: err = launch_hist<8>(s, grid, n_int, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
         }
         if (err != cudaSuccess) return err;
         ++*launches;
     }
     return cudaSuccess;
+}
+
+// Runs the pilot and folds its per-tile maxima on the host.  pilot[0] = m_ref (finite; 0 when every pilot
+// weight is -inf / nan), pilot[1] = min int, pilot[2] = max int (min > max when there are no int predicts).
+// Leaves m_ref in e->d_pilot[0] for the kernels.
+int run_pilot(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, const philox_keys & keys, size_t n_obs, uint64_t n_total,
+              const double * m_ref_override, double pilot[3])
+{
+    const int n_pilot = static_cast<int>(std::min<uint64_t>(n_total, kPilot));
+    const int tiles = (n_pilot + 511) / 512;
+    double raw[3 * kPilotTiles];
+    CU_TRY(e->d_pilot.reserve(3 * kPilotTiles));
+    CU_TRY(vt->launch_pilot(e->compute, &keys, e->d_obs.ptr, static_cast<int>(n_obs), n_pilot, e->d_pilot.ptr));
+    CU_TRY(cudaMemcpyAsync(raw, e->d_pilot.ptr, 3 * tiles * sizeof(double), cudaMemcpyDeviceToHost, e->compute));
+    CU_TRY(cudaStreamSynchronize(e->compute));
+    double mx = -std::numeric_limits<double>::infinity(), nmin = mx, imax = mx;
+    for (int t = 0; t < tiles; ++t) {
+        mx = std::fmax(mx, raw[3 * t]);
+        nmin = std::fmax(nmin, raw[3 * t + 1]);
+        imax = std::fmax(imax, raw[3 * t + 2]);
+    }
+    pilot[0] = (mx > -1.0e300 && mx < 1.0e300) ? mx : 0.0;
+    pilot[1] = -nmin;
+    pilot[2] = imax;
+    const double m_ref = m_ref_override ? *m_ref_override : pilot[0];
+    CU_TRY(cudaMemcpyAsync(e->d_pilot.ptr, &m_ref, sizeof(double), cudaMemcpyHostToDevice, e->compute));
+    CU_TRY(cudaStreamSynchronize(e->compute));   // m_ref lives on this stack frame
+    pilot[0] = m_ref;
+    return 0;
 }
 
 struct shard_options {
@@ -263,7 +292,7 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     res->device_ms = 0.0;
 
     CU_TRY(e->d_obs.reserve(n_obs));
-    CU_TRY(e->d_pilot.reserve(4));
+    CU_TRY(e->d_pilot.reserve(3 * kPilotTiles));
     CU_TRY(e->d_counter.reserve(1));
     CU_TRY(cudaMemcpyAsync(e->d_obs.ptr, obs, n_obs * sizeof(double), cudaMemcpyHostToDevice, e->compute));
 
@@ -271,17 +300,10 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     // starts here: it covers the pilot, the particle kernel(s) and the row reductions.
     const philox_keys keys(e->seed);
     CU_TRY(cudaEventRecord(e->ev_begin, e->compute));
-    const int n_pilot = static_cast<int>(std::min<uint64_t>(n_total, kPilot));
     double pilot[3] = {0, 0, 0};
-    CU_TRY(vt->launch_pilot(e->compute, &keys, e->d_obs.ptr, static_cast<int>(n_obs), n_pilot, e->d_pilot.ptr));
+    if (int rc = run_pilot(e, vt, keys, n_obs, n_total, m_ref_override, pilot)) return rc;
     ++res->launches;
-    CU_TRY(cudaMemcpyAsync(pilot, e->d_pilot.ptr, 3 * sizeof(double), cudaMemcpyDeviceToHost, e->compute));
-    CU_TRY(cudaStreamSynchronize(e->compute));
-    double m_ref = pilot[0];
-    if (m_ref_override) {
-        m_ref = *m_ref_override;
-        CU_TRY(cudaMemcpyAsync(e->d_pilot.ptr, &m_ref, sizeof(double), cudaMemcpyHostToDevice, e->compute));
-    }
+    const double m_ref = pilot[0];
     hist_window hw;
     if (n_int > 0) {
         if (hw_override) {
@@ -426,13 +448,13 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         CU_TRY(cudaGetLastError());
         ++res->launches;
         if (n_real > 0) {
-            const dim3 g(subs_here, static_cast<unsigned>((n_real + kMomTile - 1) / kMomTile));
-            k_row_moments<<<g, kBlock, 0, e->compute>>>(a.real_rows, a.w, cap, n_here, kSubChunk, n_real, a.partials, n_cols);
+            const unsigned g = subs_here * static_cast<unsigned>((n_real + kMomTile - 1) / kMomTile);
+            k_row_moments<<<g, kBlock, 0, e->compute>>>(a.real_rows, a.w, cap, n_here, n_real, a.partials, n_cols);
             CU_TRY(cudaGetLastError());
             ++res->launches;
         }
         if (n_int > 0) {
-            CU_TRY(launch_hist_all(e->compute, subs_here, kSubChunk, n_int, a.int_rows, a.w, cap, n_here, hw, kBaseCols + 2 * n_real,
+            CU_TRY(launch_hist_all(e->compute, subs_here, n_int, a.int_rows, a.w, cap, n_here, hw, kBaseCols + 2 * n_real,
                                    a.partials, n_cols, &res->launches));
         }
         if (emit) {
@@ -796,12 +818,9 @@ int cpprob_sis_merge(cpprob_sis_engine * e, int model_id, const double * obs, si
         CU_TRY(e->d_obs.reserve(n_obs));
         CU_TRY(e->d_pilot.reserve(4));
         CU_TRY(cudaMemcpyAsync(e->d_obs.ptr, obs, n_obs * sizeof(double), cudaMemcpyHostToDevice, e->compute));
-        const int n_pilot = static_cast<int>(std::min<uint64_t>(n_particles_total, kPilot));
         const philox_keys keys(e->seed);
         double pilot[3];
-        CU_TRY(vt->launch_pilot(e->compute, &keys, e->d_obs.ptr, static_cast<int>(n_obs), n_pilot, e->d_pilot.ptr));
-        CU_TRY(cudaMemcpyAsync(pilot, e->d_pilot.ptr, 3 * sizeof(double), cudaMemcpyDeviceToHost, e->compute));
-        CU_TRY(cudaStreamSynchronize(e->compute));
+        if (int rc = run_pilot(e, vt, keys, n_obs, n_particles_total, nullptr, pilot)) return rc;
         hw.lo = pilot[1] <= pilot[2] ? static_cast<long long>(pilot[1]) : 0;
     }
     uint64_t launches = 0;
@@ -887,13 +906,13 @@ int cpprob_sis_reduce_records(cpprob_sis_engine * e, const double * real_rows, i
     CU_TRY(cudaGetLastError());
     launches += 2;
     if (n_real > 0) {
-        const dim3 g(n_chunks, static_cast<unsigned>((n_real + kMomTile - 1) / kMomTile));
-        k_row_moments<<<g, kBlock, 0, e->compute>>>(e->d_real[0].ptr, e->d_w[0].ptr, stride, n, kSubChunk, n_real, e->d_partials.ptr, n_cols);
+        const unsigned g = n_chunks * static_cast<unsigned>((n_real + kMomTile - 1) / kMomTile);
+        k_row_moments<<<g, kBlock, 0, e->compute>>>(e->d_real[0].ptr, e->d_w[0].ptr, stride, n, n_real, e->d_partials.ptr, n_cols);
         CU_TRY(cudaGetLastError());
         ++launches;
     }
     if (n_int > 0) {
-        CU_TRY(launch_hist_all(e->compute, n_chunks, kSubChunk, n_int, e->d_int[0].ptr, e->d_w[0].ptr, stride, n, hw, kBaseCols + 2 * n_real,
+        CU_TRY(launch_hist_all(e->compute, n_chunks, n_int, e->d_int[0].ptr, e->d_w[0].ptr, stride, n, hw, kBaseCols + 2 * n_real,
                                e->d_partials.ptr, n_cols, &launches));
     }
     CU_TRY(cudaEventRecord(e->ev_end, e->compute));

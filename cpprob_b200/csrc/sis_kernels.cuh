@@ -38,6 +38,7 @@ constexpr unsigned kChunk = 1u << 15;       // particles per deterministic reduc
 constexpr unsigned kSubChunk = 1u << 12;    // particles per partial row on the row (SoA) path; kChunk / kSubChunk rows per chunk
 constexpr int kBaseCols = 8;                // partial columns every run has (see col:: below)
 constexpr int kPilot = 4096;                // pilot particles (global indices [0, kPilot))
+constexpr int kPilotTiles = kPilot / 512;   // one CTA each
 constexpr int kMomTile = 8;                 // real rows per k_row_moments CTA
 constexpr int kMaxFusedReal = 4;            // register-staged predict slots in the fused kernel
 
@@ -305,19 +306,23 @@ private:
 };
 
 // ------------------------------------------------------------------------------------------------
-// K_pilot: max log_w and int-predict range over global particles [0, n_pilot).  One CTA.
-// out[0] = m_ref (finite; 0 if every pilot weight is -inf / nan), out[1] = imin, out[2] = imax
-// (as doubles; imin > imax when the model has no int predicts).
+// K_pilot: max log_w and int-predict range over global particles [0, n_pilot).  One CTA per stream
+// tile (512 particles), so that long traces (hmm<1000>) do not serialise on a single SM.
+// out[3*cta + {0,1,2}] = max log_w, max(-int), max(int) of that tile (-inf where there is none); the
+// host takes the maximum over the kPilot/512 tiles (max is order-independent: deterministic).
 // ------------------------------------------------------------------------------------------------
 template<class Model>
 __global__ void __launch_bounds__(kBlock) k_pilot(const __grid_constant__ philox_keys keys, const double * __restrict__ obs,
                                                   int n_obs, int n_pilot, double * __restrict__ out)
 {
+    constexpr unsigned kTile = 2 * kPairStride;
     __shared__ double smem[kWarps * 3];
     const Model model{};
     const obs_cache<Model> oc(obs, n_obs);
     double v[3] = {dm::neg_inf(), dm::neg_inf(), dm::neg_inf()};   // max lw, max(-imin), max(imax)
-    for_each_owned_particle(keys, 0ull, static_cast<unsigned>(n_pilot), [&](philox_stream & rng, unsigned) {
+    const unsigned base = blockIdx.x * kTile;
+    const unsigned n_here = static_cast<unsigned>(n_pilot) > base ? min(static_cast<unsigned>(n_pilot) - base, kTile) : 0u;
+    for_each_owned_particle(keys, static_cast<unsigned long long>(base), n_here, [&](philox_stream & rng, unsigned) {
         null_policy pol;
         particle<null_policy> p(rng, pol);
         invoke_model(model, p, oc.data(), n_obs);
@@ -328,9 +333,7 @@ __global__ void __launch_bounds__(kBlock) k_pilot(const __grid_constant__ philox
         }
     });
     const double r = block_reduce<3>(v, 0x7ull, smem);
-    if (threadIdx.x == 0) out[0] = (r > -1.0e300 && r < 1.0e300) ? r : 0.0;
-    if (threadIdx.x == 1) out[1] = -r;
-    if (threadIdx.x == 2) out[2] = r;
+    if (threadIdx.x < 3) out[3 * blockIdx.x + threadIdx.x] = r;
 }
 
 // ------------------------------------------------------------------------------------------------
