@@ -25,7 +25,7 @@ SYMBOLS = [
     "cpprob_sis_describe", "cpprob_sis_run", "cpprob_sis_infer_to_files", "cpprob_sis_run_shard",
     "cpprob_sis_merge", "cpprob_sis_replay", "cpprob_sis_reduce_records", "cpprob_sis_logpdf",
     "cpprob_sis_sample", "cpprob_sis_philox", "cpprob_sis_dmath", "cpprob_sis_measure_dfma_peak",
-    "cpprob_sis_measure_store_peak", "cpprob_sis_plan_shard", "cpprob_sis_probe_issue",
+    "cpprob_sis_measure_store_peak", "cpprob_sis_plan_shard", "cpprob_sis_probe_issue", "cpprob_sis_probe_dfma_chains",
 ]
 
 
@@ -111,6 +111,7 @@ def lib():
         L.cpprob_sis_measure_dfma_peak.argtypes = [C.c_void_p, dp, dp]
         L.cpprob_sis_measure_store_peak.argtypes = [C.c_void_p, dp]
         L.cpprob_sis_probe_issue.argtypes = [C.c_void_p, C.c_int, dp]
+        L.cpprob_sis_probe_dfma_chains.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, dp]
         L.cpprob_sis_plan_shard.argtypes = [u64, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                             C.POINTER(u64), C.POINTER(u64)]
         _lib = L
@@ -309,6 +310,11 @@ class Engine:
         ms = C.c_double()
         _check(self._L.cpprob_sis_probe_issue(self._h, int_per_dfma, C.byref(ms)))
         return ms.value
+
+    def probe_dfma_chains(self, chains, blocks_per_sm):
+        ms, n = C.c_double(), C.c_double()
+        _check(self._L.cpprob_sis_probe_dfma_chains(self._h, chains, blocks_per_sm, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def store_peak(self):
         g = C.c_double()

@@ -188,6 +188,26 @@ __global__ void __launch_bounds__(kBlock) k_dfma_peak(double * __restrict__ out,
     if (s == 123.456) out[blockIdx.x * kBlock + threadIdx.x] = s;   // never true; keeps the chain alive
 }
 
+// Latency probe: C independent DFMA chains per thread (C = 1, 2, 4, 8), `iters` x 32 DFMA per chain.
+template<int C>
+__global__ void __launch_bounds__(kBlock) k_dfma_chains(double * __restrict__ out, int iters, double a, double b)
+{
+    double x[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) x[c] = threadIdx.x + c;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) x[c] = fma(x[c], a, b);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) s += x[c];
+    if (s == 123.456) out[blockIdx.x * kBlock + threadIdx.x] = s;
+}
+
 // Issue-model probe: the same 8 DFMA chains with NI independent integer (ALU-pipe) instructions per DFMA
 // interleaved.  If time does not grow with NI <= 1 the FP64 pipe co-issues with the ALU pipe; if it
 // grows by ~50% per NI, an FP64 warp instruction holds the issue port for both of its cycles.

@@ -1055,6 +1055,37 @@ int cpprob_sis_measure_dfma_peak(cpprob_sis_engine * e, double * tflops, double 
     return 0;
 }
 
+// chains: independent DFMA chains per thread (1,2,4,8); blocks_per_sm CTAs of 256 threads per SM.
+// Returns DFMA warp-instructions per cycle per SM sub-partition assuming `sm_mhz`.
+int cpprob_sis_probe_dfma_chains(cpprob_sis_engine * e, int chains, int blocks_per_sm, double * ms_out, double * dfma_per_thread)
+{
+    if (!e || !ms_out) return fail(CPPROB_SIS_EINVAL, "bad argument");
+    if (int rc = use_device(e)) return rc;
+    const int grid = e->sm_count * blocks_per_sm;
+    CU_TRY(e->d_w[0].reserve(static_cast<size_t>(grid) * kBlock));
+    const int iters = 1024;
+    double best_ms = 1e30;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU_TRY(cudaEventRecord(e->ev_begin, e->compute));
+        switch (chains) {
+        case 1: k_dfma_chains<1><<<grid, kBlock, 0, e->compute>>>(e->d_w[0].ptr, iters, 0.999999, 1.0e-6); break;
+        case 2: k_dfma_chains<2><<<grid, kBlock, 0, e->compute>>>(e->d_w[0].ptr, iters, 0.999999, 1.0e-6); break;
+        case 4: k_dfma_chains<4><<<grid, kBlock, 0, e->compute>>>(e->d_w[0].ptr, iters, 0.999999, 1.0e-6); break;
+        default: k_dfma_chains<8><<<grid, kBlock, 0, e->compute>>>(e->d_w[0].ptr, iters, 0.999999, 1.0e-6); break;
+        }
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaEventRecord(e->ev_end, e->compute));
+        CU_TRY(cudaStreamSynchronize(e->compute));
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));
+        if (rep > 0) best_ms = std::min<double>(best_ms, ms);
+        ++e->launches;
+    }
+    *ms_out = best_ms;
+    if (dfma_per_thread) *dfma_per_thread = static_cast<double>(iters) * 32.0 * (chains == 1 || chains == 2 || chains == 4 ? chains : 8);
+    return 0;
+}
+
 int cpprob_sis_probe_issue(cpprob_sis_engine * e, int int_per_dfma, double * ms_out)
 {
     if (!e || !ms_out || int_per_dfma < 0 || int_per_dfma > 3) return fail(CPPROB_SIS_EINVAL, "bad argument");

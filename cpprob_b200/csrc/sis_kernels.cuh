@@ -26,10 +26,10 @@ namespace cpprob {
 namespace engine {
 
 #ifndef CPPROB_TILES_PER_TRIP
-#define CPPROB_TILES_PER_TRIP 1             // stream tiles (pairs of particles per thread) per loop trip
+#define CPPROB_TILES_PER_TRIP 2             // stream tiles (pairs of particles per thread) per loop trip
 #endif
 #ifndef CPPROB_FUSED_MIN_BLOCKS
-#define CPPROB_FUSED_MIN_BLOCKS 4           // resident CTAs per SM the fused kernel is compiled for
+#define CPPROB_FUSED_MIN_BLOCKS 2           // resident CTAs per SM the fused kernel is compiled for (<= 128 registers)
 #endif
 
 constexpr int kBlock = 256;                 // threads per CTA
@@ -358,23 +358,23 @@ __global__ void __launch_bounds__(kBlock, NR == 1 ? CPPROB_FUSED_MIN_BLOCKS : 1)
         const unsigned long long left = a.n_particles - base;
         const unsigned n_here = left < kChunk ? static_cast<unsigned>(left) : kChunk;
 
-        double max_lw = dm::neg_inf(), s0 = 0.0, s00 = 0.0;
-        unsigned n_neginf = 0, n_nan = 0;
+        double max_lw, s0, s00;
+        unsigned n_neginf, n_nan;
         double s1[NR], s2[NR];
+        // Fast pass: weights by exp_weight_unchecked, no per-particle special-case handling; only the
+        // smallest exponent k and the largest exponent field of log_w are tracked (2-3 ALU instructions
+        // per particle).  If any particle of the chunk had a non-finite log_w or a weight below the
+        // normal range, the whole chunk is recomputed by the careful pass.  The choice depends only on
+        // the chunk's own data, so results stay deterministic.
+        int k_min = 0;
+        unsigned exp_max = 0;
+        auto reset = [&] {
+            max_lw = dm::neg_inf(); s0 = 0.0; s00 = 0.0; n_neginf = 0; n_nan = 0;
 #pragma unroll
-        for (int j = 0; j < NR; ++j) { s1[j] = 0.0; s2[j] = 0.0; }
-
-        for_each_owned_particle(a.keys, a.first_particle + base, n_here, [&](philox_stream & rng, unsigned) {
-            reg_policy<NR> pol;
-            particle<reg_policy<NR>> p(rng, pol);
-            invoke_model(model, p, oc.data(), a.n_obs);
-            const double lw = p.log_w();
-            const double w = dm::exp_weight(lw - m_ref);
+            for (int j = 0; j < NR; ++j) { s1[j] = 0.0; s2[j] = 0.0; }
+        };
+        auto accumulate = [&](double lw, double w, const reg_policy<NR> & pol) {
             max_lw = lw > max_lw ? lw : max_lw;
-            if (__builtin_expect(!is_finite(lw), 0)) {
-                n_neginf += is_neg_inf(lw) ? 1u : 0u;
-                n_nan += is_nan(lw) ? 1u : 0u;
-            }
             s0 += w;
             s00 = fma(w, w, s00);
 #pragma unroll
@@ -383,7 +383,32 @@ __global__ void __launch_bounds__(kBlock, NR == 1 ? CPPROB_FUSED_MIN_BLOCKS : 1)
                 s1[j] += wx;
                 s2[j] = fma(wx, pol.v[j], s2[j]);
             }
+        };
+        reset();
+        for_each_owned_particle(a.keys, a.first_particle + base, n_here, [&](philox_stream & rng, unsigned) {
+            reg_policy<NR> pol;
+            particle<reg_policy<NR>> p(rng, pol);
+            invoke_model(model, p, oc.data(), a.n_obs);
+            const double lw = p.log_w();
+            int k;
+            const double w = dm::exp_weight_unchecked(lw - m_ref, k);
+            k_min = min(k_min, k);
+            exp_max = max(exp_max, static_cast<unsigned>(__double2hiint(lw)) & 0x7FF00000u);
+            accumulate(lw, w, pol);
         });
+        if (__syncthreads_or(k_min < -1021 || exp_max == 0x7FF00000u)) {
+            reset();
+            for_each_owned_particle(a.keys, a.first_particle + base, n_here, [&](philox_stream & rng, unsigned) {
+                reg_policy<NR> pol;
+                particle<reg_policy<NR>> p(rng, pol);
+                invoke_model(model, p, oc.data(), a.n_obs);
+                const double lw = p.log_w();
+                const double w = dm::exp_weight(lw - m_ref);
+                n_neginf += is_neg_inf(lw) ? 1u : 0u;
+                n_nan += is_nan(lw) ? 1u : 0u;
+                accumulate(lw, w, pol);
+            });
+        }
 
         double v[NV];
         v[col::max_lw] = max_lw;

@@ -240,6 +240,25 @@ __device__ __forceinline__ double exp_weight(double x)
     return e * __hiloint2double(biased << 20, 0);
 }
 
+// Fast-path variant for the fused kernel: no clamp, 2^k applied by adding k to the exponent field.
+// Valid only when x is finite and the result is a normal number (k >= -1021); the caller tracks the
+// smallest k and the exponent field of x per chunk and recomputes the chunk with exp_weight otherwise.
+__device__ __forceinline__ double exp_weight_unchecked(double x, int & k_out)
+{
+    const double magic = tbl::k_round_magic;
+    const double t = fma(x, tbl::k_log2e, magic);
+    const int k = __double2loint(t);
+    const double kf = t - magic;
+    double r = fma(kf, -tbl::k_ln2_hi, x);
+    r = fma(kf, -tbl::k_ln2_lo, r);
+    double q = tbl::exp_q[9];
+#pragma unroll
+    for (int i = 8; i >= 0; --i) q = fma(q, r, tbl::exp_q[i]);
+    const double e = fma(r * r, q, r) + 1.0;
+    k_out = k;
+    return __hiloint2double(__double2hiint(e) + (k << 20), __double2loint(e));
+}
+
 __device__ __forceinline__ double lgamma(double x) { return ::lgamma(x); }
 __device__ __forceinline__ double pow(double a, double b) { return ::pow(a, b); }
 __device__ __forceinline__ double floor(double x) { return ::floor(x); }
@@ -262,6 +281,7 @@ inline double cos_2pi(double u) { return std::cos(two_pi * u); }
 inline double sin_2pi(double u) { return std::sin(two_pi * u); }
 inline double exp(double x) { return std::exp(x); }
 inline double exp_weight(double x) { return x != x ? 0.0 : std::exp(x); }
+inline double exp_weight_unchecked(double x, int & k_out) { k_out = 0; return std::exp(x); }
 inline double lgamma(double x) { return std::lgamma(x); }
 inline double pow(double a, double b) { return std::pow(a, b); }
 inline double floor(double x) { return std::floor(x); }

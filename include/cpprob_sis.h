@@ -224,6 +224,8 @@ int cpprob_sis_measure_dfma_peak(cpprob_sis_engine * e, double * tflops, double 
 int cpprob_sis_measure_store_peak(cpprob_sis_engine * e, double * gbytes_per_s);
 /* issue-model probe: time of a fixed DFMA workload with `int_per_dfma` (0..3) ALU instructions interleaved per DFMA */
 int cpprob_sis_probe_issue(cpprob_sis_engine * e, int int_per_dfma, double * ms_out);
+/* latency probe: `chains` (1,2,4,8) independent DFMA chains per thread, blocks_per_sm CTAs of 256 threads per SM */
+int cpprob_sis_probe_dfma_chains(cpprob_sis_engine * e, int chains, int blocks_per_sm, double * ms_out, double * dfma_per_thread);
 
 #ifdef __cplusplus
 }

@@ -47,15 +47,23 @@ def particle_loop(body, marker="MUFU.RSQ64H"):
         if m:
             instr.append((int(m.group(1), 16), m.group(2)))
     marks = [a for a, t in instr if marker in t]
-    best = None
+    best, best_key = None, None
     for a, t in instr:
         m = re.search(r"\bBRA\s+(?:\w+,\s*)?0x([0-9a-f]+)", t)
         if not m:
             continue
         tgt = int(m.group(1), 16)
-        if tgt < a and any(tgt <= x <= a for x in marks):
-            if best is None or (a - tgt) < (best[1] - best[0]):
-                best = (tgt, a)
+        n_marks = sum(1 for x in marks if tgt <= x <= a)
+        if tgt < a and n_marks:
+            # the hot loop is the one with the most sampler invocations per trip that is still innermost:
+            # reject spans that contain another backward branch (outer loops)
+            inner_back = any(tgt < a2 < a and (mm := re.search(r"\bBRA\s+(?:\w+,\s*)?0x([0-9a-f]+)", t2)) and int(mm.group(1), 16) < a2
+                             and int(mm.group(1), 16) >= tgt for a2, t2 in instr)
+            if inner_back:
+                continue
+            key = (n_marks, -(a - tgt))
+            if best_key is None or key > best_key:
+                best, best_key = (tgt, a), key
     return best
 
 
@@ -69,6 +77,8 @@ def loop_budget(path, needle):
         if m and lo <= int(m.group(1), 16) <= hi:
             c["total"] += 1
             base = m.group(2).split(".")[0]
+            if m.group(2).startswith("MUFU.RSQ64H"):
+                c["box_muller"] += 1            # one per stream pair = 2 particles
             if classify(m.group(2)) == "fp64":
                 c["fp64"] += 1
             if base in ("DFMA", "DADD", "DMUL", "DSETP"):
