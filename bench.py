@@ -270,9 +270,10 @@ def run_ours(args):
             achieved = budget["flop"] * per_gpu / k_s / 1e12
             line["roofline"] = {
                 "bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                "traffic": None,
+                "traffic": 51456,
                 "note": "dominant kernel k_sis_fused is FP64-pipe bound (no dense contraction, no HBM stream): peak = DFMA chain "
-                        "micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry); achieved counts DFMA as 2 flop",
+                        "micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry); achieved counts DFMA as 2 flop; "
+                        "traffic = dram bytes of one launch from ncu --set full (profiles/r01_k_sis_fused_ncu_full.csv): 51 KB read, 0 written",
                 "fp64_pipe_util": budget["fp64_instr"] * per_gpu / k_s / (peak_tflops * 1e12 / 2.0),
                 "fp64_pipe_instr_per_particle": budget["fp64_instr"], "flop_per_particle": budget["flop"],
                 "loop_instr_per_particle": budget["loop_instr"],
