@@ -12,17 +12,26 @@
 //     = id, file truncated) and removes every kind whose list was empty for all traces.
 // The net effect for a model with a fixed predict structure is: a kind that has predicts gets one
 // line per trace appended; a kind that has none ends up removed (even if it pre-existed).  That is
-// what this writer produces, one buffered write per trace block instead of three open/append/close
-// per trace.
+// what this writer produces, with the text of a trace block formatted by all host cores and written
+// in a few large writes instead of three open/append/close per trace.
 #ifndef CPPROB_B200_POSTERIOR_TEXT_HPP
 #define CPPROB_B200_POSTERIOR_TEXT_HPP
 
+#include <algorithm>
 #include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <functional>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <fcntl.h>
+#include <sys/types.h>
+#include <unistd.h>
 
 #include "cpprob_sis.h"
 
@@ -82,84 +91,35 @@ public:
     }
     ~posterior_writer()
     {
-        if (f_real_) std::fclose(f_real_);
-        if (f_int_) std::fclose(f_int_);
+        if (f_real_ >= 0) ::close(f_real_);
+        if (f_int_ >= 0) ::close(f_int_);
     }
     posterior_writer(const posterior_writer &) = delete;
     posterior_writer & operator=(const posterior_writer &) = delete;
 
     bool open()
     {
+        // appended to, never truncated (ios::app in the reference); offsets are tracked here so that the
+        // slices of a block can be written concurrently with pwrite
         if (!real_ids_.empty()) {
-            f_real_ = std::fopen((prefix_ + ".real").c_str(), "ab");
-            if (!f_real_) return false;
+            f_real_ = ::open((prefix_ + ".real").c_str(), O_WRONLY | O_CREAT, 0666);
+            if (f_real_ < 0) return false;
+            off_real_ = ::lseek(f_real_, 0, SEEK_END);
         }
         if (!int_ids_.empty()) {
-            f_int_ = std::fopen((prefix_ + ".int").c_str(), "ab");
-            if (!f_int_) return false;
+            f_int_ = ::open((prefix_ + ".int").c_str(), O_WRONLY | O_CREAT, 0666);
+            if (f_int_ < 0) return false;
+            off_int_ = ::lseek(f_int_, 0, SEEK_END);
         }
         return true;
     }
 
+    // One trace block -> text.  The block is cut into slices that are formatted concurrently (one buffer
+    // per slice) and written in order, so the file content does not depend on the thread count.
     bool append(const cpprob_sis_block & blk)
     {
-        if (f_real_) {
-            // "(" "[" n*( "(" id " " 23 ")" " " ) "]" " " 24 ")" "\n"
-            const size_t per_line = 8 + real_ids_.size() * 48 + 32;
-            buf_.resize(per_line * 4096);
-            size_t done = 0;
-            while (done < blk.n) {
-                const size_t n = std::min<size_t>(4096, blk.n - done);
-                char * p = buf_.data();
-                for (size_t i = done; i < done + n; ++i) {
-                    *p++ = '(';
-                    *p++ = '[';
-                    for (size_t r = 0; r < real_ids_.size(); ++r) {
-                        if (r) *p++ = ' ';
-                        *p++ = '(';
-                        p = format_int(p, real_ids_[r]);
-                        *p++ = ' ';
-                        p = format_double(p, blk.real_rows[r * blk.stride + i]);
-                        *p++ = ')';
-                    }
-                    *p++ = ']';
-                    *p++ = ' ';
-                    p = format_double(p, blk.log_w[i]);
-                    *p++ = ')';
-                    *p++ = '\n';
-                }
-                if (std::fwrite(buf_.data(), 1, static_cast<size_t>(p - buf_.data()), f_real_) != static_cast<size_t>(p - buf_.data())) return false;
-                done += n;
-            }
-        }
-        if (f_int_) {
-            const size_t per_line = 8 + int_ids_.size() * 40 + 32;
-            buf_.resize(per_line * 4096);
-            size_t done = 0;
-            while (done < blk.n) {
-                const size_t n = std::min<size_t>(4096, blk.n - done);
-                char * p = buf_.data();
-                for (size_t i = done; i < done + n; ++i) {
-                    *p++ = '(';
-                    *p++ = '[';
-                    for (size_t r = 0; r < int_ids_.size(); ++r) {
-                        if (r) *p++ = ' ';
-                        *p++ = '(';
-                        p = format_int(p, int_ids_[r]);
-                        *p++ = ' ';
-                        p = format_int(p, blk.int_rows[r * blk.stride + i]);
-                        *p++ = ')';
-                    }
-                    *p++ = ']';
-                    *p++ = ' ';
-                    p = format_double(p, blk.log_w[i]);
-                    *p++ = ')';
-                    *p++ = '\n';
-                }
-                if (std::fwrite(buf_.data(), 1, static_cast<size_t>(p - buf_.data()), f_int_) != static_cast<size_t>(p - buf_.data())) return false;
-                done += n;
-            }
-        }
+        if (f_real_ >= 0 && !append_kind(blk, false)) return false;
+        if (f_int_ >= 0 && !append_kind(blk, true)) return false;
         return true;
     }
 
@@ -167,8 +127,8 @@ public:
     bool finish(const std::vector<std::string> & ids)
     {
         bool ok = true;
-        if (f_real_) { ok = std::fclose(f_real_) == 0 && ok; f_real_ = nullptr; }
-        if (f_int_) { ok = std::fclose(f_int_) == 0 && ok; f_int_ = nullptr; }
+        if (f_real_ >= 0) { ok = ::close(f_real_) == 0 && ok; f_real_ = -1; }
+        if (f_int_ >= 0) { ok = ::close(f_int_) == 0 && ok; f_int_ = -1; }
         ok = write_ids(prefix_, ids) && ok;
         if (int_ids_.empty()) std::remove((prefix_ + ".int").c_str());
         if (real_ids_.empty()) std::remove((prefix_ + ".real").c_str());
@@ -177,11 +137,100 @@ public:
     }
 
 private:
+    // grow-only, never zero-filled text buffer of one formatting thread
+    struct text_buffer {
+        std::unique_ptr<char[]> p;
+        size_t cap = 0, len = 0;
+        char * reserve(size_t n)
+        {
+            if (n > cap) {
+                p.reset(new char[n]);
+                cap = n;
+            }
+            return p.get();
+        }
+    };
+
+    void format_slice(const cpprob_sis_block & blk, bool is_int, size_t i0, size_t i1, text_buffer & out) const
+    {
+        const std::vector<int> & ids = is_int ? int_ids_ : real_ids_;
+        // "(" "[" n*( "(" id " " value ")" " " ) "]" " " logw ")" "\n"
+        const size_t per_line = 8 + ids.size() * (is_int ? 40 : 48) + 32;
+        char * p = out.reserve(per_line * (i1 - i0));
+        char * const begin = p;
+        for (size_t i = i0; i < i1; ++i) {
+            *p++ = '(';
+            *p++ = '[';
+            for (size_t r = 0; r < ids.size(); ++r) {
+                if (r) *p++ = ' ';
+                *p++ = '(';
+                p = format_int(p, ids[r]);
+                *p++ = ' ';
+                p = is_int ? format_int(p, blk.int_rows[r * blk.stride + i]) : format_double(p, blk.real_rows[r * blk.stride + i]);
+                *p++ = ')';
+            }
+            *p++ = ']';
+            *p++ = ' ';
+            p = format_double(p, blk.log_w[i]);
+            *p++ = ')';
+            *p++ = '\n';
+        }
+        out.len = static_cast<size_t>(p - begin);
+    }
+
+    static bool write_all(int fd, const char * p, size_t n, off_t off)
+    {
+        while (n > 0) {
+            const ssize_t w = ::pwrite(fd, p, n, off);
+            if (w < 0) return false;
+            p += w;
+            n -= static_cast<size_t>(w);
+            off += w;
+        }
+        return true;
+    }
+
+    bool append_kind(const cpprob_sis_block & blk, bool is_int)
+    {
+        const int fd = is_int ? f_int_ : f_real_;
+        off_t & file_off = is_int ? off_int_ : off_real_;
+        const size_t kSlice = 1 << 16;                      // records per slice
+        const size_t n_slices = (blk.n + kSlice - 1) / kSlice;
+        unsigned hw = std::thread::hardware_concurrency();
+        if (const char * s = std::getenv("CPPROB_SIS_WRITER_THREADS")) hw = static_cast<unsigned>(std::atoi(s));
+        const size_t n_threads = std::max<size_t>(1, std::min<size_t>({static_cast<size_t>(hw ? hw : 1), n_slices, 32}));
+        // waves of n_threads slices: format concurrently, then (offsets known) write concurrently
+        if (bufs_.size() < n_threads) bufs_.resize(n_threads);
+        std::vector<text_buffer> & bufs = bufs_;
+        std::vector<off_t> offs(n_threads);
+        std::vector<char> ok(n_threads, 1);
+        auto run_wave = [&](size_t wave, const std::function<void(size_t)> & fn) {
+            if (wave == 1) { fn(0); return; }
+            std::vector<std::thread> pool;
+            pool.reserve(wave);
+            for (size_t t = 0; t < wave; ++t) pool.emplace_back(fn, t);
+            for (auto & th : pool) th.join();
+        };
+        for (size_t s0 = 0; s0 < n_slices; s0 += n_threads) {
+            const size_t wave = std::min(n_threads, n_slices - s0);
+            run_wave(wave, [&](size_t t) {
+                format_slice(blk, is_int, (s0 + t) * kSlice, std::min<size_t>(blk.n, (s0 + t + 1) * kSlice), bufs[t]);
+            });
+            for (size_t t = 0; t < wave; ++t) {
+                offs[t] = file_off;
+                file_off += static_cast<off_t>(bufs[t].len);
+            }
+            run_wave(wave, [&](size_t t) { ok[t] = write_all(fd, bufs[t].p.get(), bufs[t].len, offs[t]) ? 1 : 0; });
+            for (size_t t = 0; t < wave; ++t) if (!ok[t]) return false;
+        }
+        return true;
+    }
+
     std::string prefix_;
     std::vector<int> real_ids_, int_ids_;   // address id of each real / int row
-    std::FILE * f_real_ = nullptr;
-    std::FILE * f_int_ = nullptr;
-    std::vector<char> buf_;
+    int f_real_ = -1, f_int_ = -1;
+    std::vector<text_buffer> bufs_;
+    off_t off_real_ = 0, off_int_ = 0;
 };
 
 // <prefix>.stats: the on-device estimators of the LAST run (the record files may hold older runs
