@@ -34,7 +34,7 @@ class Config(C.Structure):
 
 
 class Slot(C.Structure):
-    _fields_ = [("is_int", C.c_int), ("id", C.c_int), ("k", C.c_int), ("row", C.c_int)]
+    _fields_ = [("is_int", C.c_int), ("id", C.c_int), ("k", C.c_int), ("row", C.c_int), ("width", C.c_int)]
 
 
 class Structure(C.Structure):
@@ -197,6 +197,7 @@ class Engine:
         _check(self._L.cpprob_sis_describe(self._h, self.model_id(model), _dptr(obs), obs.size, C.byref(s)))
         return {"ids": [s.ids[i].decode() for i in range(s.n_ids)],
                 "slots": [(s.slots[i].is_int, s.slots[i].id, s.slots[i].k, s.slots[i].row) for i in range(s.n_slots)],
+                "widths": [s.slots[i].width for i in range(s.n_slots)],
                 "n_real": s.n_real, "n_int": s.n_int, "n_samples": s.n_samples}
 
     # ---- inference ----------------------------------------------------------------------------

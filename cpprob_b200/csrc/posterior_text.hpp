@@ -79,15 +79,7 @@ class posterior_writer {
 public:
     posterior_writer(const std::string & prefix, const std::vector<cpprob_sis_slot> & slots) : prefix_(prefix)
     {
-        for (const auto & s : slots) {
-            if (s.is_int) {
-                if (int_ids_.size() <= static_cast<size_t>(s.row)) int_ids_.resize(static_cast<size_t>(s.row) + 1);
-                int_ids_[static_cast<size_t>(s.row)] = s.id;
-            } else {
-                if (real_ids_.size() <= static_cast<size_t>(s.row)) real_ids_.resize(static_cast<size_t>(s.row) + 1);
-                real_ids_[static_cast<size_t>(s.row)] = s.id;
-            }
-        }
+        for (const auto & s : slots) (s.is_int ? int_ids_ : real_ids_).push_back(s);   // program order = row order
     }
     ~posterior_writer()
     {
@@ -153,9 +145,10 @@ private:
 
     void format_slice(const cpprob_sis_block & blk, bool is_int, size_t i0, size_t i1, text_buffer & out) const
     {
-        const std::vector<int> & ids = is_int ? int_ids_ : real_ids_;
-        // "(" "[" n*( "(" id " " value ")" " " ) "]" " " logw ")" "\n"
-        const size_t per_line = 8 + ids.size() * (is_int ? 40 : 48) + 32;
+        const std::vector<cpprob_sis_slot> & ids = is_int ? int_ids_ : real_ids_;
+        // "(" "[" n*( "(" id " " value ")" " " ) "]" " " logw ")" "\n"; a vector value is "[v0 v1 ...]"
+        size_t per_line = 8 + 32;
+        for (const auto & s : ids) per_line += 24 + static_cast<size_t>(s.width) * 26;
         char * p = out.reserve(per_line * (i1 - i0));
         char * const begin = p;
         for (size_t i = i0; i < i1; ++i) {
@@ -164,9 +157,21 @@ private:
             for (size_t r = 0; r < ids.size(); ++r) {
                 if (r) *p++ = ' ';
                 *p++ = '(';
-                p = format_int(p, ids[r]);
+                p = format_int(p, ids[r].id);
                 *p++ = ' ';
-                p = is_int ? format_int(p, blk.int_rows[r * blk.stride + i]) : format_double(p, blk.real_rows[r * blk.stride + i]);
+                const size_t row = static_cast<size_t>(ids[r].row);
+                if (is_int) {
+                    p = format_int(p, blk.int_rows[row * blk.stride + i]);
+                } else if (ids[r].width == 1) {
+                    p = format_double(p, blk.real_rows[row * blk.stride + i]);
+                } else {                                   // NDArray vector: ndarray.hpp:273-288 -> "[v0 v1 ...]"
+                    *p++ = '[';
+                    for (int c = 0; c < ids[r].width; ++c) {
+                        if (c) *p++ = ' ';
+                        p = format_double(p, blk.real_rows[(row + c) * blk.stride + i]);
+                    }
+                    *p++ = ']';
+                }
                 *p++ = ')';
             }
             *p++ = ']';
@@ -227,7 +232,7 @@ private:
     }
 
     std::string prefix_;
-    std::vector<int> real_ids_, int_ids_;   // address id of each real / int row
+    std::vector<cpprob_sis_slot> real_ids_, int_ids_;   // the real / int predict slots in program order
     int f_real_ = -1, f_int_ = -1;
     std::vector<text_buffer> bufs_;
     off_t off_real_ = 0, off_int_ = 0;
@@ -252,7 +257,10 @@ inline bool write_stats_sidecar(const std::string & prefix, const cpprob_sis_sta
     for (const auto & s : ids) std::fprintf(f, "id %s\n", s.c_str());
     for (const auto & s : slots) {
         if (!s.is_int) {
-            std::fprintf(f, "real %d %d %.17g %.17g\n", s.id, s.k, st.real_mean[s.row], st.real_var[s.row]);
+            std::fprintf(f, "real %d %d %d", s.id, s.k, s.width);
+            for (int c = 0; c < s.width; ++c) std::fprintf(f, " %.17g", st.real_mean[s.row + c]);
+            for (int c = 0; c < s.width; ++c) std::fprintf(f, " %.17g", st.real_var[s.row + c]);
+            std::fprintf(f, "\n");
         }
     }
     for (const auto & s : slots) {

@@ -164,7 +164,7 @@ int probe_structure(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, c
     for (const auto & s : e->structure.ids) e->id_ptrs.push_back(s.c_str());
     e->slots.clear();
     for (const auto & s : e->structure.slots) {
-        e->slots.push_back(cpprob_sis_slot{s.is_int ? 1 : 0, static_cast<int>(s.id), static_cast<int>(s.k), static_cast<int>(s.row)});
+        e->slots.push_back(cpprob_sis_slot{s.is_int ? 1 : 0, static_cast<int>(s.id), static_cast<int>(s.k), static_cast<int>(s.row), static_cast<int>(s.width)});
     }
     return 0;
 }

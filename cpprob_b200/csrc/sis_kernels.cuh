@@ -216,6 +216,7 @@ struct null_policy {
         imax = x > imax ? x : imax;
     }
     template<class S> __device__ __forceinline__ void predict_real(double, const S &) {}
+    template<class S> __device__ __forceinline__ void begin_vector(int, const S &) {}
 };
 
 // Fused kernel: up to NR real predicts staged in registers.
@@ -237,6 +238,7 @@ struct reg_policy {
         for (int i = 0; i < NR; ++i) if (k == i) v[i] = x;
         ++k;
     }
+    template<class S> __device__ __forceinline__ void begin_vector(int, const S &) {}
 };
 
 // Row kernel: address-major SoA rows in HBM; consecutive threads own consecutive columns, so each
@@ -268,6 +270,7 @@ struct row_policy {
         *real_col = x;
         real_col += stride;
     }
+    template<class S> __device__ __forceinline__ void begin_vector(int, const S &) {}
 };
 
 // Replay: the k-th sample statement of a kind returns the k-th recorded predict of that kind.
@@ -282,13 +285,33 @@ struct replay_policy {
     template<class D>
     __device__ __forceinline__ typename D::result_type sample(const D &, philox_stream &)
     {
-        return take(std::integral_constant<bool, std::is_integral<typename D::result_type>::value>(),
-                    static_cast<typename D::result_type *>(nullptr));
+        return take_any(static_cast<typename D::result_type *>(nullptr));
     }
     template<class S> __device__ __forceinline__ void predict_int(long long, const S &) {}
     template<class S> __device__ __forceinline__ void predict_real(double, const S &) {}
+    template<class S> __device__ __forceinline__ void begin_vector(int, const S &) {}
+    // one recorded real value (used by vector-valued distributions, component by component)
+    __device__ __forceinline__ double take_real()
+    {
+        const double x = __ldg(real_col);
+        real_col += stride;
+        return x;
+    }
 
 private:
+    template<class R>
+    __device__ __forceinline__ R take_any(R * tag)
+    {
+        return take(std::integral_constant<bool, std::is_integral<R>::value>(), tag);
+    }
+    template<class T, int N>
+    __device__ __forceinline__ vecn<T, N> take_any(vecn<T, N> *)
+    {
+        vecn<T, N> r;
+#pragma unroll
+        for (int i = 0; i < N; ++i) r[i] = static_cast<T>(take_real());
+        return r;
+    }
     template<class R>
     __device__ __forceinline__ R take(std::true_type, R *)
     {

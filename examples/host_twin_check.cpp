@@ -45,6 +45,16 @@ int main()
         CHECK(s.ids.size() == 1 && s.ids[0] == "State" && s.n_real == 5 && s.slots[3].k == 3 && s.slots[3].row == 3 && !s.slots[3].is_int);
         s = probe_model(models::hmm_model{}, obs5, 5);
         CHECK(s.ids[0] == "State" && s.n_int == 5 && s.n_real == 0 && s.n_samples == 5 && s.slots[4].is_int && s.slots[4].k == 4);
+        s = probe_model(models::gaussian_2d_unk_mean_model{}, obs2, 2);
+        CHECK(s.ids[0] == "Mu" && s.slots.size() == 1 && s.slots[0].width == 2 && s.n_real == 2);
+        s = probe_model(models::all_distr_model{}, obs2, 2);
+        CHECK(s.ids.size() == 1 && s.ids[0] == "[models::all_distr(int, int)]" && s.slots.size() == 5 && s.slots[4].width == 4 &&
+              s.slots[4].row == 2 && s.n_real == 6 && s.n_int == 2 && s.slots[3].is_int && s.slots[3].k == 1);
+        const double pts[4] = {1, 2.1, 2, 3.9};
+        s = probe_model(models::linear_regression_model{}, pts, 4);
+        CHECK(s.ids.size() == 2 && s.ids[0] == "a" && s.ids[1] == "b");
+        s = probe_model(models::poly_adjustment_model<3>{}, pts, 4);
+        CHECK(s.n_real == 4 && s.slots[3].k == 3);
     }
     {   // log-pdfs on the host twin, survey golden values
         CHECK(std::abs(logpdf<normal_distribution<>>()(normal_distribution<>(1, 2), 3.0) - -2.112085713764618) < 1e-14);
@@ -75,6 +85,11 @@ int main()
     }
     {   // outside inference a model stub is a dry run; inference on an unbound callable throws
         models::gaussian_unknown_mean<>(3.0, 4.0);
+        models::normal_rejection_sampling<>(3.0, 4.0);
+        models::gaussian_2d_unk_mean<>(std::vector<double>{3.0, 4.0});
+        models::all_distr(0, 0);
+        models::poly_adjustment<2, 2>(std::array<std::array<double, 2>, 2>{{{{1, 2.1}}, {{2, 3.9}}}});
+        models::linear_regression<>(std::vector<std::pair<double, double>>{{1, 2.1}, {2, 3.9}});
         bool threw = false;
         try {
             cpprob::inference(cpprob::StateType::sis, [](double, double) {}, std::make_tuple(3., 4.), 10, "/tmp/never");

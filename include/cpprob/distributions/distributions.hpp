@@ -509,5 +509,80 @@ struct logpdf<beta_distribution<RealType>> {
     }
 };
 
+// -------------------------------------------------------------------------------------------------
+// multivariate normal with diagonal covariance, fixed dimension N
+// (/root/reference include/cpprob/distributions/multivariate_normal.hpp:19-311: a vector of
+// independent normals; log-pdf utils_multivariate_normal.hpp:20-33 = sum of the component log-pdfs)
+// -------------------------------------------------------------------------------------------------
+template<class T, int N> struct vecn;   // cpprob/particle.hpp
+
+template<class RealType = double, int N = 2>
+class multivariate_normal_distribution {
+public:
+    using result_type = vecn<RealType, N>;
+    using input_type = RealType;
+
+    // (means..., one sigma for every component) — multivariate_normal.hpp:38-42, :64-68
+    template<class RangeMean>
+    CPPROB_HD multivariate_normal_distribution(const RangeMean & mean, RealType sigma)
+    {
+        int i = 0;
+        for (auto it = mean.begin(); it != mean.end() && i < N; ++it, ++i) { mean_[i] = *it; sigma_[i] = sigma; }
+    }
+    // (means..., sigmas...) — multivariate_normal.hpp:44-61, :70-75
+    template<class RangeMean, class RangeSigma>
+    CPPROB_HD multivariate_normal_distribution(const RangeMean & mean, const RangeSigma & sigma)
+    {
+        int i = 0;
+        auto is = sigma.begin();
+        for (auto it = mean.begin(); it != mean.end() && i < N; ++it, ++is, ++i) { mean_[i] = *it; sigma_[i] = *is; }
+    }
+    CPPROB_HD multivariate_normal_distribution(std::initializer_list<RealType> mean, std::initializer_list<RealType> sigma)
+    {
+        int i = 0;
+        auto is = sigma.begin();
+        for (auto it = mean.begin(); it != mean.end() && i < N; ++it, ++is, ++i) { mean_[i] = *it; sigma_[i] = *is; }
+    }
+    CPPROB_HD multivariate_normal_distribution(std::initializer_list<RealType> mean, RealType sigma)
+    {
+        int i = 0;
+        for (auto it = mean.begin(); it != mean.end() && i < N; ++it, ++i) { mean_[i] = *it; sigma_[i] = sigma; }
+    }
+
+    CPPROB_HD RealType mean(int i) const { return mean_[i]; }
+    CPPROB_HD RealType sigma(int i) const { return sigma_[i]; }
+    static constexpr int dimension() { return N; }
+
+    template<class Rng>
+    CPPROB_HD result_type operator()(Rng & rng) const
+    {
+        result_type r;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int i = 0; i < N; ++i) r.v[i] = normal_distribution<RealType>(mean_[i], sigma_[i])(rng);
+        return r;
+    }
+
+private:
+    RealType mean_[N], sigma_[N];
+};
+
+template<class RealType, int N>
+struct logpdf<multivariate_normal_distribution<RealType, N>> {
+    template<class Vec>
+    CPPROB_HD RealType operator()(const multivariate_normal_distribution<RealType, N> & distr, const Vec & x) const
+    {
+        RealType ret = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int i = 0; i < N; ++i) {
+            ret += logpdf<normal_distribution<RealType>>()(normal_distribution<RealType>(distr.mean(i), distr.sigma(i)), x[i]);
+        }
+        return ret;
+    }
+};
+
 }  // namespace cpprob
 #endif  // CPPROB_DISTRIBUTIONS_HPP

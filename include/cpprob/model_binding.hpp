@@ -34,6 +34,7 @@ struct dryrun_policy {
     template<class D> typename D::result_type sample(const D & d, philox_stream & rng) { return d(rng); }
     template<class S> void predict_int(long long, const S &) {}
     template<class S> void predict_real(double, const S &) {}
+    template<class S> void begin_vector(int, const S &) {}
 };
 
 inline std::uint64_t & dryrun_counter()

@@ -54,12 +54,34 @@ struct obs_span {
     CPPROB_HD const T & operator[](int i) const { return ptr[i]; }
 };
 
+// Fixed-size vector value (the reference's NDArray<double> for the vector-valued models,
+// /root/reference include/cpprob/ndarray.hpp:26): what a multivariate distribution samples and what
+// `predict` records as `[a b ...]`.
+template<class T, int N>
+struct vecn {
+    T v[N];
+    static constexpr int size() { return N; }
+    CPPROB_HD T & operator[](int i) { return v[i]; }
+    CPPROB_HD const T & operator[](int i) const { return v[i]; }
+    CPPROB_HD const T * begin() const { return v; }
+    CPPROB_HD const T * end() const { return v + N; }
+};
+
+namespace detail {
+// what logpdf<D> receives: D::result_type for scalar distributions (so that `observe(poisson, 3.0)` converts
+// as in the reference), the value itself for vector-valued ones (any indexable range)
+template<class D, class Value, bool Scalar = std::is_arithmetic<typename D::result_type>::value>
+struct observed { using type = typename D::result_type; };
+template<class D, class Value>
+struct observed<D, Value, false> { using type = Value; };
+}  // namespace detail
+
 template<class Policy>
 class particle {
 public:
     // `rng` is the stream this particle draws from; the two particles of a stream pair are run one
     // after the other on the same stream object (random/philox.hpp, "particle -> stream map").
-    CPPROB_HD particle(philox_stream & rng, Policy & policy) : rng_(rng), log_w_(0.0), policy_(policy) {}
+    CPPROB_HD particle(philox_stream & rng, Policy & policy) : rng_(rng), log_w_(0.0), policy_(policy), default_address_("[model]") {}
 
     // cpprob::sample(distr, control) — cpprob.hpp:68-76.  `control` is accepted and, as in the
     // reference's SIS branch (:72), has no effect.
@@ -85,10 +107,10 @@ public:
     }
 
     // cpprob::observe(distr, x) — cpprob.hpp:79-90 -> StateInfer::increment_log_prob, state.cpp:221.
-    template<class Distribution>
-    CPPROB_HD void observe(const Distribution & distr, const typename Distribution::result_type & x)
+    template<class Distribution, class Value>
+    CPPROB_HD void observe(const Distribution & distr, const Value & x)
     {
-        log_w_ += logpdf<Distribution>()(distr, x);
+        log_w_ += logpdf<Distribution>()(distr, static_cast<const typename detail::observed<Distribution, Value>::type &>(x));
     }
 
     // cpprob::predict(x, addr) — cpprob.hpp:92-98 -> StateInfer::add_predict, state.hpp:312-326.
@@ -112,6 +134,35 @@ public:
         policy_.predict_real(static_cast<double>(x), addr);
     }
 
+    // vector-valued predict: NDArray route of StateInfer::add_predict (state.hpp:328-340), recorded in
+    // the .real file as `(id [v0 v1 ...])`
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+    template<class T, int N, class String>
+    CPPROB_HD void predict(const vecn<T, N> & x, const String & addr)
+    {
+        policy_.begin_vector(N, addr);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int i = 0; i < N; ++i) policy_.predict_real(static_cast<double>(x[i]), addr);
+    }
+
+    // cpprob::predict(x) — cpprob.hpp:100-106.  The reference derives the address from the call stack
+    // (get_addr, src/cpprob/utils.cpp:71-128), which at function granularity is the same string for every
+    // statement of a model: "[<model signature>]".  Device code has no stack trace; the model supplies that
+    // string once through set_default_address (invoke_model does it from Model::address()).
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+    template<class T>
+    CPPROB_HD void predict(const T & x)
+    {
+        predict(x, default_address_);
+    }
+    CPPROB_HD void set_default_address(const char * a) { default_address_ = a; }
+
     CPPROB_HD double log_w() const { return log_w_; }
     CPPROB_HD philox_stream & rng() { return rng_; }
 
@@ -119,13 +170,14 @@ private:
     philox_stream & rng_;
     double log_w_;
     Policy & policy_;
+    const char * default_address_;
 };
 
 // Free-function spellings.
 template<class P, class D>
 CPPROB_HD typename D::result_type sample(particle<P> & p, const D & d, bool control = false) { return p.sample(d, control); }
-template<class P, class D>
-CPPROB_HD void observe(particle<P> & p, const D & d, const typename D::result_type & x) { p.observe(d, x); }
+template<class P, class D, class V>
+CPPROB_HD void observe(particle<P> & p, const D & d, const V & x) { p.observe(d, x); }
 template<class P, class T, class S>
 CPPROB_HD void predict(particle<P> & p, T x, const S & addr) { p.predict(x, addr); }
 
@@ -153,9 +205,17 @@ CPPROB_HD void invoke_model_impl(const Model & m, P & p, const double * obs, int
 }
 }  // namespace detail
 
+namespace detail {
+template<class Model, class P>
+CPPROB_HD auto set_address(P & p, int) -> decltype(Model::address(), void()) { p.set_default_address(Model::address()); }
+template<class Model, class P>
+CPPROB_HD void set_address(P &, long) {}
+}  // namespace detail
+
 template<class Model, class P>
 CPPROB_HD void invoke_model(const Model & m, P & p, const double * obs, int n_obs)
 {
+    detail::set_address<Model>(p, 0);
     detail::invoke_model_impl(m, p, obs, n_obs, std::integral_constant<bool, (Model::n_scalar_obs >= 0)>());
 }
 
@@ -169,7 +229,8 @@ struct predict_slot {
     bool is_int;          // routed to the .int (true) or .real (false) record list
     std::size_t id;       // address id
     std::size_t k;        // occurrence index of this id within the trace (StatsPrinter key)
-    std::size_t row;      // row index inside the int / real SoA block
+    std::size_t row;      // (first) row index inside the int / real SoA block
+    std::size_t width;    // 1 for a scalar predict, N for a vector predict (N consecutive real rows)
 };
 
 struct model_structure {
@@ -190,7 +251,22 @@ public:
         return d(rng);
     }
     template<class S> void predict_int(long long, const S & addr) { add(true, std::string(addr)); }
-    template<class S> void predict_real(double, const S & addr) { add(false, std::string(addr)); }
+    template<class S> void predict_real(double, const S & addr)
+    {
+        if (vector_left_ > 0) {          // component of a vector predict: one more row of the open slot
+            ++out_.n_real;
+            --vector_left_;
+            return;
+        }
+        add(false, std::string(addr));
+    }
+    template<class S> void begin_vector(int n, const S & addr)
+    {
+        add(false, std::string(addr));
+        out_.slots.back().width = static_cast<std::size_t>(n);
+        --out_.n_real;                   // add() counted one row; the n components count themselves
+        vector_left_ = n;
+    }
 
 private:
     void add(bool is_int, std::string addr)
@@ -199,13 +275,14 @@ private:
         if (it.second) out_.ids.push_back(addr);
         const std::size_t id = it.first->second;
         std::size_t k = 0;
-        for (const auto & s : out_.slots) if (s.id == id) ++k;
+        for (const auto & s : out_.slots) if (s.id == id && s.is_int == is_int) ++k;   // per record file, as StatsPrinter counts
         const std::size_t row = is_int ? out_.n_int++ : out_.n_real++;
-        out_.slots.push_back(predict_slot{is_int, id, k, row});
+        out_.slots.push_back(predict_slot{is_int, id, k, row, 1});
     }
 
     model_structure & out_;
     std::unordered_map<std::string, std::size_t> index_;
+    int vector_left_ = 0;
 };
 
 template<class Model>

@@ -40,7 +40,7 @@ namespace cpprob {
 
 class StatsPrinter {
 public:
-    struct real_estimate { double mean = 0, variance = 0; };
+    struct real_estimate { std::vector<double> mean, variance; };   // one element per component (1 for a scalar predict)
     struct int_estimate {
         std::map<int, double> distribution;
         int map = 0;
@@ -74,8 +74,11 @@ public:
                     out << ' ' << i;
                 }
                 out << ':' << std::endl;
-                out << "  Mean: " << est.mean << std::endl
-                    << "  Variance: " << est.variance << std::endl;
+                out << "  Mean: ";
+                print_value(out, est.mean);
+                out << std::endl << "  Variance: ";
+                print_value(out, est.variance);
+                out << std::endl;
                 ++i;
             }
         }
@@ -110,16 +113,24 @@ public:
     double max_log_weight() const { return max_log_w_; }
 
 private:
-    struct parsed_record_file {
-        std::vector<std::pair<std::size_t, std::size_t>> keys;   // (id, k) of every column, first-record order
-        std::vector<double> real_cols;                             // [n_cols][n] (filled when !is_int)
-        std::vector<std::int32_t> int_cols;
-        std::vector<double> log_w;
-        std::size_t n = 0;
+    // NDArray printing (ndarray.hpp:273-288): a scalar prints bare, a vector as [a b c]
+    static void print_value(std::ostream & out, const std::vector<double> & v)
+    {
+        if (v.size() == 1) { out << v[0]; return; }
+        out << '[';
+        for (std::size_t i = 0; i < v.size(); ++i) out << (i ? " " : "") << v[i];
+        out << ']';
+    }
+
+    struct col_key {
+        std::size_t id, k;
+        int comp, width;
+        bool operator<(const col_key & o) const { return id != o.id ? id < o.id : (k != o.k ? k < o.k : comp < o.comp); }
     };
 
     // `([(id v) (id v) ...] logw)` — hand-rolled scanner for the grammar of serialization.hpp:41-98
-    static bool parse_line(const char * p, bool is_int, std::vector<std::pair<std::size_t, double>> & items, double & logw)
+    struct item { std::size_t id; int comp; int width; double v; };
+    static bool parse_line(const char * p, bool is_int, std::vector<item> & items, double & logw)
     {
         auto skip = [&p] { while (*p == ' ' || *p == '\t' || *p == '\r') ++p; };
         items.clear();
@@ -135,17 +146,27 @@ private:
             const unsigned long long id = std::strtoull(p, &end, 10);
             if (end == p) return false;
             p = end;
-            double v;
-            if (is_int) {
-                v = static_cast<double>(std::strtol(p, &end, 10));
+            skip();
+            if (!is_int && *p == '[') {                    // vector value: (id [v0 v1 ...])
+                ++p;
+                const std::size_t first = items.size();
+                for (int comp = 0;; ++comp) {
+                    skip();
+                    if (*p == ']') { ++p; break; }
+                    const double v = std::strtod(p, &end);
+                    if (end == p) return false;
+                    p = end;
+                    items.push_back(item{static_cast<std::size_t>(id), comp, 0, v});
+                }
+                for (std::size_t j = first; j < items.size(); ++j) items[j].width = static_cast<int>(items.size() - first);
             } else {
-                v = std::strtod(p, &end);
+                const double v = is_int ? static_cast<double>(std::strtol(p, &end, 10)) : std::strtod(p, &end);
+                if (end == p) return false;
+                p = end;
+                items.push_back(item{static_cast<std::size_t>(id), 0, 1, v});
             }
-            if (end == p) return false;
-            p = end;
             skip();
             if (*p++ != ')') return false;
-            items.emplace_back(static_cast<std::size_t>(id), v);
         }
         char * end = nullptr;
         logw = std::strtod(p, &end);
@@ -161,12 +182,12 @@ private:
         if (!file.is_open()) return false;
 
         // column-major staging: one growing vector per (id, k) column
-        std::map<std::pair<std::size_t, std::size_t>, std::size_t> col_of;
-        std::vector<std::pair<std::size_t, std::size_t>> keys;
+        std::map<col_key, std::size_t> col_of;
+        std::vector<col_key> keys;
         std::vector<std::vector<double>> cols;
         std::vector<std::vector<double>> col_logw;   // only used if the records are ragged
         std::vector<double> log_w;
-        std::vector<std::pair<std::size_t, double>> items;
+        std::vector<item> items;
         bool ragged = false;
         std::size_t n = 0;
         for (std::string line; std::getline(file, line);) {
@@ -177,7 +198,8 @@ private:
             }
             std::map<std::size_t, std::size_t> seen;   // occurrences of each id within this record
             for (const auto & it : items) {
-                const std::pair<std::size_t, std::size_t> key(it.first, seen[it.first]++);
+                if (it.comp == 0) ++seen[it.id];
+                const col_key key{it.id, seen[it.id] - 1, it.comp, it.width};
                 auto found = col_of.find(key);
                 if (found == col_of.end()) {
                     found = col_of.emplace(key, cols.size()).first;
@@ -186,7 +208,7 @@ private:
                     col_logw.emplace_back();
                     if (n != 0) ragged = true;
                 }
-                cols[found->second].push_back(it.second);
+                cols[found->second].push_back(it.v);
                 col_logw[found->second].push_back(lw);
             }
             log_w.push_back(lw);
@@ -204,14 +226,14 @@ private:
             // records of differing shape: every (id, k) has its own weight vector, as in the reference
             for (std::size_t c = 0; c < cols.size(); ++c) {
                 std::vector<std::vector<double>> one(1, cols[c]);
-                std::vector<std::pair<std::size_t, std::size_t>> key(1, keys[c]);
+                std::vector<col_key> key(1, keys[c]);
                 reduce_dense(engine, is_int, key, one, col_logw[c], cols[c].size());
             }
         }
         return true;
     }
 
-    void reduce_dense(sis::engine & engine, bool is_int, const std::vector<std::pair<std::size_t, std::size_t>> & keys,
+    void reduce_dense(sis::engine & engine, bool is_int, const std::vector<col_key> & keys,
                       const std::vector<std::vector<double>> & cols, const std::vector<double> & log_w, std::size_t n)
     {
         const int rows = static_cast<int>(cols.size());
@@ -229,7 +251,7 @@ private:
         log_evidence_ = st.log_evidence;
         max_log_w_ = st.max_log_w;
         for (int r = 0; r < rows; ++r) {
-            const std::size_t id = keys[r].first, k = keys[r].second;
+            const std::size_t id = keys[r].id, k = keys[r].k;
             if (is_int) {
                 auto & vec = int_[id];
                 if (vec.size() <= k) vec.resize(k + 1);
@@ -244,8 +266,12 @@ private:
             } else {
                 auto & vec = real_[id];
                 if (vec.size() <= k) vec.resize(k + 1);
-                vec[k].mean = st.real_mean[r];
-                vec[k].variance = st.real_var[r];
+                if (vec[k].mean.size() < static_cast<std::size_t>(keys[r].width)) {
+                    vec[k].mean.resize(static_cast<std::size_t>(keys[r].width));
+                    vec[k].variance.resize(static_cast<std::size_t>(keys[r].width));
+                }
+                vec[k].mean[static_cast<std::size_t>(keys[r].comp)] = st.real_mean[r];
+                vec[k].variance[static_cast<std::size_t>(keys[r].comp)] = st.real_var[r];
             }
         }
     }
@@ -270,9 +296,13 @@ private:
             else if (key == "log_evidence") is >> log_evidence_;
             else if (key == "max_log_w") is >> max_log_w_;
             else if (key == "real") {
-                std::size_t id, k;
+                std::size_t id, k, width;
                 real_estimate e;
-                is >> id >> k >> e.mean >> e.variance;
+                is >> id >> k >> width;
+                e.mean.resize(width);
+                e.variance.resize(width);
+                for (auto & m : e.mean) is >> m;
+                for (auto & v : e.variance) is >> v;
                 auto & vec = real_[id];
                 if (vec.size() <= k) vec.resize(k + 1);
                 vec[k] = e;

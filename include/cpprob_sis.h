@@ -67,7 +67,8 @@ typedef struct cpprob_sis_slot {
     int is_int;      /* 1: value goes to <out>.int, 0: to <out>.real */
     int id;          /* address id = line number in <out>.ids */
     int k;           /* occurrence index of this id within one trace (StatsPrinter's key) */
-    int row;         /* row inside the int / real SoA block */
+    int row;         /* (first) row inside the int / real SoA block */
+    int width;       /* 1 for a scalar predict; N for a vector predict = N consecutive real rows, `(id [v0 .. vN-1])` */
 } cpprob_sis_slot;
 
 typedef struct cpprob_sis_structure {

@@ -130,5 +130,175 @@ struct hmm_model {
     }
 };
 
+// -------------------------------------------------------------------------------------------------
+// 2-D Gaussian with unknown mean, diagonal covariances — /root/reference include/models/models.hpp:38-49.
+// The sampled / predicted value is a vector: recorded as `(0 [m0 m1])` in the .real file.
+// -------------------------------------------------------------------------------------------------
+struct gaussian_2d_unk_mean_model {
+    static constexpr int n_scalar_obs = -1;
+    static constexpr bool replayable = true;
+    static constexpr const char * name() { return "gaussian_2d_unk_mean"; }
+
+    template<class P>
+    CPPROB_HD void operator()(P & cpprob, const ::cpprob::obs_span<double> y1) const
+    {
+        const ::cpprob::multivariate_normal_distribution<double, 2> prior{{1, 2}, {2.2360679774997898 /* sqrt 5 */, 1.7320508075688772 /* sqrt 3 */}};
+        const auto mu = cpprob.sample(prior, true);
+        const double var = 1.4142135623730951 /* sqrt 2 */;
+
+        const ::cpprob::multivariate_normal_distribution<double, 2> likelihood{mu, var};
+        cpprob.observe(likelihood, y1);
+        cpprob.predict(mu, "Mu");
+    }
+};
+
+// -------------------------------------------------------------------------------------------------
+// N(1, sqrt 5) prior simulated by rejection sampling from its pdf — models.hpp:82-112.  The number of
+// sample statements per trace is data dependent (warp lanes leave the loop at different trips); the
+// predict structure is fixed.  `rejection_sampling` is the RAII marker of cpprob.hpp:116-125, which does
+// nothing to the weights in SIS (state.cpp:35-46).
+// -------------------------------------------------------------------------------------------------
+struct rejection_sampling_marker {
+    CPPROB_HD rejection_sampling_marker() {}
+    CPPROB_HD ~rejection_sampling_marker() {}
+};
+
+struct normal_rejection_sampling_model {
+    static constexpr int n_scalar_obs = 2;
+    static constexpr bool replayable = false;      // the accept/reject draws are not predicted
+    static constexpr const char * name() { return "normal_rejection_sampling"; }
+
+    static CPPROB_HD double normal_pdf(double mu, double sigma, double x)
+    {
+        const double z = (x - mu) / sigma;
+        return ::cpprob::dm::exp(-0.5 * z * z) / (sigma * 2.5066282746310002 /* sqrt(2 pi) */);
+    }
+
+    template<class P>
+    CPPROB_HD void operator()(P & cpprob, const double y1, const double y2) const
+    {
+        const double mu_prior = 1;
+        const double sigma_prior = 2.2360679774997898;   // sqrt 5
+        const double sigma = 1.4142135623730951;         // sqrt 2
+
+        const double maxval = normal_pdf(mu_prior, sigma_prior, mu_prior);
+        const ::cpprob::uniform_real_distribution<> proposal{mu_prior - 20 * sigma_prior, mu_prior + 20 * sigma_prior};
+        const ::cpprob::uniform_real_distribution<> accept{0, maxval};
+        double mu;
+
+        {rejection_sampling_marker rej{};
+            do {
+                mu = cpprob.sample(proposal, true);
+            } while (cpprob.sample(accept, true) > normal_pdf(mu_prior, sigma_prior, mu));
+        }
+
+        const ::cpprob::normal_distribution<> likelihood{mu, sigma};
+        cpprob.observe(likelihood, y1);
+        cpprob.observe(likelihood, y2);
+        cpprob.predict(mu, "Mu");
+    }
+};
+
+// -------------------------------------------------------------------------------------------------
+// Polynomial regression of degree D — /root/reference include/models/poly_adjustment.hpp:17-31,85-95.
+// Observations are the points flattened as x0 y0 x1 y1 ...
+// -------------------------------------------------------------------------------------------------
+template<int D>
+struct poly_adjustment_model {
+    static constexpr int n_scalar_obs = -1;
+    static constexpr bool replayable = true;
+    static constexpr const char * name() { return D == 1 ? "poly_adjustment_1" : D == 2 ? "poly_adjustment_2" : D == 3 ? "poly_adjustment_3" : "poly_adjustment"; }
+
+    template<class P>
+    CPPROB_HD void operator()(P & cpprob, const ::cpprob::obs_span<double> points) const
+    {
+        const ::cpprob::normal_distribution<> prior{0, 10};
+        double poly[D + 1];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int i = 0; i <= D; ++i) poly[i] = cpprob.sample(prior, true);
+
+        for (int j = 0; j + 1 < points.size(); j += 2) {
+            double acc = 0.0;                      // Horner, highest coefficient first (eval_poly :25-29)
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+            for (int i = D; i >= 0; --i) acc = acc * points[j] + poly[i];
+            const ::cpprob::normal_distribution<> likelihood{acc, 1};
+            cpprob.observe(likelihood, points[j + 1]);
+        }
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int i = 0; i <= D; ++i) cpprob.predict(poly[i], "Coefficient");
+    }
+};
+
+// -------------------------------------------------------------------------------------------------
+// y = a x + b — poly_adjustment.hpp:60-82 (the Builder parameter only matters for `compile`).
+// -------------------------------------------------------------------------------------------------
+struct linear_regression_model {
+    static constexpr int n_scalar_obs = -1;
+    static constexpr bool replayable = true;
+    static constexpr const char * name() { return "linear_regression"; }
+
+    template<class P>
+    CPPROB_HD void operator()(P & cpprob, const ::cpprob::obs_span<double> points) const
+    {
+        const ::cpprob::normal_distribution<> prior{0, 10};
+        const double a = cpprob.sample(prior, true);
+        const double b = cpprob.sample(prior, true);
+
+        for (int j = 0; j + 1 < points.size(); j += 2) {
+            const ::cpprob::normal_distribution<> likelihood{a * points[j] + b, 1};
+            cpprob.observe(likelihood, points[j + 1]);
+        }
+        cpprob.predict(a, "a");
+        cpprob.predict(b, "b");
+    }
+};
+
+// -------------------------------------------------------------------------------------------------
+// One statement of every distribution — /root/reference src/models/models.cpp:13-47.  It uses the
+// one-argument predict, whose address the reference takes from the call stack: at function granularity
+// that is the same string for all five statements, reproduced here by address().
+// -------------------------------------------------------------------------------------------------
+struct all_distr_model {
+    static constexpr int n_scalar_obs = 2;
+    static constexpr bool replayable = false;
+    static constexpr const char * name() { return "all_distr"; }
+    static constexpr const char * address() { return "[models::all_distr(int, int)]"; }
+
+    template<class P>
+    CPPROB_HD void operator()(P & cpprob, double, double) const
+    {
+        const ::cpprob::normal_distribution<> normal{1, 2};
+        const auto normal_val = cpprob.sample(normal, true);
+        cpprob.predict(normal_val);
+        cpprob.observe(normal, normal_val);
+
+        const ::cpprob::uniform_smallint<> discrete{2, 7};
+        const auto discrete_val = cpprob.sample(discrete, true);
+        cpprob.predict(discrete_val);
+        cpprob.observe(discrete, discrete_val);
+
+        const ::cpprob::uniform_real_distribution<> rand_unif{2, 9.5};
+        const auto rand_unif_val = cpprob.sample(rand_unif, true);
+        cpprob.predict(rand_unif_val);
+        cpprob.observe(rand_unif, rand_unif_val);
+
+        const ::cpprob::poisson_distribution<> poiss(0.8);
+        const auto poiss_val = cpprob.sample(poiss, true);
+        cpprob.predict(poiss_val);
+        cpprob.observe(poiss, poiss_val);
+
+        const ::cpprob::multivariate_normal_distribution<double, 4> multi{{1, 2, 3, 4}, {2, 1, 5, 3}};
+        const auto sample_multi = cpprob.sample(multi, true);
+        cpprob.predict(sample_multi);
+        cpprob.observe(multi, sample_multi);
+    }
+};
+
 }  // namespace models
 #endif  // CPPROB_MODELS_DEVICE_MODELS_HPP

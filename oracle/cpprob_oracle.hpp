@@ -120,6 +120,27 @@ struct poisson_distribution {
     template<class G> Int operator()(G & g) const { return static_cast<Int>(std::poisson_distribution<long>(mean_)(g)); }
 };
 
+// diagonal multivariate normal (include/cpprob/distributions/multivariate_normal.hpp:19-311): a vector of
+// independent normals; the sampled value is an NDArray, here a std::vector<double>.
+struct multivariate_normal_distribution {
+    using result_type = std::vector<double>;
+    std::vector<normal_distribution<>> distr_;
+    multivariate_normal_distribution(const std::vector<double> & mean, const std::vector<double> & sigma)
+    {
+        for (std::size_t i = 0; i < mean.size(); ++i) distr_.emplace_back(mean[i], sigma[i]);
+    }
+    multivariate_normal_distribution(const std::vector<double> & mean, double sigma)
+    {
+        for (double m : mean) distr_.emplace_back(m, sigma);
+    }
+    template<class G> result_type operator()(G & g) const
+    {
+        result_type r;
+        for (const auto & d : distr_) r.push_back(d(g));
+        return r;
+    }
+};
+
 // =================================================================================================
 // log-pdfs — the `logpdf<D>` trait family (include/cpprob/distributions/utils_base.hpp:27-28).
 // =================================================================================================
@@ -181,6 +202,17 @@ struct logpdf<poisson_distribution<Int, Real>> {
         if (lam == 0.0) return -std::numeric_limits<Real>::infinity();
         Real acc = x * std::log(lam) - lam;
         for (int i = 1; i <= x; ++i) acc -= std::log(i);
+        return acc;
+    }
+};
+
+// utils_multivariate_normal.hpp:20-33 — sum of the component log-pdfs
+template<>
+struct logpdf<multivariate_normal_distribution> {
+    double operator()(const multivariate_normal_distribution & d, const std::vector<double> & x) const
+    {
+        double acc = 0;
+        for (std::size_t i = 0; i < d.distr_.size(); ++i) acc += logpdf<normal_distribution<>>()(d.distr_[i], x[i]);
         return acc;
     }
 };
@@ -387,12 +419,26 @@ struct engine {
 // =================================================================================================
 // The three statements (include/cpprob/cpprob.hpp:68-76, :79-90, :92-98), SIS branches.
 // =================================================================================================
+template<class D, class R>
+R replay_take(const D &, R *)
+{
+    engine & e = engine::get();
+    return static_cast<R>(e.replay_values[e.replay_pos++]);
+}
+inline std::vector<double> replay_take(const multivariate_normal_distribution & d, std::vector<double> *)
+{
+    engine & e = engine::get();
+    std::vector<double> r;
+    for (std::size_t i = 0; i < d.distr_.size(); ++i) r.push_back(e.replay_values[e.replay_pos++]);
+    return r;
+}
+
 template<class D>
 typename D::result_type sample(const D & distr, bool control = false)
 {
     (void)control;   // cpprob.hpp:72: `!control || dryrun || sis` -> plain prior draw
     engine & e = engine::get();
-    if (e.replay_values) return static_cast<typename D::result_type>(e.replay_values[e.replay_pos++]);
+    if (e.replay_values) return replay_take(distr, static_cast<typename D::result_type *>(nullptr));
     return distr(get_rng());
 }
 
@@ -411,6 +457,13 @@ void predict(T x, const std::string & addr)   // state.hpp:312-318
 }
 template<class T, typename std::enable_if<std::is_floating_point<T>::value, int>::type = 0>
 void predict(T x, const std::string & addr)   // state.hpp:320-326
+{
+    engine & e = engine::get();
+    const auto id = e.register_addr(addr);
+    e.trace.predict_real.emplace_back(id, erased_value(x));
+}
+
+inline void predict(const std::vector<double> & x, const std::string & addr)   // state.hpp:328-340 (NDArray)
 {
     engine & e = engine::get();
     const auto id = e.register_addr(addr);
@@ -497,12 +550,133 @@ inline void hmm(const std::vector<double> & observed)   // models.hpp:114-141
     }
 }
 
+inline void gaussian_2d_unk_mean(const std::vector<double> & y1)   // models.hpp:38-49
+{
+    multivariate_normal_distribution prior{{1, 2}, std::vector<double>{std::sqrt(5), std::sqrt(3)}};
+    const auto mu = sample(prior, true);
+    const double var = std::sqrt(2);
+    multivariate_normal_distribution likelihood{mu, var};
+    observe(likelihood, y1);
+    predict(mu, "Mu");
+}
+
+inline double normal_pdf(double mu, double sigma, double x)   // boost::math::pdf(normal_distribution)
+{
+    const double z = (x - mu) / sigma;
+    return std::exp(-0.5 * z * z) / (sigma * std::sqrt(2 * 3.141592653589793238462643383279502884));
+}
+
+inline void normal_rejection_sampling(double y1, double y2)   // models.hpp:82-112
+{
+    const double mu_prior = 1, sigma_prior = std::sqrt(5), sigma = std::sqrt(2);
+    const double maxval = normal_pdf(mu_prior, sigma_prior, mu_prior);
+    uniform_real_distribution<> proposal{mu_prior - 20 * sigma_prior, mu_prior + 20 * sigma_prior};
+    uniform_real_distribution<> accept{0, maxval};
+    double mu;
+    do {
+        mu = sample(proposal, true);
+    } while (sample(accept, true) > normal_pdf(mu_prior, sigma_prior, mu));
+    normal_distribution<> likelihood{mu, sigma};
+    observe(likelihood, y1);
+    observe(likelihood, y2);
+    predict(mu, "Mu");
+}
+
+inline void poly_adjustment(int degree, const std::vector<double> & flat_points)   // poly_adjustment.hpp:17-31,85-95
+{
+    normal_distribution<> prior{0, 10};
+    std::vector<double> poly(static_cast<std::size_t>(degree) + 1);
+    for (auto & c : poly) c = sample(prior, true);
+    for (std::size_t j = 0; j + 1 < flat_points.size(); j += 2) {
+        const double at = flat_points[j];
+        const double val = std::accumulate(poly.crbegin(), poly.crend(), 0.0, [at](double acc, double next) { return acc * at + next; });
+        normal_distribution<> likelihood{val, 1};
+        observe(likelihood, flat_points[j + 1]);
+    }
+    for (const auto c : poly) predict(c, "Coefficient");
+}
+
+inline void linear_regression(const std::vector<double> & flat_points)   // poly_adjustment.hpp:60-82
+{
+    normal_distribution<> prior{0, 10};
+    const auto a = sample(prior, true);
+    const auto b = sample(prior, true);
+    for (std::size_t j = 0; j + 1 < flat_points.size(); j += 2) {
+        normal_distribution<> likelihood{a * flat_points[j] + b, 1};
+        observe(likelihood, flat_points[j + 1]);
+    }
+    predict(a, "a");
+    predict(b, "b");
+}
+
+// src/models/models.cpp:13-47.  One-argument predict: the reference's get_addr() (utils.cpp:71-128) yields the
+// same stack string for every statement of the function.
+inline void all_distr(int, int)
+{
+    const std::string addr = "[models::all_distr(int, int)]";
+    normal_distribution<> normal{1, 2};
+    auto normal_val = sample(normal, true);
+    predict(normal_val, addr);
+    observe(normal, normal_val);
+    uniform_smallint<> discrete{2, 7};
+    auto discrete_val = sample(discrete, true);
+    predict(discrete_val, addr);
+    observe(discrete, discrete_val);
+    uniform_real_distribution<> rand_unif{2, 9.5};
+    auto rand_unif_val = sample(rand_unif, true);
+    predict(rand_unif_val, addr);
+    observe(rand_unif, rand_unif_val);
+    poisson_distribution<> poiss(0.8);
+    auto poiss_val = sample(poiss, true);
+    predict(poiss_val, addr);
+    observe(poiss, poiss_val);
+    multivariate_normal_distribution multi{{1, 2, 3, 4}, std::vector<double>{2, 1, 5, 3}};
+    auto sample_multi = sample(multi, true);
+    predict(sample_multi, addr);
+    observe(multi, sample_multi);
+}
+
 }  // namespace models
 
 // =================================================================================================
 // Post-processing: EmpiricalDistribution + StatsPrinter
 // (include/cpprob/postprocess/empirical_distribution.hpp:16-147, stats_printer.hpp:22-121).
 // =================================================================================================
+// Minimal NDArray<double> (include/cpprob/ndarray.hpp): what StatsPrinter parses real values as
+// (stats_printer.hpp:84).  Scalar prints bare, vector as [a b c] (:273-288); scalar/vector input :290-334.
+struct nd_value {
+    std::vector<double> v;
+    nd_value() = default;
+    nd_value(double x) : v(1, x) {}
+    nd_value & operator+=(const nd_value & o)
+    {
+        if (v.size() < o.v.size()) v.resize(o.v.size(), 0.0);
+        for (std::size_t i = 0; i < o.v.size(); ++i) v[i] += o.v[i];
+        return *this;
+    }
+    friend nd_value operator*(double a, const nd_value & x) { nd_value r = x; for (auto & e : r.v) e *= a; return r; }
+    friend nd_value operator*(const nd_value & a, const nd_value & b) { nd_value r = a; for (std::size_t i = 0; i < r.v.size(); ++i) r.v[i] *= b.v[i]; return r; }
+    friend nd_value operator-(const nd_value & a, const nd_value & b) { nd_value r = a; for (std::size_t i = 0; i < r.v.size(); ++i) r.v[i] -= b.v[i]; return r; }
+    friend std::ostream & operator<<(std::ostream & os, const nd_value & x)
+    {
+        if (x.v.size() == 1) return os << x.v[0];
+        return os << x.v;
+    }
+    friend std::istream & operator>>(std::istream & is, nd_value & x)
+    {
+        char ch;
+        if (!(is >> std::ws >> ch)) return is;
+        is.putback(ch);
+        if (ch != '[') {
+            double s;
+            if (is >> s) x.v.assign(1, s);
+            return is;
+        }
+        x.v.clear();
+        return is >> x.v;
+    }
+};
+
 template<class T>
 class empirical_distribution {
 public:
@@ -522,26 +696,27 @@ public:
                    return a.second < b.second;
                })->first;
     }
-    double raw_moment(int n) const   // :52-66
+    nd_value raw_moment(int n) const   // :52-66
     {
-        if (pts_.empty()) return 0.0;
+        if (pts_.empty()) return nd_value();
         const double ln = log_norm();
-        double acc = 0;
-        for (const auto & p : pts_) acc += std::exp(p.second - ln) * ipow(static_cast<double>(p.first), n);
+        nd_value acc;
+        for (const auto & p : pts_) acc += std::exp(p.second - ln) * ipow(nd_value(p.first), n);
         return acc;
     }
-    double mean() const { return raw_moment(1); }                              // :68-71
-    double variance(double m) const { return raw_moment(2) - m * m; }          // :78-81
+    nd_value mean() const { return raw_moment(1); }                                        // :68-71
+    nd_value variance(const nd_value & m) const { return raw_moment(2) - m * m; }          // :78-81
 
 private:
-    static double ipow(double a, int b)   // fast_pow :93-115, same multiplication order
+    static nd_value ipow(nd_value a, int b)   // fast_pow :93-115, same multiplication order
     {
-        if (b == 0) return 1;
+        if (b == 0) return nd_value(1.0);
         if (b == 1) return a;
-        double aux = a, result = 1;
+        nd_value aux = a, result;
+        result.v.assign(a.v.size(), 1.0);
         while (b != 0) {
-            if (b % 2 == 0) { aux *= aux; b /= 2; }
-            else { result *= aux; b -= 1; }
+            if (b % 2 == 0) { aux = aux * aux; b /= 2; }
+            else { result = result * aux; b -= 1; }
         }
         return result;
     }
@@ -581,7 +756,7 @@ public:
                 out << sp.ids_[kv.first];
                 if (kv.second.size() > 1) out << ' ' << i;
                 out << ':' << std::endl;
-                const double m = d.mean();
+                const nd_value m = d.mean();
                 out << "  Mean: " << m << std::endl << "  Variance: " << d.variance(m) << std::endl;
                 ++i;
             }
@@ -604,7 +779,7 @@ public:
     }
 
     const std::map<std::size_t, std::vector<empirical_distribution<int>>> & ints() const { return int_distr_; }
-    const std::map<std::size_t, std::vector<empirical_distribution<double>>> & reals() const { return real_distr_; }
+    const std::map<std::size_t, std::vector<empirical_distribution<nd_value>>> & reals() const { return real_distr_; }
     const std::vector<std::string> & ids() const { return ids_; }
 
 private:
@@ -632,7 +807,7 @@ private:
     }
 
     std::map<std::size_t, std::vector<empirical_distribution<int>>> int_distr_;
-    std::map<std::size_t, std::vector<empirical_distribution<double>>> real_distr_;
+    std::map<std::size_t, std::vector<empirical_distribution<nd_value>>> real_distr_;
     std::vector<std::string> ids_;
     std::string file_name_;
 };

@@ -64,6 +64,11 @@ double oracle_run(const char * model, const double * obs, int n_obs, unsigned lo
     if (m == "gaussian_unknown_mean_mu" && n_obs == 2) return timed_inference([&] { models::gaussian_unknown_mean_mu(o[0], o[1]); }, n, prefix, how);
     if (m == "linear_gaussian_1d") return timed_inference([&] { models::linear_gaussian_1d(o); }, n, prefix, how);
     if (m == "hmm") return timed_inference([&] { models::hmm(o); }, n, prefix, how);
+    if (m == "gaussian_2d_unk_mean") return timed_inference([&] { models::gaussian_2d_unk_mean(o); }, n, prefix, how);
+    if (m == "normal_rejection_sampling" && n_obs == 2) return timed_inference([&] { models::normal_rejection_sampling(o[0], o[1]); }, n, prefix, how);
+    if (m.rfind("poly_adjustment_", 0) == 0) return timed_inference([&] { models::poly_adjustment(m.back() - '0', o); }, n, prefix, how);
+    if (m == "linear_regression") return timed_inference([&] { models::linear_regression(o); }, n, prefix, how);
+    if (m == "all_distr") return timed_inference([&] { models::all_distr(0, 0); }, n, prefix, how);
     return -1.0;
 }
 
@@ -82,6 +87,9 @@ int oracle_replay_logw(const char * model, const double * obs, int n_obs, const 
         else if (m == "gaussian_unknown_mean_mu") models::gaussian_unknown_mean_mu(o[0], o[1]);
         else if (m == "linear_gaussian_1d") models::linear_gaussian_1d(o);
         else if (m == "hmm") models::hmm(o);
+        else if (m == "gaussian_2d_unk_mean") models::gaussian_2d_unk_mean(o);
+        else if (m.rfind("poly_adjustment_", 0) == 0) models::poly_adjustment(m.back() - '0', o);
+        else if (m == "linear_regression") models::linear_regression(o);
         else { e.replay_values = nullptr; return -1; }
         logw_out[t] = e.trace.log_w;
     }
@@ -99,8 +107,8 @@ const char * oracle_stats_text(const char * prefix)
     return g_text.c_str();
 }
 
-// Numeric estimators.  Rows are ordered by (kind real then int, id, k).  For real rows out = {mean, var};
-// returns the number of rows written, or -1.  For ints use oracle_stats_int.
+// Numeric estimators.  Rows are ordered by (id, k, component); a vector-valued predict contributes one row per
+// component.  Returns the number of rows written, or -1.  For ints use oracle_stats_int.
 int oracle_stats_real(const char * prefix, int max_rows, int * ids, int * ks, double * mean, double * var)
 {
     stats_printer sp{prefix};
@@ -108,12 +116,17 @@ int oracle_stats_real(const char * prefix, int max_rows, int * ids, int * ks, do
     for (const auto & kv : sp.reals()) {
         int k = 0;
         for (const auto & d : kv.second) {
-            if (r >= max_rows) return -1;
-            ids[r] = static_cast<int>(kv.first);
-            ks[r] = k++;
-            mean[r] = d.mean();
-            var[r] = d.variance(mean[r]);
-            ++r;
+            const nd_value m = d.mean();
+            const nd_value v = d.variance(m);
+            for (std::size_t c = 0; c < m.v.size(); ++c) {
+                if (r >= max_rows) return -1;
+                ids[r] = static_cast<int>(kv.first);
+                ks[r] = k;
+                mean[r] = m.v[c];
+                var[r] = v.v[c];
+                ++r;
+            }
+            ++k;
         }
     }
     return r;
@@ -156,12 +169,19 @@ long long oracle_parse_records(const char * path, int kind, int per_record, unsi
         if (n >= max_records) return -1;
         std::istringstream iss(line);
         if (kind == 0) {
-            std::pair<std::vector<std::pair<std::size_t, double>>, double> rec;
-            if (!(iss >> rec) || static_cast<int>(rec.first.size()) != per_record) return -1;
-            for (int j = 0; j < per_record; ++j) {
-                values[n * per_record + j] = rec.first[j].second;
-                if (n == 0) ids_out[j] = static_cast<int>(rec.first[j].first);
+            // values are flattened component by component: per_record counts doubles, not predicts
+            std::pair<std::vector<std::pair<std::size_t, nd_value>>, double> rec;
+            if (!(iss >> rec)) return -1;
+            int j = 0;
+            for (const auto & el : rec.first) {
+                for (double x : el.second.v) {
+                    if (j >= per_record) return -1;
+                    values[n * per_record + j] = x;
+                    if (n == 0) ids_out[j] = static_cast<int>(el.first);
+                    ++j;
+                }
             }
+            if (j != per_record) return -1;
             logw[n] = rec.second;
         } else {
             std::pair<std::vector<std::pair<std::size_t, int>>, double> rec;
