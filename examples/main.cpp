@@ -17,6 +17,8 @@
 
 namespace {
 
+const char * const kModelNames = "{unk_mean,unk_mean_rejection,linear_gaussian,hmm,linear_regression,dyn_linear_reg,unk_mean_2d}";
+
 struct options {
     bool sis = false, estimate = false;
     std::string model, model_folder, observes, observes_file, generated_file = "post";
@@ -29,7 +31,7 @@ void usage()
                  "  -h [ --help ]                 Print help message\n"
                  "  --sis                         Sequential Importance Sampling: Priors as proposals.\n"
                  "  --estimate                    Estimators.\n"
-                 "  --model {unk_mean,linear_gaussian,hmm}\n"
+                 "  --model {unk_mean,unk_mean_rejection,linear_gaussian,hmm,linear_regression,dyn_linear_reg,unk_mean_2d}\n"
                  "                                (SIS) Select the model to be executed\n"
                  "  --model_folder arg            Folder to save the model data. Default: the model name\n"
                  "  -n [ --n_samples ] arg (=10000)  (SIS) Number of particles to be sampled from the posterior.\n"
@@ -109,12 +111,16 @@ int main(int argc, char ** argv)
         return EXIT_FAILURE;
     }
     try {
-        // the registry of /root/reference src/main.cpp:123-130, restricted to the models with device functors
+        // the registry of /root/reference src/main.cpp:123-130
         if (opt.model == "unk_mean") execute(&models::gaussian_unknown_mean<>, opt);
+        else if (opt.model == "unk_mean_rejection") execute(&models::normal_rejection_sampling<>, opt);
         else if (opt.model == "linear_gaussian") execute(&models::linear_gaussian_1d<50>, opt);
         else if (opt.model == "hmm") execute(&models::hmm<10>, opt);
+        else if (opt.model == "linear_regression") execute(&models::poly_adjustment<1, 6>, opt);
+        else if (opt.model == "dyn_linear_reg") execute(&models::linear_regression<>, opt);
+        else if (opt.model == "unk_mean_2d") execute(&models::gaussian_2d_unk_mean<>, opt);
         else {
-            std::cerr << "Incorrect model.\n\n" << "The list of available models is: {unk_mean,linear_gaussian,hmm}\n";
+            std::cerr << "Model not available. Please provide one of the following:" << std::endl << kModelNames << std::endl;
             return EXIT_FAILURE;
         }
     } catch (const std::exception & e) {

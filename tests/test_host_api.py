@@ -29,7 +29,7 @@ def test_cli_argument_errors(built):
     r = subprocess.run([main, "--sis"], capture_output=True, text=True)
     assert r.returncode != 0 and "'--model' is required" in r.stderr
     r = subprocess.run([main, "--sis", "--model", "nope"], capture_output=True, text=True)
-    assert r.returncode != 0 and "Incorrect model." in r.stderr
+    assert r.returncode != 0 and "Model not available." in r.stderr
     r = subprocess.run([main, "--csis", "--model", "hmm"], capture_output=True, text=True)
     assert r.returncode != 0 and "inference compilation" in r.stderr
 
@@ -79,3 +79,30 @@ def test_stats_printer_text_equals_reference(built, tmp_path, oracle):
     assert r.returncode == 0, r.stdout + r.stderr
     assert sorted(os.listdir(tmp_path / "lg")) == ["post_sis.ids", "post_sis.stats"]
     assert "State 49:\n  Mean: " in r.stdout
+
+
+@pytest.mark.gpu
+def test_cli_models_with_aggregate_observations(built, tmp_path):
+    """Observation strings of the aggregate-typed models go through the serialization grammar
+    (poly_adjustment.hpp:33: -o [[1 2.1] [2 3.9] ...])."""
+    env = dict(os.environ, CPPROB_SIS_SEED="3")
+    main = os.path.join(built, "main")
+    pts = "[[1 2.1] [2 3.9] [3 5.3] [4 7.7] [5 10.2] [6 12.9]]"
+    r = subprocess.run([main, "--sis", "--estimate", "--model", "linear_regression", "-n", "20000", "-o", pts,
+                        "--model_folder", str(tmp_path / "lr")], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Coefficient 0:\n  Mean: " in r.stdout and "Coefficient 1:\n  Mean: " in r.stdout
+    r = subprocess.run([main, "--sis", "--estimate", "--model", "dyn_linear_reg", "-n", "20000", "-o",
+                        "[(1 2.1) (2 3.9) (3 5.3)]", "--model_folder", str(tmp_path / "dl")], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "a:\n  Mean: " in r.stdout and "b:\n  Mean: " in r.stdout
+    r = subprocess.run([main, "--sis", "--estimate", "--model", "unk_mean_2d", "-n", "20000", "-o", "[3 4]",
+                        "--model_folder", str(tmp_path / "g2")], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Mu:\n  Mean: [" in r.stdout and "  Variance: [" in r.stdout
+    r = subprocess.run([main, "--sis", "--estimate", "--model", "unk_mean_rejection", "-n", "20000", "-o", "3 4",
+                        "--model_folder", str(tmp_path / "rj")], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and "Mu:\n  Mean: 3." in r.stdout, r.stdout + r.stderr
+    r = subprocess.run([main, "--sis", "--model", "unk_mean", "-o", "3 oops", "--model_folder", str(tmp_path / "bad")],
+                       capture_output=True, text=True, env=env)
+    assert r.returncode != 0 and "Could not parse the observations." in r.stderr
