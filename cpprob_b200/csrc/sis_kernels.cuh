@@ -247,23 +247,22 @@ struct row_policy {
     double * real_col;
     int * int_col;
     unsigned long long stride;
-    long long hist_lo;
-    int hist_bins;
-    int oor;
-    long long imin, imax;
+    unsigned hist_lo32, hist_bins;
+    unsigned oor;
+    int imin, imax;                       // of the stored (int32) values
     __device__ __forceinline__ row_policy(double * rc, int * ic, unsigned long long s, long long lo, int bins)
-        : real_col(rc), int_col(ic), stride(s), hist_lo(lo), hist_bins(bins), oor(0),
-          imin(0x7fffffffffffffffLL), imax(-0x7fffffffffffffffLL - 1) {}
+        : real_col(rc), int_col(ic), stride(s), hist_lo32(static_cast<unsigned>(static_cast<int>(lo))),
+          hist_bins(static_cast<unsigned>(bins)), oor(0), imin(0x7fffffff), imax(static_cast<int>(0x80000000u)) {}
     template<class D>
     __device__ __forceinline__ typename D::result_type sample(const D & d, philox_stream & rng) { return d(rng); }
     template<class S> __device__ __forceinline__ void predict_int(long long x, const S &)
     {
-        *int_col = static_cast<int>(x);
+        const int xi = static_cast<int>(x);
+        *int_col = xi;
         int_col += stride;
-        imin = x < imin ? x : imin;
-        imax = x > imax ? x : imax;
-        const long long b = x - hist_lo;
-        oor += (b < 0 || b >= hist_bins) ? 1 : 0;
+        imin = min(imin, xi);
+        imax = max(imax, xi);
+        oor += (static_cast<unsigned>(xi) - hist_lo32 >= hist_bins) ? 1u : 0u;   // outside [lo, lo + bins)
     }
     template<class S> __device__ __forceinline__ void predict_real(double x, const S &)
     {
@@ -489,8 +488,8 @@ __global__ void __launch_bounds__(kBlock) k_sis_rows(const __grid_constant__ run
                     invoke_model(model, p, oc.data(), a.n_obs);
                     a.logw[colidx] = p.log_w();
                     oor += pol.oor;
-                    vmin = pol.imin < vmin ? static_cast<int>(pol.imin) : vmin;
-                    vmax = pol.imax > vmax ? static_cast<int>(pol.imax) : vmax;
+                    vmin = min(vmin, pol.imin);
+                    vmax = max(vmax, pol.imax);
                 }
             }
         }

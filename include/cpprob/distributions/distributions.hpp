@@ -196,7 +196,7 @@ public:
     using input_type = WeightType;
     static constexpr int capacity = MaxK;
 
-    CPPROB_HD discrete_distribution() { probs_.n = 1; probs_.p[0] = 1; for (int i = 1; i < MaxK; ++i) probs_.p[i] = 0; }
+    CPPROB_HD discrete_distribution() { probs_.n = 1; probs_.p[0] = 1; for (int i = 1; i < MaxK; ++i) probs_.p[i] = 0; set_thresholds(); }
 
     template<class Iter>
     CPPROB_HD discrete_distribution(Iter first, Iter last) { init(first, last); }
@@ -224,30 +224,29 @@ public:
 #endif
             for (int i = 0; i < N; ++i) probs_.p[i] = w.v[i] / sum;
         }
+        set_thresholds();
     }
 
     CPPROB_HD IntType min() const { return 0; }
     CPPROB_HD IntType max() const { return static_cast<IntType>(probs_.n - 1); }
     CPPROB_HD const probability_array<WeightType, MaxK> & probabilities() const { return probs_; }
 
+    // Inverse CDF by linear scan on one 32-bit word r: the smallest i with u < p0 + ... + pi, u = (r + 0.5) 2^-32.
+    // The comparison is done on integers against thresholds fixed at construction,
+    // t_i = ceil((p0 + ... + pi) 2^32 - 0.5)  <=>  (r + 0.5) 2^-32 < p0 + ... + pi  exactly,
+    // so drawing costs a few ALU instructions and no FP64 work.
     template<class Rng>
     CPPROB_HD result_type operator()(Rng & rng) const
     {
-        // inverse CDF by linear scan; u in (0,1) with 32 random bits
-        const WeightType u = (static_cast<WeightType>(rng.next_u32()) + WeightType(0.5)) * WeightType(2.3283064365386962890625e-10);
-        WeightType acc = 0;
-        int r = probs_.n - 1;
-        bool found = false;   // the smallest i with u < p0 + ... + p_i wins
+        const std::uint32_t r = rng.next_u32();
+        int out = probs_.n - 1;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-        for (int i = 0; i < MaxK; ++i) {
-            if (i < probs_.n - 1) {
-                acc += probs_.p[i];
-                if (!found && u < acc) { r = i; found = true; }
-            }
+        for (int i = MaxK - 2; i >= 0; --i) {
+            if (i < probs_.n - 1 && r < thr_[i]) out = i;
         }
-        return static_cast<IntType>(r);
+        return static_cast<IntType>(out);
     }
 
 private:
@@ -265,9 +264,27 @@ private:
         if (sum != WeightType(1)) {          // x / 1 == x exactly: skip the divisions when already normalised
             for (int i = 0; i < n; ++i) probs_.p[i] /= sum;
         }
+        set_thresholds();
+    }
+
+    CPPROB_HD void set_thresholds()
+    {
+        WeightType acc = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int i = 0; i < MaxK - 1; ++i) {
+            acc += probs_.p[i];
+            const WeightType t = acc * WeightType(4294967296.0) - WeightType(0.5);
+            // ceil() of a value in [-0.5, 2^32): by truncation plus one when a fraction was dropped
+            const WeightType tc = t < WeightType(0) ? WeightType(0) : (t > WeightType(4294967295.0) ? WeightType(4294967295.0) : t);
+            const std::uint32_t fl = static_cast<std::uint32_t>(tc);
+            thr_[i] = (static_cast<WeightType>(fl) < tc && fl != 0xFFFFFFFFu) ? fl + 1u : fl;
+        }
     }
 
     probability_array<WeightType, MaxK> probs_;
+    std::uint32_t thr_[MaxK > 1 ? MaxK - 1 : 1];
 };
 
 template<class IntType, class WeightType, int MaxK>

@@ -112,6 +112,11 @@ struct hmm_model {
         const ::cpprob::reg_table<::cpprob::reg_table<double, k>, k> T{{{{0.1, 0.5, 0.4}},
                                                                       {{0.2, 0.2, 0.6}},
                                                                       {{0.15, 0.15, 0.7}}}};
+        // one transition distribution per row, built once per trace; the reference builds
+        // `discrete_distribution{T[state].begin(), T[state].end()}` anew at every step (models.hpp:135), which
+        // yields the same three objects
+        using transition_t = ::cpprob::discrete_distribution<std::size_t, double, k>;
+        const ::cpprob::reg_table<transition_t, k> transition{{transition_t{T[0]}, transition_t{T[1]}, transition_t{T[2]}}};
         const ::cpprob::uniform_smallint<std::size_t> prior{0, 2};
         auto state = cpprob.sample(prior, true);
         cpprob.predict(state, "State");
@@ -121,8 +126,7 @@ struct hmm_model {
         ++obs_it;
 
         for (; obs_it != observed_states.end(); ++obs_it) {
-            const ::cpprob::discrete_distribution<std::size_t, double, k> transition_distr{T[state]};   // {T[state].begin(), T[state].end()}
-            state = cpprob.sample(transition_distr, true);
+            state = cpprob.sample(transition[state], true);
             cpprob.predict(state, "State");
             likelihood = ::cpprob::normal_distribution<>{state_mean[state], 1};
             cpprob.observe(likelihood, *obs_it);
