@@ -189,7 +189,11 @@ def run_ours(args):
                 # the one collective of the path: all-gather of the per-chunk partial sums in rank order (NCCL over NVLink)
                 local = (torch.as_tensor(_DeviceArray(p.device_ptr, (p.n_chunks_local, p.n_cols)), device="cuda") if p.n_chunks_local
                          else torch.empty((0, p.n_cols), dtype=torch.float64, device="cuda"))
-                g = gather_partials(local, total, world, gathered_buf.get("scratch"), p.rows_per_chunk)
+                if "scratch" not in gathered_buf:
+                    max_local = -(-p.n_chunks_total // world)
+                    gathered_buf["scratch"] = (torch.zeros((max_local, p.n_cols), dtype=torch.float64, device="cuda"),
+                                               torch.empty((world, max_local, p.n_cols), dtype=torch.float64, device="cuda"))
+                g = gather_partials(local, total, world, gathered_buf["scratch"], p.rows_per_chunk)
                 torch.cuda.synchronize()
                 ptr, n_chunks = g.data_ptr(), g.shape[0]
             st, rebase = engine.merge(MODEL, OBS, ptr, n_chunks, p.n_cols, p.m_ref, total)

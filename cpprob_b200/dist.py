@@ -3,17 +3,20 @@ an all-gather of the per-chunk partial sums in rank order (NCCL over NVLink on t
 tests).  Merging the gathered rows in chunk order (cpprob_sis_merge) gives bit-identical results on every
 rank and for every world size; there is no data-path collective because particles are i.i.d.
 (/root/reference include/cpprob/cpprob.hpp:194-201 has no inter-particle dependence)."""
+import functools
+
 import torch
 import torch.distributed as dist
 
 from . import capi
 
 
+@functools.lru_cache(maxsize=64)
 def shard_sizes(n_total, world, rows_per_chunk=1):
     """partial rows of every rank (host arithmetic of cpprob_sis_plan_shard); a rank's rows are
     ceil(n_local / (CHUNK / rows_per_chunk))."""
     row_particles = capi.CHUNK // rows_per_chunk
-    return [-(-capi.plan_shard(n_total, r, world)[4] // row_particles) for r in range(world)]
+    return tuple(-(-capi.plan_shard(n_total, r, world)[4] // row_particles) for r in range(world))
 
 
 def gather_partials(local, n_total, world, scratch=None, rows_per_chunk=1):
