@@ -39,16 +39,36 @@ __global__ void __launch_bounds__(kBlock) k_row_moments(const double * __restric
 #pragma unroll
     for (int j = 0; j < 2 * kMomTile; ++j) acc[j] = 0.0;
 
-    for (unsigned i = threadIdx.x; i < n_here; i += kBlock) {
-        const unsigned long long colidx = base + i;
-        const double wi = w[colidx];
+    if (n_here == kSubChunk && row0 + kMomTile <= n_real) {
+        // whole sub-chunk, whole tile: compile-time offsets, 8 row loads in flight per element
+        constexpr int kPer = kSubChunk / kBlock;
+        const double * __restrict__ q = w + base + threadIdx.x;
+        const double * __restrict__ p = real_rows + static_cast<unsigned long long>(row0) * stride + base + threadIdx.x;
+#pragma unroll 4
+        for (int k = 0; k < kPer; ++k) {
+            const double wi = q[k * kBlock];
+            double x[kMomTile];
 #pragma unroll
-        for (int j = 0; j < kMomTile; ++j) {
-            if (row0 + j < n_real) {
-                const double x = __ldcs(real_rows + static_cast<unsigned long long>(row0 + j) * stride + colidx);
-                const double wx = wi * x;
+            for (int j = 0; j < kMomTile; ++j) x[j] = __ldcs(p + static_cast<unsigned long long>(j) * stride + k * kBlock);
+#pragma unroll
+            for (int j = 0; j < kMomTile; ++j) {
+                const double wx = wi * x[j];
                 acc[2 * j] += wx;
-                acc[2 * j + 1] = fma(wx, x, acc[2 * j + 1]);
+                acc[2 * j + 1] = fma(wx, x[j], acc[2 * j + 1]);
+            }
+        }
+    } else {
+        for (unsigned i = threadIdx.x; i < n_here; i += kBlock) {
+            const unsigned long long colidx = base + i;
+            const double wi = w[colidx];
+#pragma unroll
+            for (int j = 0; j < kMomTile; ++j) {
+                if (row0 + j < n_real) {
+                    const double x = __ldcs(real_rows + static_cast<unsigned long long>(row0 + j) * stride + colidx);
+                    const double wx = wi * x;
+                    acc[2 * j] += wx;
+                    acc[2 * j + 1] = fma(wx, x, acc[2 * j + 1]);
+                }
             }
         }
     }
@@ -81,14 +101,35 @@ __global__ void __launch_bounds__(kBlock) k_row_hist(const int * __restrict__ in
     const int * __restrict__ src = int_rows + static_cast<unsigned long long>(row) * stride + base;
     const double * __restrict__ wsrc = w + base;
 
+    const unsigned lo32 = static_cast<unsigned>(static_cast<int>(lo));
     double h[V];
 #pragma unroll
     for (int b = 0; b < V; ++b) h[b] = 0.0;
-    for (unsigned i = threadIdx.x; i < n_here; i += kBlock) {
-        const long long x = static_cast<long long>(__ldcs(src + i)) - lo;
-        const double wi = wsrc[i];
+    if (n_here == kSubChunk) {
+        // whole sub-chunk: 16 elements per thread at compile-time offsets (no per-element address arithmetic),
+        // all loads issued up front
+        constexpr int kPer = kSubChunk / kBlock;
+        const int * __restrict__ p = src + threadIdx.x;
+        const double * __restrict__ q = wsrc + threadIdx.x;
+        unsigned x[kPer];
+        double wi[kPer];
 #pragma unroll
-        for (int b = 0; b < V; ++b) h[b] += (x == b) ? wi : 0.0;
+        for (int k = 0; k < kPer; ++k) {
+            x[k] = static_cast<unsigned>(__ldcs(p + k * kBlock)) - lo32;
+            wi[k] = q[k * kBlock];
+        }
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+#pragma unroll
+            for (int b = 0; b < V; ++b) h[b] += (x[k] == static_cast<unsigned>(b)) ? wi[k] : 0.0;   // select, not a branch
+        }
+    } else {
+        for (unsigned i = threadIdx.x; i < n_here; i += kBlock) {
+            const unsigned x = static_cast<unsigned>(__ldcs(src + i)) - lo32;
+            const double wi = wsrc[i];
+#pragma unroll
+            for (int b = 0; b < V; ++b) h[b] += (x == static_cast<unsigned>(b)) ? wi : 0.0;
+        }
     }
     const double r = block_reduce<V>(h, 0ull, smem);
     if (threadIdx.x < V && bin_offset + static_cast<int>(threadIdx.x) < hist_bins) {

@@ -81,7 +81,8 @@ class particle {
 public:
     // `rng` is the stream this particle draws from; the two particles of a stream pair are run one
     // after the other on the same stream object (random/philox.hpp, "particle -> stream map").
-    CPPROB_HD particle(philox_stream & rng, Policy & policy) : rng_(rng), log_w_(0.0), policy_(policy), default_address_("[model]") {}
+    CPPROB_HD particle(philox_stream & rng, Policy & policy)
+        : rng_(rng), log_w_(0.0), policy_(policy), default_address_("[model]"), observed_(false) {}
 
     // cpprob::sample(distr, control) — cpprob.hpp:68-76.  `control` is accepted and, as in the
     // reference's SIS branch (:72), has no effect.
@@ -110,7 +111,11 @@ public:
     template<class Distribution, class Value>
     CPPROB_HD void observe(const Distribution & distr, const Value & x)
     {
-        log_w_ += logpdf<Distribution>()(distr, static_cast<const typename detail::observed<Distribution, Value>::type &>(x));
+        const double lp = logpdf<Distribution>()(distr, static_cast<const typename detail::observed<Distribution, Value>::type &>(x));
+        // log_w starts at 0.0 (trace.hpp:59); 0.0 + lp == lp, so the first observe stores instead of adding
+        // (one FP64 instruction per particle; `observed_` is resolved at compile time in straight-line models)
+        log_w_ = observed_ ? log_w_ + lp : lp;
+        observed_ = true;
     }
 
     // cpprob::predict(x, addr) — cpprob.hpp:92-98 -> StateInfer::add_predict, state.hpp:312-326.
@@ -171,6 +176,7 @@ private:
     double log_w_;
     Policy & policy_;
     const char * default_address_;
+    bool observed_;
 };
 
 // Free-function spellings.

@@ -38,7 +38,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     a = ap.parse_args()
     g = analytic.golden()
-    with Engine(seed=0x5EED) as e:
+    with Engine(seed=0x5EED, max_batch=int(os.environ.get("CPPROB_SIS_MAX_BATCH", "0"))) as e:
         print(json.dumps({"store_peak_GBps": e.store_peak(), "dfma_peak_tflops": e.dfma_peak()[0]}), flush=True)
         run(e, "C2 fused", "gaussian_unknown_mean", [3.0, 4.0], int(1e9 * a.scale))
         run(e, "C2 rows (forced)", "gaussian_unknown_mean", [3.0, 4.0], int(1e8 * a.scale), force_rows=True)
