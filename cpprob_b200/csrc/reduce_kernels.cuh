@@ -14,7 +14,7 @@ namespace engine {
 __global__ void __launch_bounds__(kBlock) k_init_int_extra(int_extra * __restrict__ x, unsigned n)
 {
     const unsigned i = blockIdx.x * kBlock + threadIdx.x;
-    if (i < n) x[i] = int_extra{0x7fffffff, static_cast<int>(0x80000000u), 0u, 0u};
+    if (i < n) x[i] = int_extra{0x7fffffff, static_cast<int>(0x80000000u)};
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -163,11 +163,12 @@ __global__ void __launch_bounds__(kBlock) k_merge_columns(const double * __restr
 // K3 k_row_base: weights w = exp(log_w - m_ref) and the base sums of one sub-chunk from its log_w
 // column (16 B of HBM traffic per particle).  Used after k_sis_rows and for externally supplied
 // records (replay / StatsPrinter-on-device).  `extras` (may be null) carries the int bookkeeping that
-// k_sis_rows accumulated for the sub-chunk.
+// k_sis_rows accumulated for the sub-chunk (min / max of the stored ints; the out-of-window flag derives from them).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_row_base(const double * __restrict__ logw, unsigned long long n_particles, unsigned chunk,
                                                      const double * __restrict__ m_ref_ptr, double * __restrict__ w_out,
-                                                     const int_extra * __restrict__ extras, double * __restrict__ partials, int n_cols)
+                                                     const int_extra * __restrict__ extras, long long hist_lo, int hist_bins,
+                                                     double * __restrict__ partials, int n_cols)
 {
     __shared__ double smem[kWarps * kBaseCols];
     const unsigned c = blockIdx.x;
@@ -196,7 +197,8 @@ __global__ void __launch_bounds__(kBlock) k_row_base(const double * __restrict__
         const int_extra x = extras[c];
         if (threadIdx.x == col::neg_imin) r = x.vmin <= x.vmax ? -static_cast<double>(x.vmin) : dm::neg_inf();
         if (threadIdx.x == col::imax) r = x.vmin <= x.vmax ? static_cast<double>(x.vmax) : dm::neg_inf();
-        if (threadIdx.x == col::int_oor) r = static_cast<double>(x.oor);
+        // non-zero when some int predict of the sub-chunk fell outside the histogram window [lo, lo + bins)
+        if (threadIdx.x == col::int_oor) r = (x.vmin <= x.vmax && (x.vmin < hist_lo || x.vmax >= hist_lo + hist_bins)) ? 1.0 : 0.0;
     }
     if (threadIdx.x < kBaseCols) partials[static_cast<size_t>(c) * n_cols + threadIdx.x] = r;
 }

@@ -444,7 +444,7 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(e->sm_count) * occ));
         CU_TRY(vt->launch_rows(e->compute, grid, &a));
         ++res->launches;
-        k_row_base<<<subs_here, kBlock, 0, e->compute>>>(a.logw, n_here, kSubChunk, e->d_pilot.ptr, a.w, a.int_extras, a.partials, n_cols);
+        k_row_base<<<subs_here, kBlock, 0, e->compute>>>(a.logw, n_here, kSubChunk, e->d_pilot.ptr, a.w, a.int_extras, hw.lo, hw.bins, a.partials, n_cols);
         CU_TRY(cudaGetLastError());
         ++res->launches;
         if (n_real > 0) {
@@ -902,7 +902,7 @@ int cpprob_sis_reduce_records(cpprob_sis_engine * e, const double * real_rows, i
     CU_TRY(cudaEventRecord(e->ev_begin, e->compute));
     k_max_array<<<1, kBlock, 0, e->compute>>>(e->d_logw[0].ptr, n, e->d_pilot.ptr);
     CU_TRY(cudaGetLastError());
-    k_row_base<<<n_chunks, kBlock, 0, e->compute>>>(e->d_logw[0].ptr, n, kSubChunk, e->d_pilot.ptr, e->d_w[0].ptr, nullptr, e->d_partials.ptr, n_cols);
+    k_row_base<<<n_chunks, kBlock, 0, e->compute>>>(e->d_logw[0].ptr, n, kSubChunk, e->d_pilot.ptr, e->d_w[0].ptr, nullptr, 0, 0, e->d_partials.ptr, n_cols);
     CU_TRY(cudaGetLastError());
     launches += 2;
     if (n_real > 0) {

@@ -247,12 +247,9 @@ struct row_policy {
     double * real_col;
     int * int_col;
     unsigned long long stride;
-    unsigned hist_lo32, hist_bins;
-    unsigned oor;
-    int imin, imax;                       // of the stored (int32) values
-    __device__ __forceinline__ row_policy(double * rc, int * ic, unsigned long long s, long long lo, int bins)
-        : real_col(rc), int_col(ic), stride(s), hist_lo32(static_cast<unsigned>(static_cast<int>(lo))),
-          hist_bins(static_cast<unsigned>(bins)), oor(0), imin(0x7fffffff), imax(static_cast<int>(0x80000000u)) {}
+    int imin, imax;                       // of the stored (int32) values; k_row_base checks them against the window
+    __device__ __forceinline__ row_policy(double * rc, int * ic, unsigned long long s)
+        : real_col(rc), int_col(ic), stride(s), imin(0x7fffffff), imax(static_cast<int>(0x80000000u)) {}
     template<class D>
     __device__ __forceinline__ typename D::result_type sample(const D & d, philox_stream & rng) { return d(rng); }
     template<class S> __device__ __forceinline__ void predict_int(long long x, const S &)
@@ -262,7 +259,6 @@ struct row_policy {
         int_col += stride;
         imin = min(imin, xi);
         imax = max(imax, xi);
-        oor += (static_cast<unsigned>(xi) - hist_lo32 >= hist_bins) ? 1u : 0u;   // outside [lo, lo + bins)
     }
     template<class S> __device__ __forceinline__ void predict_real(double x, const S &)
     {
@@ -459,7 +455,7 @@ __global__ void __launch_bounds__(kBlock, NR == 1 ? CPPROB_FUSED_MIN_BLOCKS : 1)
 // The weights, the base sums and the per-row estimator sums are formed afterwards by k_row_base,
 // k_row_moments and k_row_hist, which stream the rows back (HBM/L2-bound, FP64 pipe nearly idle).
 // ------------------------------------------------------------------------------------------------
-struct int_extra { int vmin, vmax; unsigned oor, pad; };
+struct int_extra { int vmin, vmax; };
 
 template<class Model>
 __global__ void __launch_bounds__(kBlock) k_sis_rows(const __grid_constant__ run_args a)
@@ -475,7 +471,6 @@ __global__ void __launch_bounds__(kBlock) k_sis_rows(const __grid_constant__ run
         const unsigned long long left = a.n_particles - base;
         const unsigned n_here = left < kTile ? static_cast<unsigned>(left) : kTile;
         int vmin = 0x7fffffff, vmax = static_cast<int>(0x80000000u);
-        unsigned oor = 0;
         if (threadIdx.x < n_here) {
             philox_stream rng(a.keys, stream0 + static_cast<unsigned long long>(tile) * kPairStride);
 #pragma unroll 1
@@ -483,11 +478,10 @@ __global__ void __launch_bounds__(kBlock) k_sis_rows(const __grid_constant__ run
                 const unsigned i = threadIdx.x + turn * kPairStride;
                 if (i < n_here) {
                     const unsigned long long colidx = base + i;
-                    row_policy pol(a.real_rows + colidx, a.int_rows + colidx, a.row_stride, a.hist_lo, a.hist_bins);
+                    row_policy pol(a.real_rows + colidx, a.int_rows + colidx, a.row_stride);
                     particle<row_policy> p(rng, pol);
                     invoke_model(model, p, oc.data(), a.n_obs);
                     a.logw[colidx] = p.log_w();
-                    oor += pol.oor;
                     vmin = min(vmin, pol.imin);
                     vmax = max(vmax, pol.imax);
                 }
@@ -497,14 +491,10 @@ __global__ void __launch_bounds__(kBlock) k_sis_rows(const __grid_constant__ run
             // a tile never straddles a sub-chunk (sub-chunk sizes are multiples of 512)
             vmin = __reduce_min_sync(0xffffffffu, vmin);
             vmax = __reduce_max_sync(0xffffffffu, vmax);
-            oor = __reduce_add_sync(0xffffffffu, oor);
-            if ((threadIdx.x & 31) == 0) {
+            if ((threadIdx.x & 31) == 0 && vmin <= vmax) {
                 int_extra * x = a.int_extras + base / a.chunk;
-                if (vmin <= vmax) {
-                    atomicMin(&x->vmin, vmin);
-                    atomicMax(&x->vmax, vmax);
-                }
-                if (oor) atomicAdd(&x->oor, oor);
+                atomicMin(&x->vmin, vmin);
+                atomicMax(&x->vmax, vmax);
             }
         }
     }

@@ -166,13 +166,14 @@ struct logpdf<uniform_smallint<IntType>> {
 template<class T, int N>
 struct reg_table {
     T v[N];
-    CPPROB_HD T operator[](std::size_t i) const
+    template<class Index>
+    CPPROB_HD T operator[](Index i) const
     {
         T r = v[0];
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-        for (int j = 1; j < N; ++j) if (i == static_cast<std::size_t>(j)) r = v[j];
+        for (int j = 1; j < N; ++j) if (i == static_cast<Index>(j)) r = v[j];
         return r;
     }
     CPPROB_HD const T * begin() const { return v; }

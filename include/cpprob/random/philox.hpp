@@ -125,7 +125,9 @@ public:
     CPPROB_HD std::uint32_t next_u32()
     {
         if (pos_ >= 4) refill();
-        const std::uint32_t r = pos_ == 0 ? w0_ : pos_ == 1 ? w1_ : pos_ == 2 ? w2_ : w3_;
+        // the pool is a shift register: the next unread word is always w0_ (three moves instead of a select chain)
+        const std::uint32_t r = w0_;
+        w0_ = w1_; w1_ = w2_; w2_ = w3_;
         ++pos_;
         return r;
     }
@@ -133,10 +135,11 @@ public:
     // Uniform double in the open interval (0,1) with 52 random bits.
     CPPROB_HD double next_uniform()
     {
-        if (pos_ >= 3) refill();          // need an aligned pair: (0,1) or (2,3)
-        double u;
-        if (pos_ == 0) { u = detail::u52_to_open01(w0_, w1_); pos_ = 2; }
-        else           { u = detail::u52_to_open01(w2_, w3_); pos_ = 4; }
+        if (pos_ >= 3) refill();          // need an aligned pair: block words (0,1) or (2,3)
+        if (pos_ == 1) { w0_ = w1_; w1_ = w2_; w2_ = w3_; pos_ = 2; }   // drop the odd word
+        const double u = detail::u52_to_open01(w0_, w1_);
+        w0_ = w2_; w1_ = w3_;
+        pos_ += 2;
         return u;
     }
 

@@ -115,9 +115,11 @@ struct hmm_model {
         // one transition distribution per row, built once per trace; the reference builds
         // `discrete_distribution{T[state].begin(), T[state].end()}` anew at every step (models.hpp:135), which
         // yields the same three objects
-        using transition_t = ::cpprob::discrete_distribution<std::size_t, double, k>;
+        // (the state is an `int` here, std::size_t in the reference: same values, same records, but 32-bit
+        // compares on the device)
+        using transition_t = ::cpprob::discrete_distribution<int, double, k>;
         const ::cpprob::reg_table<transition_t, k> transition{{transition_t{T[0]}, transition_t{T[1]}, transition_t{T[2]}}};
-        const ::cpprob::uniform_smallint<std::size_t> prior{0, 2};
+        const ::cpprob::uniform_smallint<int> prior{0, 2};
         auto state = cpprob.sample(prior, true);
         cpprob.predict(state, "State");
         auto obs_it = observed_states.begin();
