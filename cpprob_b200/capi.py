@@ -25,7 +25,7 @@ SYMBOLS = [
     "cpprob_sis_describe", "cpprob_sis_run", "cpprob_sis_infer_to_files", "cpprob_sis_run_shard",
     "cpprob_sis_merge", "cpprob_sis_replay", "cpprob_sis_reduce_records", "cpprob_sis_logpdf",
     "cpprob_sis_sample", "cpprob_sis_philox", "cpprob_sis_dmath", "cpprob_sis_measure_dfma_peak",
-    "cpprob_sis_measure_store_peak", "cpprob_sis_plan_shard", "cpprob_sis_probe_issue", "cpprob_sis_probe_dfma_chains",
+    "cpprob_sis_measure_store_peak", "cpprob_sis_plan_shard", "cpprob_sis_probe_issue", "cpprob_sis_probe_dfma_chains", "cpprob_sis_run_multi", "cpprob_sis_write_summary",
 ]
 
 
@@ -110,6 +110,8 @@ def lib():
         L.cpprob_sis_dmath.argtypes = [C.c_void_p, C.c_int, dp, u64, dp]
         L.cpprob_sis_measure_dfma_peak.argtypes = [C.c_void_p, dp, dp]
         L.cpprob_sis_measure_store_peak.argtypes = [C.c_void_p, dp]
+        L.cpprob_sis_write_summary.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(Stats)]
+        L.cpprob_sis_run_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, dp, C.c_size_t, u64, C.POINTER(Stats)]
         L.cpprob_sis_probe_issue.argtypes = [C.c_void_p, C.c_int, dp]
         L.cpprob_sis_probe_dfma_chains.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, dp]
         L.cpprob_sis_plan_shard.argtypes = [u64, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
@@ -156,6 +158,15 @@ def stats_to_dict(st, structure=None):
     d["int_map"] = np.array([st.int_map[i] for i in range(st.n_int)], dtype=np.int64)
     d["sums"] = np.array([st.sums[i] for i in range(st.n_cols)])
     return d
+
+
+def run_multi(engines, model, obs, n):
+    """cpprob_sis_run_multi: one inference over several GPUs of this process (engines[0] owns the results)."""
+    obs = _f64(obs)
+    arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    st = Stats()
+    _check(lib().cpprob_sis_run_multi(arr, len(engines), engines[0].model_id(model), _dptr(obs), obs.size, int(n), C.byref(st)))
+    return stats_to_dict(st)
 
 
 class Engine:

@@ -12,6 +12,7 @@
 #include <limits>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -797,6 +798,85 @@ int cpprob_sis_run_shard(cpprob_sis_engine * e, int model_id, const double * obs
     out->device_ms = res.device_ms;
     out->kernel_launches = res.launches;
     e->launches += res.launches;
+    return 0;
+}
+
+int cpprob_sis_write_summary(cpprob_sis_engine * e, const char * prefix, const cpprob_sis_stats * stats)
+{
+    if (!e || !prefix || !stats) return fail(CPPROB_SIS_EINVAL, "null argument");
+    if (!cpprob::text::write_ids(prefix, e->structure.ids)) return fail(CPPROB_SIS_EIO, std::string("cannot write ") + prefix + ".ids");
+    if (!cpprob::text::write_stats_sidecar(prefix, *stats, e->slots, e->structure.ids)) {
+        return fail(CPPROB_SIS_EIO, std::string("cannot write ") + prefix + ".stats");
+    }
+    return 0;
+}
+
+int cpprob_sis_run_multi(cpprob_sis_engine * const * engines, int n_engines, int model_id, const double * obs, size_t n_obs,
+                         uint64_t n_particles, cpprob_sis_stats * out)
+{
+    if (!engines || n_engines <= 0 || !obs || !out) return fail(CPPROB_SIS_EINVAL, "bad argument");
+    for (int r = 0; r < n_engines; ++r) {
+        if (!engines[r]) return fail(CPPROB_SIS_EINVAL, "null engine");
+        if (engines[r]->seed != engines[0]->seed) return fail(CPPROB_SIS_EINVAL, "all engines of a multi-GPU run must share one seed");
+    }
+    const cpprob_sis_model_vtable * vt = model_of(model_id);
+    if (!vt) return fail(CPPROB_SIS_ENOMODEL, "unknown model id");
+    cpprob_sis_engine * primary = engines[0];
+    double m_ref_override = 0.0;
+    const double * mo = nullptr;
+    double total_ms = 0.0;
+    uint64_t launches = 0;
+    for (int pass = 1;; ++pass) {
+        // one host thread per GPU; every shard leaves its partial rows in its own engine
+        std::vector<shard_result> res(static_cast<size_t>(n_engines));
+        std::vector<int> rc(static_cast<size_t>(n_engines), 0);
+        std::vector<std::string> msg(static_cast<size_t>(n_engines));
+        std::vector<std::thread> pool;
+        for (int r = 0; r < n_engines; ++r) {
+            pool.emplace_back([&, r] {
+                shard_options so;
+                rc[static_cast<size_t>(r)] = run_shard_impl(engines[r], vt, obs, n_obs, n_particles, r, n_engines, mo, nullptr, so, &res[static_cast<size_t>(r)]);
+                if (rc[static_cast<size_t>(r)] != 0) msg[static_cast<size_t>(r)] = g_last_error;   // thread-local: carry it out
+            });
+        }
+        for (auto & t : pool) t.join();
+        for (int r = 0; r < n_engines; ++r) {
+            if (rc[static_cast<size_t>(r)] != 0) return fail(rc[static_cast<size_t>(r)], "device " + std::to_string(engines[r]->device) + ": " + msg[static_cast<size_t>(r)]);
+        }
+        // gather in rank order on the primary GPU (peer copies over NVLink), then the usual merge
+        if (int rc0 = use_device(primary)) return rc0;
+        const int n_cols = res[0].n_cols;
+        const uint32_t rows_total = res[0].n_rows_total;
+        CU_TRY(primary->d_gather.reserve(static_cast<size_t>(rows_total) * n_cols));
+        double shard_ms = 0.0;
+        for (int r = 0; r < n_engines; ++r) {
+            const shard_result & sr = res[static_cast<size_t>(r)];
+            shard_ms = std::max(shard_ms, sr.device_ms);
+            launches += sr.launches;
+            if (sr.n_rows_local == 0) continue;
+            CU_TRY(cudaMemcpyPeerAsync(primary->d_gather.ptr + static_cast<size_t>(sr.row_first) * n_cols, primary->device,
+                                       engines[r]->d_partials.ptr, engines[r]->device,
+                                       static_cast<size_t>(sr.n_rows_local) * n_cols * sizeof(double), primary->compute));
+        }
+        double merge_ms = 0.0;
+        const int mrc = merge_impl(primary, primary->d_gather.ptr, rows_total, n_cols, static_cast<int>(primary->structure.n_real),
+                                   static_cast<int>(primary->structure.n_int), res[0].hw, res[0].m_ref, n_particles, out, &launches, &merge_ms);
+        if (mrc < 0) return mrc;
+        total_ms += shard_ms + merge_ms;
+        if (primary->structure.n_int > 0 && out->sums[col::int_oor] != 0.0) {
+            return fail(CPPROB_SIS_ERANGE, "int predicts fell outside the pilot's histogram window");
+        }
+        if (mrc == 1 && pass < 3) {
+            m_ref_override = out->max_log_w;
+            mo = &m_ref_override;
+            continue;
+        }
+        out->passes = pass;
+        break;
+    }
+    out->device_ms = total_ms;
+    out->kernel_launches = launches;
+    primary->launches += launches;
     return 0;
 }
 

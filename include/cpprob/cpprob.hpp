@@ -18,18 +18,21 @@
 //   * the progress line printed every 100 traces (cpprob.hpp:195-197) is dropped: at 10^9 particles it
 //     would be 10^7 lines.
 // Environment knobs (additions, all optional): CPPROB_SIS_SEED, CPPROB_SIS_DEVICE,
-// CPPROB_SIS_EMIT=all|none (none: estimators + .ids + .stats only, no per-particle records).
+// CPPROB_SIS_EMIT=all|none (none: estimators + .ids + .stats only, no per-particle records),
+// CPPROB_SIS_DEVICES=0,1,... (with EMIT=none: shard the particles over these GPUs).
 #ifndef INCLUDE_CPPROB_HPP
 #define INCLUDE_CPPROB_HPP
 
 #include <cstddef>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <tuple>
 #include <type_traits>
 #include <utility>
+#include <vector>
 
 #include "cpprob/distributions/distributions.hpp"
 #include "cpprob/engine.hpp"
@@ -146,11 +149,24 @@ void inference(
         if (std::strcmp(e, "none") == 0) emit = CPPROB_SIS_EMIT_NONE;
     }
 
-    sis::engine engine;
-    const int model = engine.model_id(who.name);
     detail::last_run_t & last = detail::last_run();
     last.valid = false;
-    last.stats = engine.infer_to_files(model, who.obs, n, file_name, emit);
+    const std::vector<int> devices = sis::device_list();
+    if (emit == CPPROB_SIS_EMIT_NONE && devices.size() > 1) {
+        // estimators only, particles sharded over the listed GPUs of this box (one host thread per GPU)
+        const std::uint64_t seed = sis::default_seed();
+        std::vector<std::unique_ptr<sis::engine>> engines;
+        for (int d : devices) engines.emplace_back(new sis::engine(d, seed));
+        std::vector<sis::engine *> others;
+        for (std::size_t i = 1; i < engines.size(); ++i) others.push_back(engines[i].get());
+        const int model = engines[0]->model_id(who.name);
+        last.stats = engines[0]->run_multi(others, model, who.obs, n);
+        sis::check(cpprob_sis_write_summary(engines[0]->handle(), file_name.c_str(), &last.stats), "cpprob_sis_write_summary");
+    } else {
+        sis::engine engine;
+        const int model = engine.model_id(who.name);
+        last.stats = engine.infer_to_files(model, who.obs, n, file_name, emit);
+    }
     // the stats struct points into engine-owned memory: keep only the scalars
     last.stats.real_mean = last.stats.real_var = last.stats.int_prob = last.stats.sums = nullptr;
     last.stats.int_map = nullptr;

@@ -40,6 +40,23 @@ inline int default_device()
     return 0;
 }
 
+// CPPROB_SIS_DEVICES="0,1,2,3": the GPUs a stats-only inference is sharded over (empty: one GPU)
+inline std::vector<int> device_list()
+{
+    std::vector<int> out;
+    if (const char * s = std::getenv("CPPROB_SIS_DEVICES")) {
+        const char * p = s;
+        while (*p) {
+            char * end = nullptr;
+            const long v = std::strtol(p, &end, 10);
+            if (end == p) break;
+            out.push_back(static_cast<int>(v));
+            p = (*end == ',') ? end + 1 : end;
+        }
+    }
+    return out;
+}
+
 class engine {
 public:
     explicit engine(int device = default_device(), std::uint64_t seed = default_seed())
@@ -68,6 +85,16 @@ public:
     {
         cpprob_sis_stats st;
         check(cpprob_sis_infer_to_files(h_, model, obs.data(), obs.size(), n, prefix.c_str(), emit, &st), "cpprob_sis_infer_to_files");
+        return st;
+    }
+
+    // stats-only inference sharded over several engines (this one is rank 0 and owns the results)
+    cpprob_sis_stats run_multi(const std::vector<engine *> & others, int model, const std::vector<double> & obs, std::uint64_t n)
+    {
+        std::vector<cpprob_sis_engine *> hs(1, h_);
+        for (engine * e : others) hs.push_back(e->handle());
+        cpprob_sis_stats st;
+        check(cpprob_sis_run_multi(hs.data(), static_cast<int>(hs.size()), model, obs.data(), obs.size(), n, &st), "cpprob_sis_run_multi");
         return st;
     }
 

@@ -183,6 +183,16 @@ int cpprob_sis_run_shard(cpprob_sis_engine * e, int model_id, const double * obs
                          const double * m_ref_override /* NULL: pilot */,
                          cpprob_sis_partials * out);
 
+/* Single-process form of the same scheme: engines[r] (one per GPU, created by the caller with ONE seed) runs shard r
+ * on its own host thread; the partial rows are copied peer-to-peer to engines[0]'s GPU in rank order and merged
+ * there.  Estimators only (no trace emission).  Results are owned by engines[0] and are bit-identical to a
+ * single-GPU run of the same seed. */
+int cpprob_sis_run_multi(cpprob_sis_engine * const * engines, int n_engines, int model_id, const double * obs,
+                         size_t n_obs, uint64_t n_particles, cpprob_sis_stats * out);
+
+/* Writes <prefix>.ids and <prefix>.stats for the engine's last run (what infer_to_files does with EMIT_NONE). */
+int cpprob_sis_write_summary(cpprob_sis_engine * e, const char * prefix, const cpprob_sis_stats * stats);
+
 /* gathered: DEVICE pointer to [n_chunks_total][n_cols].  Returns 1 (not an error) if the weights
  * have to be re-based: call run_shard again with *m_ref_override = out->max_log_w. */
 int cpprob_sis_merge(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs,

@@ -299,3 +299,25 @@ def test_structure_probe(engine):
     assert d["ids"] == ["State"] and d["n_real"] == 32 and [s[2] for s in d["slots"]] == list(range(32))
     d = engine.describe("hmm", G["obs_hmm_64"])
     assert d["ids"] == ["State"] and d["n_int"] == 64 and d["n_real"] == 0 and d["n_samples"] == 64
+
+
+def test_single_process_multi_gpu_is_bit_identical():
+    """cpprob_sis_run_multi: shards on several GPUs of one process, peer-copied partials, merge on GPU 0."""
+    import torch
+    from cpprob_b200 import Engine
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = 61 * capi.CHUNK + 99
+    with Engine(device=0, seed=77) as ref:
+        base = ref.run("gaussian_unknown_mean", [3.0, 4.0], n)
+        base_hmm = ref.run("hmm", G["obs_hmm_64"][:9], n // 8)
+    engines = [Engine(device=d, seed=77) for d in range(min(n_dev, 8))]
+    try:
+        st = capi.run_multi(engines, "gaussian_unknown_mean", [3.0, 4.0], n)
+        assert (st["sums"] == base["sums"]).all() and st["real_mean"][0] == base["real_mean"][0]
+        st = capi.run_multi(engines, "hmm", G["obs_hmm_64"][:9], n // 8)
+        assert (st["sums"] == base_hmm["sums"]).all()
+    finally:
+        for e in engines:
+            e.close()
