@@ -26,6 +26,7 @@ SYMBOLS = [
     "cpprob_sis_merge", "cpprob_sis_replay", "cpprob_sis_reduce_records", "cpprob_sis_logpdf",
     "cpprob_sis_sample", "cpprob_sis_philox", "cpprob_sis_dmath", "cpprob_sis_measure_dfma_peak",
     "cpprob_sis_measure_store_peak", "cpprob_sis_plan_shard", "cpprob_sis_probe_issue", "cpprob_sis_probe_dfma_chains", "cpprob_sis_run_multi", "cpprob_sis_write_summary",
+    "cpprob_sis_text_stage_stats",
 ]
 
 
@@ -112,6 +113,7 @@ def lib():
         L.cpprob_sis_measure_store_peak.argtypes = [C.c_void_p, dp]
         L.cpprob_sis_write_summary.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(Stats)]
         L.cpprob_sis_run_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, dp, C.c_size_t, u64, C.POINTER(Stats)]
+        L.cpprob_sis_text_stage_stats.argtypes = [C.c_void_p, dp, dp, dp, C.POINTER(u64), C.POINTER(u64)]
         L.cpprob_sis_probe_issue.argtypes = [C.c_void_p, C.c_int, dp]
         L.cpprob_sis_probe_dfma_chains.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, dp]
         L.cpprob_sis_plan_shard.argtypes = [u64, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
@@ -244,6 +246,13 @@ class Engine:
         _check(self._L.cpprob_sis_infer_to_files(self._h, self.model_id(model), _dptr(obs), obs.size, int(n), prefix.encode(), emit,
                                                  C.byref(st)))
         return stats_to_dict(st)
+
+    def text_stage_stats(self):
+        """Stage times of the last infer_to_files(EMIT_ALL): GPU text kernels, D2H copies, host file writes."""
+        k, c, w = C.c_double(), C.c_double(), C.c_double()
+        b, f = C.c_uint64(), C.c_uint64()
+        _check(self._L.cpprob_sis_text_stage_stats(self._h, C.byref(k), C.byref(c), C.byref(w), C.byref(b), C.byref(f)))
+        return {"kernel_ms": k.value, "copy_ms": c.value, "write_s": w.value, "bytes": b.value, "fixups": f.value}
 
     def run_shard(self, model, obs, n_total, rank, world, m_ref=None):
         obs = _f64(obs)

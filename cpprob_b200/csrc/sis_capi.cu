@@ -5,12 +5,14 @@
 // and pinned buffers grow on demand and are kept between calls.
 #include <algorithm>
 #include <cerrno>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
+#include <future>
 #include <string>
 #include <thread>
 #include <vector>
@@ -22,6 +24,7 @@
 #include "model_vtable.cuh"
 #include "posterior_text.hpp"
 #include "reduce_kernels.cuh"
+#include "text_kernels.cuh"
 
 using namespace cpprob;
 using namespace cpprob::engine;
@@ -122,6 +125,19 @@ struct cpprob_sis_engine {
     device_buffer<int> d_int[2];
     device_buffer<unsigned> d_counter;
     device_buffer<int_extra> d_int_extra;
+    // device-side text stage: per-record lengths, CTA sums / offsets, the text itself, slot descriptors, ambiguity list
+    device_buffer<unsigned> d_text_len;
+    device_buffer<unsigned long long> d_text_bsum, d_text_meta;   // meta: [kind]{total bytes, #ambiguous}
+    device_buffer<char> d_text[2][2];                             // [double buffer][kind: 0 real, 1 int]
+    device_buffer<text_slot> d_text_slots[2];
+    device_buffer<text_flag> d_text_flags;                        // [kind][kMaxTextFlags]
+    pinned_buffer<char> h_text[2][2];
+    pinned_buffer<unsigned long long> h_text_meta[2];
+    pinned_buffer<text_flag> h_text_flags;
+    cudaEvent_t ev_text[2] = {nullptr, nullptr}, ev_copy_begin[2] = {nullptr, nullptr};
+    unsigned long long text_force_every = 0;                      // CPPROB_SIS_TEXT_FORCE_AMBIGUOUS (test hook)
+    double text_kernel_ms = 0.0, text_copy_ms = 0.0, text_write_s = 0.0;   // stage times of the last emitting run
+    uint64_t text_bytes = 0, text_fixups = 0;
     pinned_buffer<double> h_real[2], h_logw[2], h_merged;
     pinned_buffer<int> h_int[2];
 
@@ -257,11 +273,14 @@ int run_pilot(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, const p
     return 0;
 }
 
+constexpr unsigned kMaxTextFlags = 4096;   // ambiguous records per batch and kind the host can re-format
+
 struct shard_options {
     int emit = CPPROB_SIS_EMIT_NONE;
     int force_rows = 0;
     cpprob_sis_block_fn on_block = nullptr;
     void * user = nullptr;
+    cpprob::text::posterior_writer * text_writer = nullptr;   // EMIT_ALL with the records formatted on the GPU
 };
 
 struct shard_result {
@@ -367,7 +386,10 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     // ---- row path: batches of whole chunks ------------------------------------------------------
     const bool emit = opt.emit == CPPROB_SIS_EMIT_ALL;
     const uint64_t bytes_per_particle = 8ull * n_real + 4ull * n_int + 16ull;
-    const uint64_t budget = emit ? (512ull << 20) : (8192ull << 20);
+    // EMIT_ALL with a text writer: the records are formatted on the GPU (text_kernels.cuh) and only text crosses
+    // PCIe; a line is ~3.3x its binary record, so the batches are smaller
+    const bool text_mode = emit && opt.text_writer != nullptr;
+    const uint64_t budget = text_mode ? (128ull << 20) : (emit ? (512ull << 20) : (8192ull << 20));
     uint64_t cap = e->max_batch ? e->max_batch : budget / bytes_per_particle;
     cap = std::max<uint64_t>(kChunk, cap / kChunk * kChunk);
     cap = std::min<uint64_t>(cap, static_cast<uint64_t>(plan.n_chunks_local) * kChunk);
@@ -377,7 +399,7 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         CU_TRY(e->d_int[b].reserve(std::max<size_t>(1, static_cast<size_t>(n_int) * cap)));
         CU_TRY(e->d_logw[b].reserve(cap));
         CU_TRY(e->d_w[b].reserve(cap));
-        if (emit) {
+        if (emit && !text_mode) {
             CU_TRY(e->h_real[b].reserve(std::max<size_t>(1, static_cast<size_t>(n_real) * cap)));
             CU_TRY(e->h_int[b].reserve(std::max<size_t>(1, static_cast<size_t>(n_int) * cap)));
             CU_TRY(e->h_logw[b].reserve(cap));
@@ -388,9 +410,67 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     if (occ <= 0) occ = 1;
     if (e->blocks_per_sm > 0) occ = std::min(occ, e->blocks_per_sm);
 
+    // text stage set-up: slot descriptors on the device, worst-case line length per kind
+    size_t max_line[2] = {0, 0};
+    int n_text_slots[2] = {0, 0};
+    if (text_mode) {
+        e->text_kernel_ms = e->text_copy_ms = e->text_write_s = 0.0;
+        e->text_bytes = e->text_fixups = 0;
+        for (int kind = 0; kind < 2; ++kind) {
+            const std::vector<cpprob_sis_slot> & sl = opt.text_writer->slots(kind == 1);
+            if (sl.empty()) continue;
+            std::vector<text_slot> h;
+            size_t line = 4 + 24 + 2;                                  // "([" ... "] " logw ")\n"
+            for (const auto & s : sl) {
+                h.push_back(text_slot{s.id, s.row, s.width});
+                line += 16 + (kind == 1 ? 12 : static_cast<size_t>(s.width) * 25 + 2);   // "(id " value ") "
+            }
+            n_text_slots[kind] = static_cast<int>(h.size());
+            max_line[kind] = line;
+            CU_TRY(e->d_text_slots[kind].reserve(h.size()));
+            CU_TRY(cudaMemcpy(e->d_text_slots[kind].ptr, h.data(), h.size() * sizeof(text_slot), cudaMemcpyHostToDevice));
+            for (int b = 0; b < 2; ++b) {
+                CU_TRY(e->d_text[b][kind].reserve(line * cap));
+                CU_TRY(e->h_text[b][kind].reserve(line * cap));
+            }
+        }
+        CU_TRY(e->d_text_len.reserve(cap));
+        CU_TRY(e->d_text_bsum.reserve((cap + kTextBlock - 1) / kTextBlock));
+        CU_TRY(e->d_text_meta.reserve(4));
+        CU_TRY(e->d_text_flags.reserve(2 * kMaxTextFlags));
+        CU_TRY(e->h_text_flags.reserve(4 * kMaxTextFlags));
+        for (int b = 0; b < 2; ++b) CU_TRY(e->h_text_meta[b].reserve(4));
+    }
+
     const uint64_t n_batches = (plan.n_local + cap - 1) / cap;
-    struct pending_block { bool valid = false; uint64_t first = 0, n = 0; };
+    struct pending_block { bool valid = false; uint64_t first = 0, n = 0; unsigned long long text_bytes[2] = {0, 0}, text_flags[2] = {0, 0}; };
     pending_block pending[2];
+    // a record the GPU formatter could not decide (text_format.cuh): its line is re-made on the host from the
+    // values still in the device rows and patched into the pinned text
+    auto fix_up = [&](int buf, int kind, const text_flag & fl) -> int {
+        std::vector<double> rv(std::max(1, n_real));
+        std::vector<int> iv(std::max(1, n_int));
+        double lw = 0.0;
+        if (n_real > 0) CU_TRY(cudaMemcpy2D(rv.data(), sizeof(double), e->d_real[buf].ptr + fl.record, cap * sizeof(double), sizeof(double), n_real, cudaMemcpyDeviceToHost));
+        if (n_int > 0) CU_TRY(cudaMemcpy2D(iv.data(), sizeof(int), e->d_int[buf].ptr + fl.record, cap * sizeof(int), sizeof(int), n_int, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(&lw, e->d_logw[buf].ptr + fl.record, sizeof(double), cudaMemcpyDeviceToHost));
+        cpprob_sis_block one;
+        one.first_particle = pending[buf].first + fl.record;
+        one.n = 1;
+        one.stride = 1;
+        one.n_real = n_real;
+        one.n_int = n_int;
+        one.real_rows = rv.data();
+        one.int_rows = iv.data();
+        one.log_w = &lw;
+        const std::string line = opt.text_writer->format_record(one, kind == 1, 0);
+        if (line.size() != fl.length || fl.offset + fl.length > pending[buf].text_bytes[kind]) {
+            return fail(CPPROB_SIS_EIO, "device text stage: host re-formatting of an ambiguous record changed its length");
+        }
+        std::memcpy(e->h_text[buf][kind].ptr + fl.offset, line.data(), line.size());
+        ++e->text_fixups;
+        return 0;
+    };
     auto deliver = [&](int buf) -> int {
         if (!pending[buf].valid) return 0;
         CU_TRY(cudaEventSynchronize(e->ev_copied[buf]));
@@ -398,6 +478,23 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         CU_TRY(cudaEventElapsedTime(&ms, e->ev_batch_begin[buf], e->ev_computed[buf]));
         res->device_ms += ms;
         pending[buf].valid = false;
+        if (text_mode) {
+            CU_TRY(cudaEventElapsedTime(&ms, e->ev_copy_begin[buf], e->ev_copied[buf]));
+            e->text_copy_ms += ms;
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int kind = 0; kind < 2; ++kind) {
+                if (!n_text_slots[kind]) continue;
+                for (unsigned long long f = 0; f < pending[buf].text_flags[kind]; ++f) {
+                    if (int rc = fix_up(buf, kind, e->h_text_flags.ptr[(2 * buf + kind) * kMaxTextFlags + f])) return rc;
+                }
+                if (!opt.text_writer->write_text(kind == 1, e->h_text[buf][kind].ptr, pending[buf].text_bytes[kind])) {
+                    return fail(CPPROB_SIS_EIO, std::string("cannot write the posterior file: ") + std::strerror(errno));
+                }
+                e->text_bytes += pending[buf].text_bytes[kind];
+            }
+            e->text_write_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            return 0;
+        }
         if (opt.on_block) {
             cpprob_sis_block blk;
             blk.first_particle = pending[buf].first;
@@ -458,7 +555,61 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
             CU_TRY(launch_hist_all(e->compute, subs_here, n_int, a.int_rows, a.w, cap, n_here, hw, kBaseCols + 2 * n_real,
                                    a.partials, n_cols, &res->launches));
         }
-        if (emit) {
+        if (text_mode) {
+            CU_TRY(cudaEventRecord(e->ev_computed[buf], e->compute));
+            CU_TRY(cudaMemsetAsync(e->d_text_meta.ptr, 0, 4 * sizeof(unsigned long long), e->compute));
+            const unsigned text_blocks = static_cast<unsigned>((n_here + kTextBlock - 1) / kTextBlock);
+            for (int kind = 0; kind < 2; ++kind) {
+                if (!n_text_slots[kind]) continue;
+                text_args ta;
+                ta.slots = e->d_text_slots[kind].ptr;
+                ta.n_slots = n_text_slots[kind];
+                ta.is_int = kind;
+                ta.real_rows = a.real_rows;
+                ta.int_rows = a.int_rows;
+                ta.logw = a.logw;
+                ta.stride = cap;
+                ta.n = n_here;
+                ta.first_particle = plan.first_particle + off;
+                ta.force_every = e->text_force_every;
+                k_text_lengths<<<text_blocks, kTextBlock, 0, e->compute>>>(ta, e->d_text_len.ptr, e->d_text_bsum.ptr);
+                CU_TRY(cudaGetLastError());
+                k_text_scan<<<1, 1024, 0, e->compute>>>(e->d_text_bsum.ptr, text_blocks, e->d_text_meta.ptr + 2 * kind);
+                CU_TRY(cudaGetLastError());
+                k_text_write<<<text_blocks, kTextBlock, 0, e->compute>>>(ta, e->d_text_len.ptr, e->d_text_bsum.ptr, e->d_text[buf][kind].ptr,
+                                                                         e->d_text_flags.ptr + kind * kMaxTextFlags,
+                                                                         e->d_text_meta.ptr + 2 * kind + 1, kMaxTextFlags);
+                CU_TRY(cudaGetLastError());
+                res->launches += 3;
+            }
+            CU_TRY(cudaMemcpyAsync(e->h_text_meta[buf].ptr, e->d_text_meta.ptr, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->compute));
+            CU_TRY(cudaEventRecord(e->ev_text[buf], e->compute));
+            // the sizes of the copies below are only known now; the batch before this one is still crossing PCIe /
+            // being written meanwhile
+            CU_TRY(cudaEventSynchronize(e->ev_text[buf]));
+            float tms = 0.f;
+            CU_TRY(cudaEventElapsedTime(&tms, e->ev_computed[buf], e->ev_text[buf]));
+            e->text_kernel_ms += tms;
+            CU_TRY(cudaEventRecord(e->ev_copy_begin[buf], e->copy));
+            for (int kind = 0; kind < 2; ++kind) {
+                if (!n_text_slots[kind]) continue;
+                const unsigned long long total = e->h_text_meta[buf].ptr[2 * kind], nf = e->h_text_meta[buf].ptr[2 * kind + 1];
+                if (total > max_line[kind] * cap) return fail(CPPROB_SIS_EIO, "device text stage: line longer than its bound");
+                if (nf > kMaxTextFlags) return fail(CPPROB_SIS_EIO, "device text stage: too many ambiguous records in one batch");
+                CU_TRY(cudaMemcpyAsync(e->h_text[buf][kind].ptr, e->d_text[buf][kind].ptr, total, cudaMemcpyDeviceToHost, e->copy));
+                if (nf) {
+                    CU_TRY(cudaMemcpyAsync(e->h_text_flags.ptr + (2 * buf + kind) * kMaxTextFlags, e->d_text_flags.ptr + kind * kMaxTextFlags,
+                                           nf * sizeof(text_flag), cudaMemcpyDeviceToHost, e->copy));
+                }
+                pending[buf].text_bytes[kind] = total;
+                pending[buf].text_flags[kind] = nf;
+            }
+            CU_TRY(cudaEventRecord(e->ev_copied[buf], e->copy));
+            pending[buf].valid = true;
+            pending[buf].first = plan.first_particle + off;
+            pending[buf].n = n_here;
+            if (int rc = deliver(buf ^ 1)) return rc;
+        } else if (emit) {
             CU_TRY(cudaEventRecord(e->ev_computed[buf], e->compute));
             CU_TRY(cudaStreamWaitEvent(e->copy, e->ev_computed[buf], 0));
             if (n_real > 0) {
@@ -614,6 +765,7 @@ int run_full(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, const do
         // the records were already delivered in the first pass; later passes only redo the sums
         opt.emit = CPPROB_SIS_EMIT_NONE;
         opt.on_block = nullptr;
+        opt.text_writer = nullptr;
         opt.force_rows = opt_in.force_rows || opt_in.emit == CPPROB_SIS_EMIT_ALL;
     }
     out->device_ms = total_ms;
@@ -720,7 +872,10 @@ int cpprob_sis_create(const cpprob_sis_config * cfg, cpprob_sis_engine ** out)
         if ((c = cudaEventCreate(&e->ev_computed[i])) != cudaSuccess) return bail(c, "cudaEventCreate");
         if ((c = cudaEventCreate(&e->ev_copied[i])) != cudaSuccess) return bail(c, "cudaEventCreate");
         if ((c = cudaEventCreate(&e->ev_batch_begin[i])) != cudaSuccess) return bail(c, "cudaEventCreate");
+        if ((c = cudaEventCreate(&e->ev_text[i])) != cudaSuccess) return bail(c, "cudaEventCreate");
+        if ((c = cudaEventCreate(&e->ev_copy_begin[i])) != cudaSuccess) return bail(c, "cudaEventCreate");
     }
+    if (const char * s = std::getenv("CPPROB_SIS_TEXT_FORCE_AMBIGUOUS")) e->text_force_every = std::strtoull(s, nullptr, 10);
     *out = e;
     return 0;
 }
@@ -733,6 +888,13 @@ void cpprob_sis_destroy(cpprob_sis_engine * e)
     if (e->copy) cudaStreamSynchronize(e->copy);
     e->d_obs.release(); e->d_pilot.release(); e->d_partials.release(); e->d_merged.release(); e->d_gather.release();
     e->d_counter.release(); e->d_int_extra.release(); e->h_merged.release();
+    e->d_text_len.release(); e->d_text_bsum.release(); e->d_text_meta.release(); e->d_text_flags.release(); e->h_text_flags.release();
+    for (int i = 0; i < 2; ++i) {
+        e->d_text_slots[i].release(); e->h_text_meta[i].release();
+        for (int k = 0; k < 2; ++k) { e->d_text[i][k].release(); e->h_text[i][k].release(); }
+        if (e->ev_text[i]) cudaEventDestroy(e->ev_text[i]);
+        if (e->ev_copy_begin[i]) cudaEventDestroy(e->ev_copy_begin[i]);
+    }
     for (int i = 0; i < 2; ++i) {
         e->d_w[i].release(); e->d_logw[i].release(); e->d_real[i].release(); e->d_int[i].release();
         e->h_real[i].release(); e->h_logw[i].release(); e->h_int[i].release();
@@ -1250,14 +1412,33 @@ int cpprob_sis_infer_to_files(cpprob_sis_engine * e, int model_id, const double 
     file_sink fs{e, &writer};
     shard_options so;
     so.emit = CPPROB_SIS_EMIT_ALL;
-    so.on_block = &file_sink_block;
-    so.user = &fs;
+    // default: lines are formatted on the GPU and only text crosses PCIe; CPPROB_SIS_TEXT=host keeps the binary
+    // rows -> pinned host -> std::to_chars path (same bytes, used as the cross-check in tests/test_files_gpu.py)
+    const char * text_env = std::getenv("CPPROB_SIS_TEXT");
+    if (text_env && std::strcmp(text_env, "host") == 0) {
+        so.on_block = &file_sink_block;
+        so.user = &fs;
+    } else {
+        so.text_writer = &writer;
+    }
     const int rc = run_full(e, vt, obs, n_obs, n_particles, so, out);
     if (rc != 0) return rc;
     if (!writer.finish(e->structure.ids)) return fail(CPPROB_SIS_EIO, std::string("cannot write ") + prefix + ".ids");
     if (!cpprob::text::write_stats_sidecar(prefix, *out, e->slots, e->structure.ids)) {
         return fail(CPPROB_SIS_EIO, std::string("cannot write ") + prefix + ".stats");
     }
+    return 0;
+}
+
+int cpprob_sis_text_stage_stats(cpprob_sis_engine * e, double * kernel_ms, double * copy_ms, double * write_s, uint64_t * bytes,
+                                uint64_t * fixups)
+{
+    if (!e) return fail(CPPROB_SIS_EINVAL, "null engine");
+    if (kernel_ms) *kernel_ms = e->text_kernel_ms;
+    if (copy_ms) *copy_ms = e->text_copy_ms;
+    if (write_s) *write_s = e->text_write_s;
+    if (bytes) *bytes = e->text_bytes;
+    if (fixups) *fixups = e->text_fixups;
     return 0;
 }
 

@@ -155,6 +155,16 @@ int cpprob_sis_infer_to_files(cpprob_sis_engine * e, int model_id, const double 
                               uint64_t n_particles, const char * prefix, int emit /* CPPROB_SIS_EMIT_* */,
                               cpprob_sis_stats * out);
 
+/* Stage times of the last cpprob_sis_infer_to_files(..., EMIT_ALL) on this engine: the lines are formatted on
+ * the GPU (`%.15e` exactly as the reference's ostream, cpprob_b200/csrc/text_format.cuh), only text crosses
+ * PCIe, and the host appends it with concurrent pwrites.  kernel_ms: text kernels (CUDA events); copy_ms:
+ * device->pinned-host copies (CUDA events); write_s: host wall time inside the file writes; bytes: text
+ * written; fixups: lines the host had to re-format (undecidable last digit, probability ~1e-22 per value).
+ * Any pointer may be NULL.  CPPROB_SIS_TEXT=host selects the older path (binary rows to the host, formatted
+ * there by std::to_chars), which produces the same bytes. */
+int cpprob_sis_text_stage_stats(cpprob_sis_engine * e, double * kernel_ms, double * copy_ms, double * write_s,
+                                uint64_t * bytes, uint64_t * fixups);
+
 /* ---- multi-GPU: shard / gather / merge ---------------------------------------------------------
  * Particles are i.i.d. (cpprob.hpp:194-201 has no inter-particle dependence), so rank r of `world`
  * takes the chunk range [r*C/world, (r+1)*C/world) of the C = ceil(n/32768) chunks and no data-path

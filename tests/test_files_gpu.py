@@ -69,3 +69,80 @@ def test_multi_batch_emission_order(tmp_path):
         ref = e2.run("linear_gaussian_1d", G["obs_linear_gaussian_32"][:4], n, collect=True)
     assert (out["real_rows"] == ref["real_rows"]).all() and (out["log_w"] == ref["log_w"]).all()
     assert (out["sums"] == ref["sums"]).all()
+
+
+# ---- device-side text stage: the GPU formats the lines, only text crosses PCIe --------
+def _files(tmp, name):
+    return {ext: open(os.path.join(tmp, name + ext), "rb").read() for ext in (".real", ".int", ".ids")
+            if os.path.exists(os.path.join(tmp, name + ext))}
+
+
+@pytest.mark.parametrize("model,obs_key,n_obs,n", [
+    ("gaussian_unknown_mean", None, 2, 70_001),
+    ("linear_gaussian_1d", "obs_linear_gaussian_32", 32, 40_000),
+    ("hmm", "obs_hmm_64", 64, 33_000),
+    ("gaussian_2d_unk_mean", None, 2, 10_000),      # vector predicts: `(id [a b])`
+    ("all_distr", None, 2, 20_000),                 # real and int kinds in the same run
+])
+def test_gpu_text_equals_host_text(model, obs_key, n_obs, n, tmp_path, monkeypatch):
+    """The lines formatted on the GPU are byte-identical to the host writer's (std::to_chars == printf %.15e ==
+    ostream << scientific << setprecision(15)), for every record kind, across several batches."""
+    from cpprob_b200 import Engine
+    obs = G[obs_key][:n_obs] if obs_key else ([3.0, 4.0][:n_obs] if n_obs else [])
+    with Engine(seed=0xABCD, max_batch=capi.CHUNK) as e:
+        if model not in e.models():
+            pytest.skip(f"{model} not built in")
+        try:
+            e.describe(model, obs)
+        except capi.SisError:
+            pytest.skip(f"{model} takes other observations")
+        monkeypatch.delenv("CPPROB_SIS_TEXT", raising=False)
+        e.infer_to_files(model, obs, n, str(tmp_path / "gpu"))
+        ts = e.text_stage_stats()
+        monkeypatch.setenv("CPPROB_SIS_TEXT", "host")
+        e.infer_to_files(model, obs, n, str(tmp_path / "host"))
+    a, b = _files(tmp_path, "gpu"), _files(tmp_path, "host")
+    assert a.keys() == b.keys() and len(a) >= 2
+    for ext in a:
+        assert a[ext] == b[ext], f"{model}{ext} differs between the GPU and the host formatter"
+    assert ts["bytes"] == sum(len(v) for k, v in a.items() if k != ".ids") and ts["fixups"] == 0
+    assert ts["kernel_ms"] > 0 and ts["copy_ms"] > 0
+
+
+def test_gpu_text_special_values(tmp_path, monkeypatch):
+    """-inf log-weights (an observation outside the support) print as `-inf`, as the reference's ostream does."""
+    from cpprob_b200 import Engine
+    with Engine(seed=3) as e:
+        # linear_gaussian_1d with an infinite observation: logpdf<normal> returns -inf (utils_normal_distribution.hpp:30-33)
+        obs = [0.5, float("inf"), 1.0]
+        monkeypatch.delenv("CPPROB_SIS_TEXT", raising=False)
+        e.infer_to_files("linear_gaussian_1d", obs, 1000, str(tmp_path / "gpu"))
+        monkeypatch.setenv("CPPROB_SIS_TEXT", "host")
+        e.infer_to_files("linear_gaussian_1d", obs, 1000, str(tmp_path / "host"))
+    a, b = _files(tmp_path, "gpu"), _files(tmp_path, "host")
+    assert a == b
+    assert all(l.endswith(b" -inf)") for l in a[".real"].splitlines())
+
+
+def test_gpu_text_ambiguous_records_are_fixed_on_the_host(tmp_path, monkeypatch):
+    """Test hook: every 977th record is reported as undecidable and damaged on the device; the host re-formats
+    exactly those from the device rows, so the file is still byte-identical."""
+    from cpprob_b200 import Engine
+    monkeypatch.setenv("CPPROB_SIS_TEXT_FORCE_AMBIGUOUS", "977")
+    monkeypatch.delenv("CPPROB_SIS_TEXT", raising=False)
+    n = 3 * capi.CHUNK + 5
+    with Engine(seed=11, max_batch=capi.CHUNK) as e:
+        e.infer_to_files("linear_gaussian_1d", G["obs_linear_gaussian_32"][:5], n, str(tmp_path / "gpu"))
+        ts = e.text_stage_stats()
+        e.infer_to_files("hmm", G["obs_hmm_64"][:9], n, str(tmp_path / "gpui"))
+        ti = e.text_stage_stats()
+    monkeypatch.delenv("CPPROB_SIS_TEXT_FORCE_AMBIGUOUS")
+    monkeypatch.setenv("CPPROB_SIS_TEXT", "host")
+    with Engine(seed=11) as e:
+        e.infer_to_files("linear_gaussian_1d", G["obs_linear_gaussian_32"][:5], n, str(tmp_path / "host"))
+        e.infer_to_files("hmm", G["obs_hmm_64"][:9], n, str(tmp_path / "hosti"))
+    expected = (n + 976) // 977
+    assert ts["fixups"] == expected and ti["fixups"] == expected
+    assert _files(tmp_path, "gpu") == _files(tmp_path, "host")
+    assert _files(tmp_path, "gpui") == _files(tmp_path, "hosti")
+    assert b"#" not in _files(tmp_path, "gpu")[".real"]
