@@ -24,7 +24,6 @@ def write_sass_budget(lib):
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import sass_mix
     b = sass_mix.loop_budget(lib, HEADLINE_KERNEL)
-    b["particles_per_trip"] = 2 * b["box_muller"]          # one Box-Muller transform feeds the two particles of a stream pair
     b["kernel"] = HEADLINE_KERNEL
     with open(os.path.join(os.path.dirname(lib), "sass_budget.json"), "w") as f:
         json.dump(b, f)

@@ -15,18 +15,20 @@ struct dist_params { double p[8]; int n; };
 template<class F>
 __global__ void __launch_bounds__(kBlock) k_map(unsigned long long n, F f)
 {
+    const unsigned zig_base = f.prepare();
     for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(kBlock) + threadIdx.x; i < n;
          i += static_cast<unsigned long long>(gridDim.x) * kBlock) {
-        f(i);
+        f(i, zig_base);
     }
 }
 
 struct logpdf_op {
+    __device__ unsigned prepare() const { return 0; }
     int kind;
     dist_params q;
     const double * x;
     double * out;
-    __device__ void operator()(unsigned long long i) const
+    __device__ void operator()(unsigned long long i, unsigned zig_base) const
     {
         const double xi = x[i];
         double r = 0.0;
@@ -66,14 +68,15 @@ struct logpdf_op {
 };
 
 struct sample_op {
+    __device__ unsigned prepare() const { return zig::load_shared(); }   // the normal / gamma samplers read the ziggurat tables
     int kind;
     dist_params q;
     unsigned long long seed, first;
     double * out;
-    __device__ void operator()(unsigned long long i) const
+    __device__ void operator()(unsigned long long i, unsigned zig_base) const
     {
         const philox_keys keys(seed);
-        philox_stream rng(keys, first + i);
+        philox_stream rng(keys, first + i, zig_base);
         double r = 0.0;
         switch (kind) {
         case CPPROB_SIS_DIST_NORMAL: r = normal_distribution<>(q.p[0], q.p[1])(rng); break;
@@ -94,10 +97,11 @@ struct sample_op {
 };
 
 struct philox_op {
+    __device__ unsigned prepare() const { return 0; }
     const unsigned * ctr;
     const unsigned * key;
     unsigned * out;
-    __device__ void operator()(unsigned long long i) const
+    __device__ void operator()(unsigned long long i, unsigned zig_base) const
     {
         unsigned o0, o1, o2, o3;
         const philox_keys keys(key[2 * i], key[2 * i + 1]);
@@ -107,10 +111,11 @@ struct philox_op {
 };
 
 struct dmath_op {
+    __device__ unsigned prepare() const { return 0; }
     int fn;
     const double * x;
     double * out;
-    __device__ void operator()(unsigned long long i) const
+    __device__ void operator()(unsigned long long i, unsigned zig_base) const
     {
         double r, s, c;
         switch (fn) {

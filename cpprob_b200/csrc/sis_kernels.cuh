@@ -142,7 +142,7 @@ __device__ __forceinline__ unsigned fetch_chunk(unsigned * counter, unsigned * s
 // thread owns local indices t and t + 256, which share one Philox stream (random/philox.hpp).
 // `global_base` is the global index of local particle 0 (a multiple of 512).
 template<class Body>
-__device__ __forceinline__ void for_each_owned_particle(const philox_keys & keys, unsigned long long global_base,
+__device__ __forceinline__ void for_each_owned_particle(const philox_keys & keys, unsigned zig_base, unsigned long long global_base,
                                                         unsigned n_here, Body && body)
 {
     constexpr unsigned kTile = 2 * kPairStride;
@@ -154,8 +154,8 @@ __device__ __forceinline__ void for_each_owned_particle(const philox_keys & keys
     // polynomial constants are fetched once for all four
 #if CPPROB_TILES_PER_TRIP == 2
     for (; tile + 2 <= full_tiles; tile += 2) {
-        philox_stream r0(keys, stream0 + static_cast<unsigned long long>(tile) * kPairStride);
-        philox_stream r1(keys, stream0 + static_cast<unsigned long long>(tile + 1) * kPairStride);
+        philox_stream r0(keys, stream0 + static_cast<unsigned long long>(tile) * kPairStride, zig_base);
+        philox_stream r1(keys, stream0 + static_cast<unsigned long long>(tile + 1) * kPairStride, zig_base);
         const unsigned i0 = tile * kTile + threadIdx.x;
         body(r0, i0);
         body(r1, i0 + kTile);
@@ -164,7 +164,7 @@ __device__ __forceinline__ void for_each_owned_particle(const philox_keys & keys
     }
 #else
     for (; tile < full_tiles; ++tile) {
-        philox_stream r0(keys, stream0 + static_cast<unsigned long long>(tile) * kPairStride);
+        philox_stream r0(keys, stream0 + static_cast<unsigned long long>(tile) * kPairStride, zig_base);
         const unsigned i0 = tile * kTile + threadIdx.x;
         body(r0, i0);
         body(r0, i0 + kPairStride);
@@ -173,7 +173,7 @@ __device__ __forceinline__ void for_each_owned_particle(const philox_keys & keys
     for (; tile * kTile < n_here; ++tile) {
         const unsigned ia = tile * kTile + threadIdx.x;
         if (ia < n_here) {
-            philox_stream rng(keys, stream0 + static_cast<unsigned long long>(tile) * kPairStride);
+            philox_stream rng(keys, stream0 + static_cast<unsigned long long>(tile) * kPairStride, zig_base);
             body(rng, ia);
             const unsigned ib = ia + kPairStride;
             if (ib < n_here) body(rng, ib);
@@ -337,10 +337,11 @@ __global__ void __launch_bounds__(kBlock) k_pilot(const __grid_constant__ philox
     __shared__ double smem[kWarps * 3];
     const Model model{};
     const obs_cache<Model> oc(obs, n_obs);
+    const unsigned zig_base = zig::load_shared();
     double v[3] = {dm::neg_inf(), dm::neg_inf(), dm::neg_inf()};   // max lw, max(-imin), max(imax)
     const unsigned base = blockIdx.x * kTile;
     const unsigned n_here = static_cast<unsigned>(n_pilot) > base ? min(static_cast<unsigned>(n_pilot) - base, kTile) : 0u;
-    for_each_owned_particle(keys, static_cast<unsigned long long>(base), n_here, [&](philox_stream & rng, unsigned) {
+    for_each_owned_particle(keys, zig_base, static_cast<unsigned long long>(base), n_here, [&](philox_stream & rng, unsigned) {
         null_policy pol;
         particle<null_policy> p(rng, pol);
         invoke_model(model, p, oc.data(), n_obs);
@@ -368,6 +369,7 @@ __global__ void __launch_bounds__(kBlock, NR == 1 ? CPPROB_FUSED_MIN_BLOCKS : 1)
     const Model model{};
     const double m_ref = *a.m_ref;
     const obs_cache<Model> oc(a.obs, a.n_obs);
+    const unsigned zig_base = zig::load_shared();
 
     for (;;) {
         const unsigned c = fetch_chunk(a.chunk_counter, &s_chunk);
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(kBlock, NR == 1 ? CPPROB_FUSED_MIN_BLOCKS : 1)
             }
         };
         reset();
-        for_each_owned_particle(a.keys, a.first_particle + base, n_here, [&](philox_stream & rng, unsigned) {
+        for_each_owned_particle(a.keys, zig_base, a.first_particle + base, n_here, [&](philox_stream & rng, unsigned) {
             reg_policy<NR> pol;
             particle<reg_policy<NR>> p(rng, pol);
             invoke_model(model, p, oc.data(), a.n_obs);
@@ -416,7 +418,7 @@ __global__ void __launch_bounds__(kBlock, NR == 1 ? CPPROB_FUSED_MIN_BLOCKS : 1)
         });
         if (__syncthreads_or(k_min < -1021 || exp_max == 0x7FF00000u)) {
             reset();
-            for_each_owned_particle(a.keys, a.first_particle + base, n_here, [&](philox_stream & rng, unsigned) {
+            for_each_owned_particle(a.keys, zig_base, a.first_particle + base, n_here, [&](philox_stream & rng, unsigned) {
                 reg_policy<NR> pol;
                 particle<reg_policy<NR>> p(rng, pol);
                 invoke_model(model, p, oc.data(), a.n_obs);
@@ -465,6 +467,7 @@ __global__ void __launch_bounds__(kBlock) k_sis_rows(const __grid_constant__ run
     const obs_cache<Model> oc(a.obs, a.n_obs);
     const unsigned n_tiles = static_cast<unsigned>((a.n_particles + kTile - 1) / kTile);
     const unsigned long long stream0 = stream_of_particle(a.first_particle) + threadIdx.x;
+    const unsigned zig_base = zig::load_shared();
 
     for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const unsigned long long base = static_cast<unsigned long long>(tile) * kTile;
@@ -472,7 +475,7 @@ __global__ void __launch_bounds__(kBlock) k_sis_rows(const __grid_constant__ run
         const unsigned n_here = left < kTile ? static_cast<unsigned>(left) : kTile;
         int vmin = 0x7fffffff, vmax = static_cast<int>(0x80000000u);
         if (threadIdx.x < n_here) {
-            philox_stream rng(a.keys, stream0 + static_cast<unsigned long long>(tile) * kPairStride);
+            philox_stream rng(a.keys, stream0 + static_cast<unsigned long long>(tile) * kPairStride, zig_base);
 #pragma unroll 1
             for (unsigned turn = 0; turn < 2; ++turn) {
                 const unsigned i = threadIdx.x + turn * kPairStride;

@@ -15,18 +15,23 @@
 //
 //     stream(p) = (p >> 9) * 256 + (p & 255)        turn(p) = (p >> 8) & 1
 //
-// so that a Box-Muller pair left over by the first particle (the README model draws a single
-// normal) is used by the second one instead of being thrown away, while consecutive lanes still
-// own consecutive particles (coalesced trace rows).  The draws of particle p are a pure function of
+// so that the half block left over by the first particle (the README model draws a single normal
+// = two words) is used by the second one instead of being thrown away, while consecutive lanes
+// still own consecutive particles (coalesced trace rows).  The draws of particle p are a pure function of
 // (seed, p): the multiset of samples of a run is identical for any GPU count / grid size / chunk
 // schedule.
 //
 // Word consumption rules (identical on host and device, they are part of the stream definition):
 //   * next_u32()      takes one 32-bit word from the current block (4 per block);
 //   * next_uniform()  takes an aligned pair of words (52 random mantissa bits, result in (0,1));
-//   * next_std_normal() returns the cached second Box-Muller variate if there is one; otherwise it
-//     discards what is left of the current block, takes a whole fresh block, runs one Box-Muller
-//     transform and caches the sine branch.
+//   * next_std_normal() takes an aligned pair of words (a, b) and runs one ziggurat trial on them
+//     (1024 layers, tools/gen_ziggurat.py): layer = a & 1023, sign = bit 10 of a, u = (b : a >> 12)
+//     * 2^-52.  99.57 % of the draws end there.  The others (wedges, the tail, rejected trials) take
+//     all further randomness from a SIDE stream — same stream id, counter word 3 = tag | 0x80000000,
+//     counter word 2 = (block index << 2 | word position) of the pair, key rotated by the trial
+//     number — so the main stream's position never depends on how a draw went.
+//     (-DCPPROB_NORMAL_BOX_MULLER selects the previous Box-Muller sampler: a whole block per pair
+//     of variates, the sine branch cached; kept for A/B measurements only.)
 #ifndef CPPROB_RANDOM_PHILOX_HPP
 #define CPPROB_RANDOM_PHILOX_HPP
 
@@ -114,12 +119,144 @@ CPPROB_HD double u52_to_open01(std::uint32_t hi_word, std::uint32_t lo_word)
 }
 }  // namespace detail
 
+
+// ------------------------------------------------------------------------------------------------
+// Ziggurat (tools/gen_ziggurat.py).  X[i]: right edges of the layers (X[0] = V/f(r), X[1] = r, X[N] = 0),
+// F[i] = exp(-X[i]^2/2).  On the device the fast path reads X[i] and X[i+1] with a per-lane index from a
+// shared-memory copy (zig::load_shared() at kernel start, returns the table's shared-space address, which
+// the streams keep in a register); X and F in global memory are only touched by the slow path.
+//
+// One trial on the word pair (a, b):   layer i = bits 3..12 of a (so that `a & 0x1ff8` IS the byte offset of
+// X[i]), sign = bit 0 of a, u = 0.m with the 52-bit mantissa m = b : (a >> 12) — 51 independent bits; the
+// last one is also the top layer bit, a dither of 2^-52 that saves an instruction — x = u X[i] rounded once,
+// as fma(1 + u, X[i], -X[i]).  Fast accept: the high word of x is below the high word of X[i+1].
+// ------------------------------------------------------------------------------------------------
+namespace zig {
+#include "cpprob/random/ziggurat_table.inc"
+constexpr int N = CPPROB_ZIG_N;
+constexpr double R = CPPROB_ZIG_R;
+static_assert(N == 1024, "the bit layout of a trial (layer = bits 3..12 of the first word) is written for 1024 layers");
+
+#if defined(__CUDACC__)
+static __device__ const double d_x[N + 1] = {CPPROB_ZIG_X_ROWS};
+static __device__ const double d_f[N + 1] = {CPPROB_ZIG_F_ROWS};
+#endif
+inline const double * h_x() { static const double t[N + 1] = {CPPROB_ZIG_X_ROWS}; return t; }
+inline const double * h_f() { static const double t[N + 1] = {CPPROB_ZIG_F_ROWS}; return t; }
+
+#if defined(__CUDACC__)
+// Every kernel that may draw a normal calls this once (all threads of the CTA) and hands the result to its
+// streams.  The address is produced by a volatile asm so that it stays in one register for the whole kernel
+// instead of being re-derived (S2UR/ULEA...) at every table access.
+__device__ __forceinline__ unsigned load_shared()
+{
+    __shared__ double t[N + 1];
+    for (int i = threadIdx.x; i <= N; i += blockDim.x) t[i] = d_x[i];
+    __syncthreads();
+    unsigned base;
+    asm volatile("{ .reg .u64 p; cvta.to.shared.u64 p, %1; cvt.u32.u64 %0, p; }" : "=r"(base) : "l"(t));
+    return base;
+}
+#endif
+
+CPPROB_HD double x_of(unsigned i)
+{
+#if CPPROB_ON_DEVICE
+    return d_x[i];
+#else
+    return h_x()[i];
+#endif
+}
+CPPROB_HD double f_of(unsigned i)
+{
+#if CPPROB_ON_DEVICE
+    return d_f[i];
+#else
+    return h_f()[i];
+#endif
+}
+
+CPPROB_HD unsigned layer_of(std::uint32_t a) { return (a >> 3) & (N - 1); }
+
+// |x| of one trial: u X[i], u = 0.m, m = b : (a >> 12); rounded once
+CPPROB_HD double trial_abs(std::uint32_t a, std::uint32_t b, double xi)
+{
+    const std::uint32_t hi = 0x3FF00000u | (b >> 12);
+    const std::uint32_t lo = (b << 20) | (a >> 12);
+#if CPPROB_ON_DEVICE
+    const double d = __hiloint2double(static_cast<int>(hi), static_cast<int>(lo));
+    return fma(d, xi, -xi);
+#else
+    const std::uint64_t bits = (static_cast<std::uint64_t>(hi) << 32) | lo;
+    double d;
+    std::memcpy(&d, &bits, sizeof d);
+    return std::fma(d, xi, -xi);
+#endif
+}
+
+CPPROB_HD std::uint32_t high_word(double x)
+{
+#if CPPROB_ON_DEVICE
+    return static_cast<std::uint32_t>(__double2hiint(x));
+#else
+    std::uint64_t bits;
+    std::memcpy(&bits, &x, sizeof bits);
+    return static_cast<std::uint32_t>(bits >> 32);
+#endif
+}
+
+CPPROB_HD double with_sign(double x, std::uint32_t a)
+{
+#if CPPROB_ON_DEVICE
+    return __hiloint2double(__double2hiint(x) ^ static_cast<int>(a << 31), __double2loint(x));
+#else
+    return (a & 1u) ? -x : x;
+#endif
+}
+
+// The 0.43 % of draws the fast test does not settle.  Pure function of its arguments (the main stream is
+// not advanced); not inlined, so the particle loops carry only a call.
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#endif
+inline double slow_path(const philox_keys & keys, std::uint32_t s_lo, std::uint32_t s_hi, std::uint32_t where, std::uint32_t tag,
+                        std::uint32_t a, std::uint32_t b)
+{
+    std::uint32_t side = 0;                                   // blocks taken from the side stream so far
+    std::uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+    for (;;) {
+        const unsigned i = layer_of(a);
+        const double x = trial_abs(a, b, x_of(i));
+        if (x < x_of(i + 1)) return with_sign(x, a);          // inside the next layer's rectangle after all
+        philox4x32::block(s_lo, s_hi, where, (tag | 0x80000000u) + (side++ << 8), keys, q0, q1, q2, q3);
+        if (i == 0) {
+            // beyond r in the base strip: the tail, by Marsaglia's exponential rejection
+            for (;;) {
+                const double u1 = detail::u52_to_open01(q0, q1), u2 = detail::u52_to_open01(q2, q3);
+                const double xx = -dm::log(u1) / R;
+                const double yy = -dm::log(u2);
+                if (yy + yy > xx * xx) return with_sign(R + xx, a);
+                philox4x32::block(s_lo, s_hi, where, (tag | 0x80000000u) + (side++ << 8), keys, q0, q1, q2, q3);
+            }
+        }
+        // wedge of layer i: y uniform between f(X[i]) and f(X[i+1])
+        const double f0 = f_of(i), f1 = f_of(i + 1);
+        const double y = fma(detail::u52_to_open01(q0, q1), f1 - f0, f0);
+        if (y < dm::exp(-0.5 * x * x)) return with_sign(x, a);
+        // rejected: a fresh trial from the rest of the side block
+        a = q2;
+        b = q3;
+    }
+}
+}  // namespace zig
+
 // One random stream.  All members live in registers on the device.
 class philox_stream {
 public:
-    CPPROB_HD philox_stream(const philox_keys & keys, std::uint64_t stream, std::uint32_t stream_tag = 0)
+    // zig_base: on the device, what zig::load_shared() returned in this kernel (unused on the host)
+    CPPROB_HD philox_stream(const philox_keys & keys, std::uint64_t stream, unsigned zig_base = 0, std::uint32_t stream_tag = 0)
         : keys_(keys), s_lo_(static_cast<std::uint32_t>(stream)), s_hi_(static_cast<std::uint32_t>(stream >> 32)),
-          tag_(stream_tag), blk_(0), pos_(4), w0_(0), w1_(0), w2_(0), w3_(0),
+          tag_(stream_tag), blk_(0), pos_(4), w0_(0), w1_(0), w2_(0), w3_(0), zig_base_(zig_base),
           spare_(0.0), has_spare_(false) {}
 
     CPPROB_HD std::uint32_t next_u32()
@@ -143,6 +280,7 @@ public:
         return u;
     }
 
+#if defined(CPPROB_NORMAL_BOX_MULLER)
     // Standard normal by Box-Muller on a whole block; the sine branch is cached.
     CPPROB_HD double next_std_normal()
     {
@@ -158,6 +296,29 @@ public:
         has_spare_ = true;
         return r * c;
     }
+#else
+    // Standard normal by the ziggurat: one aligned pair of words, two shared-memory loads, one DFMA.
+    CPPROB_HD double next_std_normal()
+    {
+        if (pos_ >= 3) refill();
+        if (pos_ == 1) { w0_ = w1_; w1_ = w2_; w2_ = w3_; pos_ = 2; }   // drop the odd word
+        const std::uint32_t a = w0_, b = w1_;
+        const std::uint32_t where = ((blk_ - 1u) << 2) | pos_;
+        w0_ = w2_; w1_ = w3_;
+        pos_ += 2;
+#if CPPROB_ON_DEVICE
+        double xi, xn;
+        const unsigned addr = zig_base_ + (a & 0x1ff8u);
+        asm("ld.shared.f64 %0, [%1];" : "=d"(xi) : "r"(addr));
+        asm("ld.shared.f64 %0, [%1+8];" : "=d"(xn) : "r"(addr));
+#else
+        const double xi = zig::x_of(zig::layer_of(a)), xn = zig::x_of(zig::layer_of(a) + 1);
+#endif
+        const double x = zig::trial_abs(a, b, xi);
+        if (CPPROB_UNLIKELY(zig::high_word(x) >= zig::high_word(xn))) return zig::slow_path(keys_, s_lo_, s_hi_, where, tag_, a, b);
+        return zig::with_sign(x, a);
+    }
+#endif
 
     CPPROB_HD std::uint32_t blocks_used() const { return blk_; }
 
@@ -172,6 +333,7 @@ private:
     const philox_keys & keys_;
     std::uint32_t s_lo_, s_hi_, tag_, blk_, pos_;
     std::uint32_t w0_, w1_, w2_, w3_;
+    unsigned zig_base_;
     double spare_;
     bool has_spare_;
 };

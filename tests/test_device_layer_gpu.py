@@ -148,6 +148,47 @@ def test_sampler_normal(engine):
     assert not (engine.sample("normal", [1.0, 1.5], 1000, seed=12) == s[:1000]).any()
 
 
+def test_sampler_normal_ziggurat_is_exact(engine):
+    """The ziggurat (include/cpprob/random/philox.hpp) at 6.4e7 draws: equiprobable-bin chi-square, the tail beyond
+    r = 4.0388 (only produced by the slow path's exponential rejection), the region around the layer edges, the
+    moments up to the 4th and the sign balance, all within 5 sigma of N(0,1)."""
+    n = 64_000_000
+    s = engine.sample("normal", [0.0, 1.0], n, seed=20240607)
+    assert np.isfinite(s).all()
+    edges = stats.norm.ppf(np.linspace(0, 1, 513)[1:-1])
+    counts = np.bincount(np.searchsorted(edges, s), minlength=512)
+    assert stats.chisquare(counts).pvalue > 1e-4
+    a = np.abs(s)
+    for lo, hi in ((4.0388498461095045, np.inf), (3.0, 4.0388498461095045), (4.5, np.inf), (0.0, 0.01), (3.9, 4.1)):
+        p = 2 * (stats.norm.sf(lo) - stats.norm.sf(hi))
+        got = np.count_nonzero((a >= lo) & (a < hi))
+        assert abs(got - n * p) < 5 * math.sqrt(n * p) + 1, (lo, hi, got, n * p)
+    assert abs(s.mean()) < 5 / math.sqrt(n)
+    assert abs((s ** 2).mean() - 1.0) < 5 * math.sqrt(2.0 / n)
+    assert abs((s ** 3).mean()) < 5 * math.sqrt(15.0 / n)
+    assert abs((s ** 4).mean() - 3.0) < 5 * math.sqrt(96.0 / n)
+    assert abs(np.count_nonzero(s > 0) - n / 2) < 5 * math.sqrt(n / 4)
+    # finer than any layer: a chi-square inside the innermost 1 % (the top layers, all wedge / cap draws)
+    inner = s[a < stats.norm.ppf(0.505)]
+    c2 = np.histogram(inner, bins=64)[0]
+    e2 = np.diff(stats.norm.cdf(np.linspace(-stats.norm.ppf(0.505), stats.norm.ppf(0.505), 65)))
+    assert stats.chisquare(c2, e2 / e2.sum() * c2.sum()).pvalue > 1e-4
+
+
+def test_sampler_normal_matches_host_twin(engine):
+    """Same header, same bits: the GPU's normals equal the host twin's (examples/zig_check.cpp).  The fast path is
+    integer work plus one fma; only the 0.43 % slow-path draws call exp / log, where libm and the device may differ
+    in the last place."""
+    import test_ziggurat
+    n = 300_000
+    host = test_ziggurat.host_normals(99, 1000, n)
+    dev = engine.sample("normal", [0.0, 1.0], n, seed=99, first=1000)
+    same = host == dev
+    assert same.mean() > 0.9999
+    np.testing.assert_allclose(dev[~same], host[~same], rtol=1e-14)
+    assert np.abs(dev).max() > 4.0388498461095045          # the tail branch was exercised
+
+
 def test_sampler_uniform_real(engine):
     s = engine.sample("uniform_real", [2.0, 9.5], N_S, seed=3)
     assert s.min() > 2.0 and s.max() < 9.5 and ks_ok(s, stats.uniform(2.0, 7.5).cdf)

@@ -18,13 +18,15 @@ def test_particle_loop_budget():
     for k in ("total", "fp64", "dfma", "dadd", "dmul"):
         assert saved[k] == b[k], k
     per = saved["particles_per_trip"]
-    assert per == 2 * b["box_muller"] and per in (2, 4)
-    # per particle: <= 64 FP64-pipe instructions and <= 120 instructions in all
-    assert b["fp64"] / per <= 64 and b["total"] / per <= 120
-    # every FP64 instruction holds the issue port for two cycles ("issue model"): the static
-    # ceiling of the FP64-pipe utilisation is 2F / (2F + O)
-    ceiling = 2 * b["fp64"] / (2 * b["fp64"] + (b["total"] - b["fp64"]))
-    assert ceiling >= 0.60
+    assert per == b["particles_per_trip"] and per in (2, 4)
+    # per particle: <= 36 FP64-pipe instructions and <= 84 hot instructions in all (the ziggurat draw is one DFMA;
+    # `cold` = call set-up that only the 0.43 % slow draws execute)
+    hot = b["total"] - b["cold"]
+    assert b["fp64"] / per <= 36 and hot / per <= 84
+    # every FP64 instruction holds the issue port for two cycles ("issue model"): issue slots per
+    # particle = 2F + O
+    slots = (2 * b["fp64"] + (hot - b["fp64"])) / per
+    assert slots <= 120
 
 
 def test_no_local_memory_in_the_particle_loop():

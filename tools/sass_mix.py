@@ -38,9 +38,17 @@ def classify(op):
     return "alu"
 
 
-def particle_loop(body, marker="MUFU.RSQ64H"):
+MARKERS = ("CALL.REL.NOINC", "MUFU.RSQ64H")   # one per normal draw: the ziggurat's slow-path call / Box-Muller's sqrt seed
+
+
+def loop_marker(body):
+    return next((m for m in MARKERS if m in body), MARKERS[0])
+
+
+def particle_loop(body, marker=None):
     """(lo, hi) addresses of the innermost loop (backward branch span) that contains `marker`:
-    the steady-state particle loop of the SIS kernels (the sampler's sqrt seed is only issued there)."""
+    the steady-state particle loop of the SIS kernels (the normal sampler is only issued there)."""
+    marker = marker or loop_marker(body)
     instr = []
     for line in body.splitlines():
         m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", line)
@@ -79,10 +87,24 @@ def loop_budget(path, needle):
             base = m.group(2).split(".")[0]
             if m.group(2).startswith("MUFU.RSQ64H"):
                 c["box_muller"] += 1            # one per stream pair = 2 particles
+            if m.group(2).startswith("CALL.REL.NOINC"):
+                c["slow_calls"] += 1            # ziggurat: one slow-path call site per draw = per particle of the README model
             if classify(m.group(2)) == "fp64":
                 c["fp64"] += 1
             if base in ("DFMA", "DADD", "DMUL", "DSETP"):
                 c[base.lower()] += 1
+    # instructions that only run on the slow path of a draw (argument set-up between the fast-accept branch and
+    # the call): static, but executed by 0.43 % of the draws
+    lines = [l for l in body.splitlines() if (mm := re.match(r"\s*/\*([0-9a-f]{4,})\*/", l)) and lo <= int(mm.group(1), 16) <= hi]
+    cold = 0
+    for i, l in enumerate(lines):
+        if "CALL.REL.NOINC" in l:
+            j = i
+            while j > 0 and "BRA" not in lines[j - 1]:
+                j -= 1
+            cold += i - j + 2                   # set-up, the call and the jump over the fast tail
+    c["cold"] = cold
+    c["particles_per_trip"] = c["slow_calls"] if c["slow_calls"] else 2 * c["box_muller"]
     return dict(c)
 
 
