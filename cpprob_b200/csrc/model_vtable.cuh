@@ -52,9 +52,9 @@ struct model_launchers {
     }
     static cudaError_t fused(cudaStream_t s, int grid, int nr, const run_args * a)
     {
-        if (nr <= 1)      k_sis_fused<Model, 1><<<grid, kBlock, 0, s>>>(*a);
-        else if (nr == 2) k_sis_fused<Model, 2><<<grid, kBlock, 0, s>>>(*a);
-        else              k_sis_fused<Model, 4><<<grid, kBlock, 0, s>>>(*a);
+        if (nr <= 1)      k_sis_fused<Model, 1><<<grid, fused_block(1), 0, s>>>(*a);
+        else if (nr == 2) k_sis_fused<Model, 2><<<grid, fused_block(2), 0, s>>>(*a);
+        else              k_sis_fused<Model, 4><<<grid, fused_block(4), 0, s>>>(*a);
         return cudaGetLastError();
     }
     static cudaError_t rows(cudaStream_t s, int grid, const run_args * a)
@@ -73,9 +73,9 @@ struct model_launchers {
         int n = 0;
         cudaError_t err;
         switch (which) {
-        case 0: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_sis_fused<Model, 1>, kBlock, 0); break;
-        case 1: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_sis_fused<Model, 2>, kBlock, 0); break;
-        case 2: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_sis_fused<Model, 4>, kBlock, 0); break;
+        case 0: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_sis_fused<Model, 1>, fused_block(1), 0); break;
+        case 1: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_sis_fused<Model, 2>, fused_block(2), 0); break;
+        case 2: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_sis_fused<Model, 4>, fused_block(4), 0); break;
         default: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_sis_rows<Model>, kBlock, 0); break;
         }
         return err == cudaSuccess ? n : 0;

@@ -121,7 +121,7 @@ struct cpprob_sis_engine {
     cudaEvent_t ev_computed[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     cudaEvent_t ev_batch_begin[2] = {nullptr, nullptr};
 
-    device_buffer<double> d_obs, d_pilot, d_partials, d_merged, d_w[2], d_logw[2], d_real[2], d_gather;
+    device_buffer<double> d_obs, d_pilot, d_partials, d_warp_partials, d_merged, d_w[2], d_logw[2], d_real[2], d_gather;
     device_buffer<int> d_int[2];
     device_buffer<unsigned> d_counter;
     device_buffer<int_extra> d_int_extra;
@@ -367,15 +367,24 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         int occ = vt->occupancy(nr == 1 ? 0 : (nr == 2 ? 1 : 2));
         if (occ <= 0) occ = 1;
         if (e->blocks_per_sm > 0) occ = std::min(occ, e->blocks_per_sm);
-        const int grid = static_cast<int>(std::min<uint64_t>(plan.n_chunks_local, static_cast<uint64_t>(e->sm_count) * occ));
+        // warp-autonomous kernel: enough CTAs to give every (chunk, warp slot) unit a warp, at most the resident set
+        const uint64_t ctas_needed = (static_cast<uint64_t>(plan.n_chunks_local) * kSlotsPerChunk * 32 + fused_block(nr) - 1) / fused_block(nr);
+        const int grid = static_cast<int>(std::min<uint64_t>(ctas_needed, static_cast<uint64_t>(e->sm_count) * occ));
         a.first_particle = plan.first_particle;
         a.n_particles = plan.n_local;
         a.n_chunks = plan.n_chunks_local;
         a.partials = e->d_partials.ptr;
+        const int nv = kBaseCols + 2 * nr;
+        CU_TRY(e->d_warp_partials.reserve(static_cast<size_t>(plan.n_chunks_local) * kSlotsPerChunk * nv));
+        a.warp_partials = e->d_warp_partials.ptr;
         CU_TRY(cudaMemsetAsync(e->d_counter.ptr, 0, sizeof(unsigned), e->compute));
         CU_TRY(vt->launch_fused(e->compute, grid, nr, &a));
+        const unsigned long long fold_n = static_cast<unsigned long long>(plan.n_chunks_local) * nv;
+        k_fold_warp_partials<<<static_cast<unsigned>((fold_n + kBlock - 1) / kBlock), kBlock, 0, e->compute>>>(
+            e->d_warp_partials.ptr, plan.n_chunks_local, nv, e->d_partials.ptr, n_cols);
+        CU_TRY(cudaGetLastError());
         CU_TRY(cudaEventRecord(e->ev_end, e->compute));
-        ++res->launches;
+        res->launches += 2;
         CU_TRY(cudaStreamSynchronize(e->compute));
         float ms = 0.f;
         CU_TRY(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));
@@ -886,7 +895,7 @@ void cpprob_sis_destroy(cpprob_sis_engine * e)
     cudaSetDevice(e->device);
     if (e->compute) cudaStreamSynchronize(e->compute);
     if (e->copy) cudaStreamSynchronize(e->copy);
-    e->d_obs.release(); e->d_pilot.release(); e->d_partials.release(); e->d_merged.release(); e->d_gather.release();
+    e->d_obs.release(); e->d_pilot.release(); e->d_partials.release(); e->d_warp_partials.release(); e->d_merged.release(); e->d_gather.release();
     e->d_counter.release(); e->d_int_extra.release(); e->h_merged.release();
     e->d_text_len.release(); e->d_text_bsum.release(); e->d_text_meta.release(); e->d_text_flags.release(); e->h_text_flags.release();
     for (int i = 0; i < 2; ++i) {

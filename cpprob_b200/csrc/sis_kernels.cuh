@@ -28,12 +28,19 @@ namespace engine {
 #ifndef CPPROB_TILES_PER_TRIP
 #define CPPROB_TILES_PER_TRIP 2             // stream tiles (pairs of particles per thread) per loop trip
 #endif
+// The fused kernel's warps are autonomous, so its CTA size is only a register budget: one CTA of 768 threads per
+// SM = 24 warps at <= 80 registers and ONE copy of the 32 KB ziggurat table (measured best of 256x2, 256x3,
+// 512, 576, 640, 704, 768: profiles/r01_notes.md).  Kernels that stage more predicts keep 256 threads.
 #ifndef CPPROB_FUSED_MIN_BLOCKS
-#define CPPROB_FUSED_MIN_BLOCKS 2           // resident CTAs per SM the fused kernel is compiled for (<= 128 registers)
+#define CPPROB_FUSED_MIN_BLOCKS 1           // resident CTAs per SM the one-predict fused kernel is compiled for
+#endif
+#ifndef CPPROB_FUSED_THREADS
+#define CPPROB_FUSED_THREADS 768            // threads per CTA of the one-predict fused kernel (any multiple of 32)
 #endif
 
 constexpr int kBlock = 256;                 // threads per CTA
 constexpr int kWarps = kBlock / 32;
+constexpr int fused_block(int nr) { return nr == 1 ? CPPROB_FUSED_THREADS : kBlock; }
 constexpr unsigned kChunk = 1u << 15;       // particles per deterministic reduction unit (fused kernel, shard granularity)
 constexpr unsigned kSubChunk = 1u << 12;    // particles per partial row on the row (SoA) path; kChunk / kSubChunk rows per chunk
 constexpr int kBaseCols = 8;                // partial columns every run has (see col:: below)
@@ -63,6 +70,7 @@ struct run_args {
     const double * m_ref;                // device scalar
     unsigned * chunk_counter;            // device, zeroed before the launch
     double * partials;                   // [n_chunks][n_cols]
+    double * warp_partials;              // fused kernel: [n_chunks * 8][kBaseCols + 2 NR] scratch, folded into partials
     int n_cols;
     // SoA trace rows (row kernels only); column index = particle index within the launch
     double * real_rows;                  // [n_real][row_stride]
@@ -138,15 +146,16 @@ __device__ __forceinline__ unsigned fetch_chunk(unsigned * counter, unsigned * s
     return c;
 }
 
-// Runs body(rng, i) for the particles of [0, n_here) owned by this thread: in every tile of 512 the
-// thread owns local indices t and t + 256, which share one Philox stream (random/philox.hpp).
-// `global_base` is the global index of local particle 0 (a multiple of 512).
+// Runs body(rng, i) for the particles of [0, n_here) owned by virtual thread `vt` (0..255): in every tile of 512
+// the thread owns local indices vt and vt + 256, which share one Philox stream (random/philox.hpp).
+// `global_base` is the global index of local particle 0 (a multiple of 512).  vt is threadIdx.x where a CTA
+// works on the range together, and warp_slot * 32 + lane in the warp-autonomous fused kernel.
 template<class Body>
-__device__ __forceinline__ void for_each_owned_particle(const philox_keys & keys, unsigned zig_base, unsigned long long global_base,
-                                                        unsigned n_here, Body && body)
+__device__ __forceinline__ void for_each_owned_particle(const philox_keys & keys, unsigned zig_base, unsigned vt,
+                                                        unsigned long long global_base, unsigned n_here, Body && body)
 {
     constexpr unsigned kTile = 2 * kPairStride;
-    const unsigned long long stream0 = stream_of_particle(global_base) + threadIdx.x;
+    const unsigned long long stream0 = stream_of_particle(global_base) + vt;
     const unsigned full_tiles = n_here / kTile;
     unsigned tile = 0;
     // two whole tiles per trip: four independent particle bodies in one straight-line block, so that the
@@ -156,7 +165,7 @@ __device__ __forceinline__ void for_each_owned_particle(const philox_keys & keys
     for (; tile + 2 <= full_tiles; tile += 2) {
         philox_stream r0(keys, stream0 + static_cast<unsigned long long>(tile) * kPairStride, zig_base);
         philox_stream r1(keys, stream0 + static_cast<unsigned long long>(tile + 1) * kPairStride, zig_base);
-        const unsigned i0 = tile * kTile + threadIdx.x;
+        const unsigned i0 = tile * kTile + vt;
         body(r0, i0);
         body(r1, i0 + kTile);
         body(r0, i0 + kPairStride);
@@ -165,13 +174,13 @@ __device__ __forceinline__ void for_each_owned_particle(const philox_keys & keys
 #else
     for (; tile < full_tiles; ++tile) {
         philox_stream r0(keys, stream0 + static_cast<unsigned long long>(tile) * kPairStride, zig_base);
-        const unsigned i0 = tile * kTile + threadIdx.x;
+        const unsigned i0 = tile * kTile + vt;
         body(r0, i0);
         body(r0, i0 + kPairStride);
     }
 #endif
     for (; tile * kTile < n_here; ++tile) {
-        const unsigned ia = tile * kTile + threadIdx.x;
+        const unsigned ia = tile * kTile + vt;
         if (ia < n_here) {
             philox_stream rng(keys, stream0 + static_cast<unsigned long long>(tile) * kPairStride, zig_base);
             body(rng, ia);
@@ -341,7 +350,7 @@ __global__ void __launch_bounds__(kBlock) k_pilot(const __grid_constant__ philox
     double v[3] = {dm::neg_inf(), dm::neg_inf(), dm::neg_inf()};   // max lw, max(-imin), max(imax)
     const unsigned base = blockIdx.x * kTile;
     const unsigned n_here = static_cast<unsigned>(n_pilot) > base ? min(static_cast<unsigned>(n_pilot) - base, kTile) : 0u;
-    for_each_owned_particle(keys, zig_base, static_cast<unsigned long long>(base), n_here, [&](philox_stream & rng, unsigned) {
+    for_each_owned_particle(keys, zig_base, threadIdx.x, static_cast<unsigned long long>(base), n_here, [&](philox_stream & rng, unsigned) {
         null_policy pol;
         particle<null_policy> p(rng, pol);
         invoke_model(model, p, oc.data(), n_obs);
@@ -358,22 +367,35 @@ __global__ void __launch_bounds__(kBlock) k_pilot(const __grid_constant__ philox
 // ------------------------------------------------------------------------------------------------
 // K1 k_sis_fused: model body + weight + estimator sums, no trace written.  Used when the model has
 // no int predicts and at most NR real predicts per trace and no trace emission was asked for.
+//
+// Warp-autonomous: the work unit is (chunk c, warp slot w) = the particles that lanes [32w, 32w+32) of a
+// 256-thread CTA would own in chunk c (4096 particles).  Any warp of the grid takes any unit from the atomic
+// counter, sums it with a fixed shuffle tree and writes NV values to warp_partials[c*8 + w][*]; after the one
+// barrier of the table load no warp ever waits for another (the ziggurat's rare slow draws make warps finish
+// at different times).  k_fold_warp_partials then adds the 8 slots of a chunk in slot order, which is the sum
+// the CTA-wide tree used to form: chunk partials are bit-identical for any grid size / schedule / GPU count.
 // Partial columns: kBaseCols then (S1, S2) per real predict slot.
 // ------------------------------------------------------------------------------------------------
+constexpr int kSlotsPerChunk = kBlock / 32;          // warp slots of one chunk
+
 template<class Model, int NR>
-__global__ void __launch_bounds__(kBlock, NR == 1 ? CPPROB_FUSED_MIN_BLOCKS : 1) k_sis_fused(const __grid_constant__ run_args a)
+__global__ void __launch_bounds__(fused_block(NR), NR == 1 ? CPPROB_FUSED_MIN_BLOCKS : 1) k_sis_fused(const __grid_constant__ run_args a)
 {
     constexpr int NV = kBaseCols + 2 * NR;
-    __shared__ double smem[kWarps * NV];
-    __shared__ unsigned s_chunk;
     const Model model{};
     const double m_ref = *a.m_ref;
     const obs_cache<Model> oc(a.obs, a.n_obs);
     const unsigned zig_base = zig::load_shared();
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned n_units = a.n_chunks * kSlotsPerChunk;
 
     for (;;) {
-        const unsigned c = fetch_chunk(a.chunk_counter, &s_chunk);
-        if (c >= a.n_chunks) break;
+        unsigned unit = 0;
+        if (lane == 0) unit = atomicAdd(a.chunk_counter, 1u);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= n_units) break;
+        const unsigned c = unit / kSlotsPerChunk;
+        const unsigned vt = (unit % kSlotsPerChunk) * 32u + lane;
         const unsigned long long base = static_cast<unsigned long long>(c) * kChunk;
         const unsigned long long left = a.n_particles - base;
         const unsigned n_here = left < kChunk ? static_cast<unsigned>(left) : kChunk;
@@ -382,12 +404,12 @@ __global__ void __launch_bounds__(kBlock, NR == 1 ? CPPROB_FUSED_MIN_BLOCKS : 1)
         unsigned n_neginf, n_nan;
         double s1[NR], s2[NR];
         // Fast pass: weights by exp_weight_unchecked, no per-particle special-case handling; only the
-        // smallest exponent k and the largest exponent field of log_w are tracked (2-3 ALU instructions
-        // per particle).  If any particle of the chunk had a non-finite log_w or a weight below the
-        // normal range, the whole chunk is recomputed by the careful pass.  The choice depends only on
-        // the chunk's own data, so results stay deterministic.
+        // smallest exponent k is tracked (one ALU instruction per particle).  A non-finite log_w needs no
+        // tracking: -inf, +inf and NaN all come out of exp_weight_unchecked as NaN (inf - inf in its range
+        // reduction) and poison the unit's weight sum.  If any particle of the unit had a non-finite
+        // log_w or a weight below the normal range, the whole unit is recomputed by the careful pass.
+        // The choice depends only on the unit's own data, so results stay deterministic.
         int k_min = 0;
-        unsigned exp_max = 0;
         auto reset = [&] {
             max_lw = dm::neg_inf(); s0 = 0.0; s00 = 0.0; n_neginf = 0; n_nan = 0;
 #pragma unroll
@@ -405,7 +427,7 @@ __global__ void __launch_bounds__(kBlock, NR == 1 ? CPPROB_FUSED_MIN_BLOCKS : 1)
             }
         };
         reset();
-        for_each_owned_particle(a.keys, zig_base, a.first_particle + base, n_here, [&](philox_stream & rng, unsigned) {
+        for_each_owned_particle(a.keys, zig_base, vt, a.first_particle + base, n_here, [&](philox_stream & rng, unsigned) {
             reg_policy<NR> pol;
             particle<reg_policy<NR>> p(rng, pol);
             invoke_model(model, p, oc.data(), a.n_obs);
@@ -413,12 +435,11 @@ __global__ void __launch_bounds__(kBlock, NR == 1 ? CPPROB_FUSED_MIN_BLOCKS : 1)
             int k;
             const double w = dm::exp_weight_unchecked(lw - m_ref, k);
             k_min = min(k_min, k);
-            exp_max = max(exp_max, static_cast<unsigned>(__double2hiint(lw)) & 0x7FF00000u);
             accumulate(lw, w, pol);
         });
-        if (__syncthreads_or(k_min < -1021 || exp_max == 0x7FF00000u)) {
+        if (__any_sync(0xffffffffu, k_min < -1021 || is_nan(s0))) {
             reset();
-            for_each_owned_particle(a.keys, zig_base, a.first_particle + base, n_here, [&](philox_stream & rng, unsigned) {
+            for_each_owned_particle(a.keys, zig_base, vt, a.first_particle + base, n_here, [&](philox_stream & rng, unsigned) {
                 reg_policy<NR> pol;
                 particle<reg_policy<NR>> p(rng, pol);
                 invoke_model(model, p, oc.data(), a.n_obs);
@@ -441,11 +462,40 @@ __global__ void __launch_bounds__(kBlock, NR == 1 ? CPPROB_FUSED_MIN_BLOCKS : 1)
         v[col::n_nan] = static_cast<double>(n_nan);
 #pragma unroll
         for (int j = 0; j < NR; ++j) { v[kBaseCols + 2 * j] = s1[j]; v[kBaseCols + 2 * j + 1] = s2[j]; }
-        const double r = block_reduce<NV>(v, kMaxColsMask, smem);
-        if (threadIdx.x < NV && threadIdx.x < a.n_cols) {
-            a.partials[static_cast<size_t>(c) * a.n_cols + threadIdx.x] = r;
+        // the warp stage of block_reduce, same tree
+        double mine = 0.0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double x = v[i];
+            const bool is_max = (kMaxColsMask >> i) & 1ull;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double y = __shfl_xor_sync(0xffffffffu, x, off);
+                x = is_max ? fmax(x, y) : x + y;
+            }
+            if (static_cast<int>(lane) == i) mine = x;
         }
+        if (static_cast<int>(lane) < NV) a.warp_partials[static_cast<size_t>(unit) * NV + lane] = mine;
     }
+}
+
+// chunk partial = warp slots 0..7 combined in slot order (the second stage of block_reduce)
+static __global__ void __launch_bounds__(kBlock) k_fold_warp_partials(const double * __restrict__ warp_partials, unsigned n_chunks, int nv,
+                                                               double * __restrict__ partials, int n_cols)
+{
+    const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(kBlock) + threadIdx.x;
+    if (i >= static_cast<unsigned long long>(n_chunks) * nv) return;
+    const unsigned c = static_cast<unsigned>(i / nv);
+    const int j = static_cast<int>(i % nv);
+    const bool is_max = (kMaxColsMask >> j) & 1ull;
+    const double * p = warp_partials + static_cast<size_t>(c) * kSlotsPerChunk * nv + j;
+    double r = p[0];
+#pragma unroll
+    for (int w = 1; w < kSlotsPerChunk; ++w) {
+        const double y = p[static_cast<size_t>(w) * nv];
+        r = is_max ? fmax(r, y) : r + y;
+    }
+    if (j < n_cols) partials[static_cast<size_t>(c) * n_cols + j] = r;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -25,8 +25,8 @@
 //   * next_u32()      takes one 32-bit word from the current block (4 per block);
 //   * next_uniform()  takes an aligned pair of words (52 random mantissa bits, result in (0,1));
 //   * next_std_normal() takes an aligned pair of words (a, b) and runs one ziggurat trial on them
-//     (1024 layers, tools/gen_ziggurat.py): layer = a & 1023, sign = bit 10 of a, u = (b : a >> 12)
-//     * 2^-52.  99.57 % of the draws end there.  The others (wedges, the tail, rejected trials) take
+//     (4096 layers, tools/gen_ziggurat.py): layer = bits 3..14 of a, sign = bit 0 of a, u = (b : a >> 12)
+//     * 2^-52.  99.88 % of the draws end there.  The others (wedges, the tail, rejected trials) take
 //     all further randomness from a SIDE stream — same stream id, counter word 3 = tag | 0x80000000,
 //     counter word 2 = (block index << 2 | word position) of the pair, key rotated by the trial
 //     number — so the main stream's position never depends on how a draw went.
@@ -126,16 +126,18 @@ CPPROB_HD double u52_to_open01(std::uint32_t hi_word, std::uint32_t lo_word)
 // shared-memory copy (zig::load_shared() at kernel start, returns the table's shared-space address, which
 // the streams keep in a register); X and F in global memory are only touched by the slow path.
 //
-// One trial on the word pair (a, b):   layer i = bits 3..12 of a (so that `a & 0x1ff8` IS the byte offset of
-// X[i]), sign = bit 0 of a, u = 0.m with the 52-bit mantissa m = b : (a >> 12) — 51 independent bits; the
-// last one is also the top layer bit, a dither of 2^-52 that saves an instruction — x = u X[i] rounded once,
-// as fma(1 + u, X[i], -X[i]).  Fast accept: the high word of x is below the high word of X[i+1].
+// One trial on the word pair (a, b):   layer i = bits 3..14 of a (so that `a & 0x7ff8` IS the byte offset of
+// X[i]), sign = bit 0 of a, u = 0.m with the 52-bit mantissa m = b : (a >> 12) — 49 independent bits; the last
+// three are also the top layer bits, i.e. a per-layer offset below 2^-49 that saves an instruction per draw —
+// x = u X[i] rounded once, as fma(1 + u, X[i], -X[i]).  Fast accept: the high word of x is below the high word
+// of X[i+1].  4096 layers make the fast path settle 99.88 % of the draws: what is left is warp-divergent work
+// (a full warp waits for its one slow lane), so the table is sized to make it rare rather than cheap.
 // ------------------------------------------------------------------------------------------------
 namespace zig {
 #include "cpprob/random/ziggurat_table.inc"
 constexpr int N = CPPROB_ZIG_N;
 constexpr double R = CPPROB_ZIG_R;
-static_assert(N == 1024, "the bit layout of a trial (layer = bits 3..12 of the first word) is written for 1024 layers");
+static_assert(N == 4096, "the bit layout of a trial (layer = bits 3..14 of the first word) is written for 4096 layers");
 
 #if defined(__CUDACC__)
 static __device__ const double d_x[N + 1] = {CPPROB_ZIG_X_ROWS};
@@ -214,20 +216,33 @@ CPPROB_HD double with_sign(double x, std::uint32_t a)
 #endif
 }
 
-// The 0.43 % of draws the fast test does not settle.  Pure function of its arguments (the main stream is
-// not advanced); not inlined, so the particle loops carry only a call.
+// exp(-x^2/2) for the wedge test, 0 <= x < 4.6: the engine's own branch-free exp on the device (2 ulp)
+CPPROB_HD double gauss_kernel(double x)
+{
+#if CPPROB_ON_DEVICE
+    int k;
+    return dm::exp_weight_unchecked(-0.5 * x * x, k);
+#else
+    return std::exp(-0.5 * x * x);
+#endif
+}
+
+// The 0.12 % of draws the fast test does not settle.  Pure function of its arguments (the main stream is
+// not advanced); not inlined, so the particle loops carry only a call.  Everything comes in by value — the key
+// as its two seed words, from which the round keys are re-derived with integer adds — so that the call touches
+// no memory but the two table reads of a wedge.
 #if defined(__CUDACC__)
 __host__ __device__ __noinline__
 #endif
-inline double slow_path(const philox_keys & keys, std::uint32_t s_lo, std::uint32_t s_hi, std::uint32_t where, std::uint32_t tag,
-                        std::uint32_t a, std::uint32_t b)
+inline double slow_path(std::uint32_t k0, std::uint32_t k1, std::uint32_t s_lo, std::uint32_t s_hi, std::uint32_t where,
+                        std::uint32_t tag, std::uint32_t a, std::uint32_t b, double x, double x_next)
 {
+    const philox_keys keys(k0, k1);
     std::uint32_t side = 0;                                   // blocks taken from the side stream so far
     std::uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
     for (;;) {
         const unsigned i = layer_of(a);
-        const double x = trial_abs(a, b, x_of(i));
-        if (x < x_of(i + 1)) return with_sign(x, a);          // inside the next layer's rectangle after all
+        if (x < x_next) return with_sign(x, a);               // inside the next layer's rectangle after all
         philox4x32::block(s_lo, s_hi, where, (tag | 0x80000000u) + (side++ << 8), keys, q0, q1, q2, q3);
         if (i == 0) {
             // beyond r in the base strip: the tail, by Marsaglia's exponential rejection
@@ -242,10 +257,13 @@ inline double slow_path(const philox_keys & keys, std::uint32_t s_lo, std::uint3
         // wedge of layer i: y uniform between f(X[i]) and f(X[i+1])
         const double f0 = f_of(i), f1 = f_of(i + 1);
         const double y = fma(detail::u52_to_open01(q0, q1), f1 - f0, f0);
-        if (y < dm::exp(-0.5 * x * x)) return with_sign(x, a);
+        if (y < gauss_kernel(x)) return with_sign(x, a);
         // rejected: a fresh trial from the rest of the side block
         a = q2;
         b = q3;
+        const unsigned j = layer_of(a);
+        x = trial_abs(a, b, x_of(j));
+        x_next = x_of(j + 1);
     }
 }
 }  // namespace zig
@@ -308,14 +326,14 @@ public:
         pos_ += 2;
 #if CPPROB_ON_DEVICE
         double xi, xn;
-        const unsigned addr = zig_base_ + (a & 0x1ff8u);
+        const unsigned addr = zig_base_ + (a & 0x7ff8u);
         asm("ld.shared.f64 %0, [%1];" : "=d"(xi) : "r"(addr));
         asm("ld.shared.f64 %0, [%1+8];" : "=d"(xn) : "r"(addr));
 #else
         const double xi = zig::x_of(zig::layer_of(a)), xn = zig::x_of(zig::layer_of(a) + 1);
 #endif
         const double x = zig::trial_abs(a, b, xi);
-        if (CPPROB_UNLIKELY(zig::high_word(x) >= zig::high_word(xn))) return zig::slow_path(keys_, s_lo_, s_hi_, where, tag_, a, b);
+        if (CPPROB_UNLIKELY(zig::high_word(x) >= zig::high_word(xn))) return zig::slow_path(keys_.k[0], keys_.k[1], s_lo_, s_hi_, where, tag_, a, b, x, xn);
         return zig::with_sign(x, a);
     }
 #endif
