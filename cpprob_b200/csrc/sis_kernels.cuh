@@ -190,6 +190,21 @@ __device__ __forceinline__ void for_each_owned_particle(const philox_keys & keys
     }
 }
 
+// A model that never draws a normal (directly or through gamma / beta) may say so with
+// `static constexpr bool draws_normals = false;`: its kernels then skip the 32 KB shared-memory ziggurat table,
+// which would otherwise cap their resident CTAs.  Absent = true (always safe).
+template<class Model, class = void>
+struct model_draws_normals : std::true_type {};
+template<class Model>
+struct model_draws_normals<Model, decltype(void(Model::draws_normals))> : std::integral_constant<bool, Model::draws_normals> {};
+
+template<class Model>
+__device__ __forceinline__ unsigned zig_prepare()
+{
+    if (model_draws_normals<Model>::value) return zig::load_shared();
+    return 0u;
+}
+
 // Observations of scalar-argument models are read once into registers; array models read theirs
 // through the read-only path as they go (the same address in every lane: one L1 hit per warp).
 template<class Model, bool Scalars = (Model::n_scalar_obs >= 0)>
@@ -346,7 +361,7 @@ __global__ void __launch_bounds__(kBlock) k_pilot(const __grid_constant__ philox
     __shared__ double smem[kWarps * 3];
     const Model model{};
     const obs_cache<Model> oc(obs, n_obs);
-    const unsigned zig_base = zig::load_shared();
+    const unsigned zig_base = zig_prepare<Model>();
     double v[3] = {dm::neg_inf(), dm::neg_inf(), dm::neg_inf()};   // max lw, max(-imin), max(imax)
     const unsigned base = blockIdx.x * kTile;
     const unsigned n_here = static_cast<unsigned>(n_pilot) > base ? min(static_cast<unsigned>(n_pilot) - base, kTile) : 0u;
@@ -385,7 +400,7 @@ __global__ void __launch_bounds__(fused_block(NR), NR == 1 ? CPPROB_FUSED_MIN_BL
     const Model model{};
     const double m_ref = *a.m_ref;
     const obs_cache<Model> oc(a.obs, a.n_obs);
-    const unsigned zig_base = zig::load_shared();
+    const unsigned zig_base = zig_prepare<Model>();
     const unsigned lane = threadIdx.x & 31u;
     const unsigned n_units = a.n_chunks * kSlotsPerChunk;
 
@@ -517,7 +532,7 @@ __global__ void __launch_bounds__(kBlock) k_sis_rows(const __grid_constant__ run
     const obs_cache<Model> oc(a.obs, a.n_obs);
     const unsigned n_tiles = static_cast<unsigned>((a.n_particles + kTile - 1) / kTile);
     const unsigned long long stream0 = stream_of_particle(a.first_particle) + threadIdx.x;
-    const unsigned zig_base = zig::load_shared();
+    const unsigned zig_base = zig_prepare<Model>();
 
     for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const unsigned long long base = static_cast<unsigned long long>(tile) * kTile;

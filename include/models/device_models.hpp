@@ -102,6 +102,7 @@ struct linear_gaussian_1d_model {
 struct hmm_model {
     static constexpr int n_scalar_obs = -1;
     static constexpr bool replayable = true;
+    static constexpr bool draws_normals = false;   // uniform_smallint + discrete only: no ziggurat table needed
     static constexpr const char * name() { return "hmm"; }
 
     template<class P>
