@@ -111,7 +111,7 @@ struct philox_op {
 };
 
 struct dmath_op {
-    __device__ unsigned prepare() const { return 0; }
+    __device__ unsigned prepare() const { return fn == 9 ? dm::exp2_table_load() : 0u; }   // the slot carries the exp table base here
     int fn;
     const double * x;
     double * out;
@@ -127,6 +127,7 @@ struct dmath_op {
         case 6: r = dm::log(x[i]); break;
         case 7: r = dm::cos_2pi(x[i]); break;
         case 8: r = dm::sin_2pi(x[i]); break;
+        case 9: { int n; r = dm::exp_weight_tab(x[i], zig_base, n); } break;
         case 5: {
             const double rad = dm::sqrt_pos(-2.0 * dm::log_unit(x[2 * i]));
             dm::sincos_2pi(x[2 * i + 1], s, c);

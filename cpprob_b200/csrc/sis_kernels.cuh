@@ -29,13 +29,13 @@ namespace engine {
 #define CPPROB_TILES_PER_TRIP 2             // stream tiles (pairs of particles per thread) per loop trip
 #endif
 // The fused kernel's warps are autonomous, so its CTA size is only a register budget: one CTA of 768 threads per
-// SM = 24 warps at <= 80 registers and ONE copy of the 32 KB ziggurat table (measured best of 256x2, 256x3,
-// 512, 576, 640, 704, 768: profiles/r01_notes.md).  Kernels that stage more predicts keep 256 threads.
+// SM = 32 warps at 64 registers and ONE copy of the 32 KB ziggurat table (measured best of 256x2, 256x3,
+// 512 ... 1024: profiles/r01_notes.md).  Kernels that stage more predicts keep 256 threads.
 #ifndef CPPROB_FUSED_MIN_BLOCKS
 #define CPPROB_FUSED_MIN_BLOCKS 1           // resident CTAs per SM the one-predict fused kernel is compiled for
 #endif
 #ifndef CPPROB_FUSED_THREADS
-#define CPPROB_FUSED_THREADS 768            // threads per CTA of the one-predict fused kernel (any multiple of 32)
+#define CPPROB_FUSED_THREADS 1024           // threads per CTA of the one-predict fused kernel (any multiple of 32)
 #endif
 
 constexpr int kBlock = 256;                 // threads per CTA
@@ -243,9 +243,11 @@ struct null_policy {
     template<class S> __device__ __forceinline__ void begin_vector(int, const S &) {}
 };
 
-// Fused kernel: up to NR real predicts staged in registers.
-template<int NR>
+// Fused kernel: up to NR real predicts staged in registers.  Lenient = the fast pass, whose units are recomputed
+// with exact special-case semantics whenever a non-finite log-weight appears (see logpdf<normal>::finite_case).
+template<int NR, bool Lenient = false>
 struct reg_policy {
+    static constexpr bool lenient_logpdf = Lenient;
     double v[NR];
     int k;
     __device__ __forceinline__ reg_policy() : k(0)
@@ -401,6 +403,7 @@ __global__ void __launch_bounds__(fused_block(NR), NR == 1 ? CPPROB_FUSED_MIN_BL
     const double m_ref = *a.m_ref;
     const obs_cache<Model> oc(a.obs, a.n_obs);
     const unsigned zig_base = zig_prepare<Model>();
+    const unsigned exp_tab = dm::exp2_table_load();
     const unsigned lane = threadIdx.x & 31u;
     const unsigned n_units = a.n_chunks * kSlotsPerChunk;
 
@@ -418,9 +421,9 @@ __global__ void __launch_bounds__(fused_block(NR), NR == 1 ? CPPROB_FUSED_MIN_BL
         double max_lw, s0, s00;
         unsigned n_neginf, n_nan;
         double s1[NR], s2[NR];
-        // Fast pass: weights by exp_weight_unchecked, no per-particle special-case handling; only the
-        // smallest exponent k is tracked (one ALU instruction per particle).  A non-finite log_w needs no
-        // tracking: -inf, +inf and NaN all come out of exp_weight_unchecked as NaN (inf - inf in its range
+        // Fast pass: weights by exp_weight_tab, no per-particle special-case handling; only the
+        // smallest scaled exponent n = 256 k + j is tracked (one ALU instruction per particle).  A non-finite log_w needs no
+        // tracking: -inf, +inf and NaN all come out of exp_weight_tab as NaN (inf - inf in its range
         // reduction) and poison the unit's weight sum.  If any particle of the unit had a non-finite
         // log_w or a weight below the normal range, the whole unit is recomputed by the careful pass.
         // The choice depends only on the unit's own data, so results stay deterministic.
@@ -430,29 +433,29 @@ __global__ void __launch_bounds__(fused_block(NR), NR == 1 ? CPPROB_FUSED_MIN_BL
 #pragma unroll
             for (int j = 0; j < NR; ++j) { s1[j] = 0.0; s2[j] = 0.0; }
         };
-        auto accumulate = [&](double lw, double w, const reg_policy<NR> & pol) {
+        auto accumulate = [&](double lw, double w, const double (&pv)[NR]) {
             max_lw = lw > max_lw ? lw : max_lw;
             s0 += w;
             s00 = fma(w, w, s00);
 #pragma unroll
             for (int j = 0; j < NR; ++j) {
-                const double wx = w * pol.v[j];
+                const double wx = w * pv[j];
                 s1[j] += wx;
-                s2[j] = fma(wx, pol.v[j], s2[j]);
+                s2[j] = fma(wx, pv[j], s2[j]);
             }
         };
         reset();
         for_each_owned_particle(a.keys, zig_base, vt, a.first_particle + base, n_here, [&](philox_stream & rng, unsigned) {
-            reg_policy<NR> pol;
-            particle<reg_policy<NR>> p(rng, pol);
+            reg_policy<NR, true> pol;
+            particle<reg_policy<NR, true>> p(rng, pol);
             invoke_model(model, p, oc.data(), a.n_obs);
             const double lw = p.log_w();
-            int k;
-            const double w = dm::exp_weight_unchecked(lw - m_ref, k);
-            k_min = min(k_min, k);
-            accumulate(lw, w, pol);
+            int n;
+            const double w = dm::exp_weight_tab(lw - m_ref, exp_tab, n);
+            k_min = min(k_min, n);
+            accumulate(lw, w, pol.v);
         });
-        if (__any_sync(0xffffffffu, k_min < -1021 || is_nan(s0))) {
+        if (__any_sync(0xffffffffu, k_min < -1021 * 256 || is_nan(s0))) {
             reset();
             for_each_owned_particle(a.keys, zig_base, vt, a.first_particle + base, n_here, [&](philox_stream & rng, unsigned) {
                 reg_policy<NR> pol;
@@ -462,7 +465,7 @@ __global__ void __launch_bounds__(fused_block(NR), NR == 1 ? CPPROB_FUSED_MIN_BL
                 const double w = dm::exp_weight(lw - m_ref);
                 n_neginf += is_neg_inf(lw) ? 1u : 0u;
                 n_nan += is_nan(lw) ? 1u : 0u;
-                accumulate(lw, w, pol);
+                accumulate(lw, w, pol.v);
             });
         }
 

@@ -72,7 +72,17 @@ struct logpdf<normal_distribution<RealType>> {
         if (CPPROB_UNLIKELY(dm::fabs(x) == std::numeric_limits<RealType>::infinity())) {
             return -std::numeric_limits<RealType>::infinity();
         }
-        RealType result = (x - mean) / std;
+        return finite_case(distr, x);
+    }
+    // The arithmetic of the regular case alone.  Where the exact log-pdf is finite this IS the exact value (same
+    // operations, up to FMA contraction); in every special case above it comes out non-finite (x or mean infinite: inf or inf - inf;
+    // sigma == 0: x/0 squared plus log 0 = inf - inf), never a wrong finite number.  The fused kernel's fast pass
+    // uses it (particle.hpp, `lenient_logpdf`) and recomputes the unit with operator() as soon as a non-finite
+    // log-weight shows up, so results are unchanged while the two selects per observe leave the hot loop.
+    CPPROB_HD RealType finite_case(const normal_distribution<RealType> & distr, const RealType & x) const
+    {
+        const RealType std = distr.sigma();
+        RealType result = (x - distr.mean()) / std;
         result *= result;
         result += dm::log(2 * dm::pi * std * std);
         result *= -0.5;

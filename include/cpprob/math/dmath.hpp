@@ -58,6 +58,14 @@ static __constant__ double k_ln2_lo = 1.90821492927058770002e-10;
 static __constant__ double k_log2e = 1.4426950408889634074;
 static __constant__ double k_round_magic = 6755399441055744.0;      // 2^52 + 2^51: x + magic rounds x to an integer
 static __constant__ double k_pi = 3.141592653589793238462643383279502884;
+// exp_weight_tab: 2^(j/256) (tools/gen_exp2_table.py), copied to shared memory by exp2_table_load()
+#include "cpprob/math/exp2_table.inc"
+static __device__ const double exp2_tab[256] = {CPPROB_EXP2_TABLE_ROWS};
+static __constant__ double k_log2e_256 = 1.4426950408889634074 * 256.0;
+static __constant__ double k_ln2_hi_256 = 6.93147180369123816490e-01 / 256.0;   // exact scalings of k_ln2_hi / k_ln2_lo
+static __constant__ double k_ln2_lo_256 = 1.90821492927058770002e-10 / 256.0;
+static __constant__ double k_exp_c1 = 1.0 / 6.0;
+static __constant__ double k_exp_c2 = 1.0 / 24.0;
 }  // namespace tbl
 #endif
 
@@ -287,6 +295,41 @@ inline double pow(double a, double b) { return std::pow(a, b); }
 inline double floor(double x) { return std::floor(x); }
 inline double fabs(double x) { return std::fabs(x); }
 #endif
+
+#if defined(__CUDACC__)
+// Table-assisted variant of exp_weight_unchecked for the fused kernel: exp(x) = 2^k 2^(j/256) e^r with
+// n = rint(256 x / ln 2) = 256 k + j and |r| <= ln2/512, so e^r - 1 = r + r^2 (1/2 + r/6 + r^2/24) to 2^-54.5:
+// 9 FP64-pipe instructions instead of 16, plus one shared-memory load (the FP64 pipe's two issue cycles per
+// instruction make that a good trade).  `tab` is what exp2_table_load() returned.
+// Same contract as exp_weight_unchecked: x finite and the result normal; the caller tracks the smallest n
+// (n >= -1021 * 256) and recomputes with exp_weight otherwise.  Non-finite x gives NaN.
+__device__ __forceinline__ unsigned exp2_table_load()
+{
+    __shared__ double t[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) t[i] = tbl::exp2_tab[i];
+    __syncthreads();
+    unsigned base;
+    asm volatile("{ .reg .u64 p; cvta.to.shared.u64 p, %1; cvt.u32.u64 %0, p; }" : "=r"(base) : "l"(t));
+    return base;
+}
+__device__ __forceinline__ double exp_weight_tab(double x, unsigned tab, int & n_out)
+{
+    const double magic = tbl::k_round_magic;
+    const double t = fma(x, tbl::k_log2e_256, magic);
+    const int n = __double2loint(t);
+    const double kf = t - magic;
+    double r = fma(kf, -tbl::k_ln2_hi_256, x);
+    r = fma(kf, -tbl::k_ln2_lo_256, r);
+    double tj;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab + ((static_cast<unsigned>(n) << 3) & 0x7f8u)));
+    double q = fma(tbl::k_exp_c2, r, tbl::k_exp_c1);
+    q = fma(q, r, 0.5);
+    const double p = fma(r * r, q, r);
+    const double e = fma(tj, p, tj);                                  // in [1, 2)
+    n_out = n;
+    return __hiloint2double(__double2hiint(e) + ((n >> 8) << 20), __double2loint(e));
+}
+#endif  // __CUDACC__
 
 }  // namespace dm
 }  // namespace cpprob

@@ -76,6 +76,25 @@ template<class D, class Value>
 struct observed<D, Value, false> { using type = Value; };
 }  // namespace detail
 
+namespace detail {
+// Policy::lenient_logpdf (absent = false): observe may use logpdf<D>::finite_case where the specialisation has one
+template<class Policy, class = void>
+struct is_lenient : std::false_type {};
+template<class Policy>
+struct is_lenient<Policy, decltype(void(Policy::lenient_logpdf))> : std::integral_constant<bool, Policy::lenient_logpdf> {};
+
+template<class D, class X>
+CPPROB_HD auto eval_logpdf(std::true_type, const D & d, const X & x, int) -> decltype(logpdf<D>().finite_case(d, x))
+{
+    return logpdf<D>().finite_case(d, x);
+}
+template<class D, class X, class Lenient>
+CPPROB_HD auto eval_logpdf(Lenient, const D & d, const X & x, long) -> decltype(logpdf<D>()(d, x))
+{
+    return logpdf<D>()(d, x);
+}
+}  // namespace detail
+
 template<class Policy>
 class particle {
 public:
@@ -111,7 +130,8 @@ public:
     template<class Distribution, class Value>
     CPPROB_HD void observe(const Distribution & distr, const Value & x)
     {
-        const double lp = logpdf<Distribution>()(distr, static_cast<const typename detail::observed<Distribution, Value>::type &>(x));
+        const double lp = detail::eval_logpdf(std::integral_constant<bool, detail::is_lenient<Policy>::value>(), distr,
+                                              static_cast<const typename detail::observed<Distribution, Value>::type &>(x), 0);
         // log_w starts at 0.0 (trace.hpp:59); 0.0 + lp == lp, so the first observe stores instead of adding
         // (one FP64 instruction per particle; `observed_` is resolved at compile time in straight-line models)
         log_w_ = observed_ ? log_w_ + lp : lp;

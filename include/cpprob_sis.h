@@ -237,7 +237,7 @@ int cpprob_sis_sample(cpprob_sis_engine * e, int kind, const double * params, in
                       uint64_t seed, uint64_t first_particle, uint64_t n, double * out);
 /* raw Philox4x32-10 blocks: out[4*i..] = block(counter = ctr[4*i..], key = key[2*i..]) */
 int cpprob_sis_philox(cpprob_sis_engine * e, const uint32_t * ctr, const uint32_t * key, uint64_t n, uint32_t * out);
-/* fp64 elementary functions of include/cpprob/math/dmath.hpp: 0 log_unit 1 exp_weight 2 sin2pi 3 cos2pi (joint) 4 sqrt_pos 5 Box-Muller z0 from (u1,u2) packed as x[2i],x[2i+1] 6 log 7 cos_2pi 8 sin_2pi (single chain) */
+/* fp64 elementary functions of include/cpprob/math/dmath.hpp: 0 log_unit 1 exp_weight 2 sin2pi 3 cos2pi (joint) 4 sqrt_pos 5 Box-Muller z0 from (u1,u2) packed as x[2i],x[2i+1] 6 log 7 cos_2pi 8 sin_2pi (single chain) 9 exp_weight_tab (table-assisted exp of the fused kernel; finite x, normal result) */
 int cpprob_sis_dmath(cpprob_sis_engine * e, int fn, const double * x, uint64_t n, double * out);
 
 /* ---- roofline denominators ----------------------------------------------------------------------*/

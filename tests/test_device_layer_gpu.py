@@ -60,6 +60,20 @@ def test_exp_weight(engine):
     assert abs(special[4] / math.exp(-708.0) - 1) < 1e-15
 
 
+def test_exp_weight_tab(engine):
+    """The fused kernel's table-assisted exp (2^(j/256) table + degree-4 tail, 9 FP64 instructions): <= 2 ulp wherever
+    its contract holds (finite argument, normal result); NaN for non-finite arguments (which is what poisons a unit's
+    weight sum and sends it to the careful pass)."""
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(-707.0, 707.0, 200_000), rng.uniform(-40, 5, 200_000), rng.uniform(-1e-3, 1e-3, 1000),
+                        [0.0, -0.0, 1e-300, -1e-17, math.log(2) / 512, -math.log(2) / 512, math.log(2) / 256]])
+    got = engine.dmath(9, x)
+    exact = np.array([float(mpmath.exp(mpmath.mpf(v))) for v in x[-25_000:]])
+    assert ulp_err(got[-25_000:], exact).max() <= 2.0
+    assert ulp_err(got, np.exp(x)).max() <= 3.0
+    assert np.isnan(engine.dmath(9, [-math.inf, math.inf, math.nan])).all()
+
+
 def test_sincos_2pi(engine):
     rng = np.random.default_rng(4)
     u = np.concatenate([rng.random(200_000), [0.0, 0.125, 0.25, 0.375, 0.5, 0.625, 0.75, 0.875, 1.0, 2 ** -53, 1 - 2 ** -53]])

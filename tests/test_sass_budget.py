@@ -19,14 +19,14 @@ def test_particle_loop_budget():
         assert saved[k] == b[k], k
     per = saved["particles_per_trip"]
     assert per == b["particles_per_trip"] and per in (2, 4)
-    # per particle: <= 36 FP64-pipe instructions and <= 84 hot instructions in all (the ziggurat draw is one DFMA;
-    # `cold` = call set-up that only the 0.12 % slow draws execute)
+    # per particle: <= 27 FP64-pipe instructions and <= 74 hot instructions in all (the ziggurat draw is one DFMA, the
+    # weight's exp nine; `cold` = call set-up that only the 0.12 % slow draws execute)
     hot = b["total"] - b["cold"]
-    assert b["fp64"] / per <= 36 and hot / per <= 84
+    assert b["fp64"] / per <= 27 and hot / per <= 74
     # every FP64 instruction holds the issue port for two cycles ("issue model"): issue slots per
     # particle = 2F + O
     slots = (2 * b["fp64"] + (hot - b["fp64"])) / per
-    assert slots <= 120
+    assert slots <= 100
 
 
 def test_no_local_memory_in_the_particle_loop():

@@ -38,6 +38,7 @@ def classify(op):
     return "alu"
 
 
+BRANCH = re.compile(r"\bBRA(?:\.\w+)*\s+(?:!?\w+,\s*)*0x([0-9a-f]+)")   # BRA 0x..., @P0 BRA P3, 0x..., BRA.U !UP0, 0x...
 MARKERS = ("CALL.REL.NOINC", "MUFU.RSQ64H")   # one per normal draw: the ziggurat's slow-path call / Box-Muller's sqrt seed
 
 
@@ -57,7 +58,7 @@ def particle_loop(body, marker=None):
     marks = [a for a, t in instr if marker in t]
     best, best_key = None, None
     for a, t in instr:
-        m = re.search(r"\bBRA\s+(?:\w+,\s*)?0x([0-9a-f]+)", t)
+        m = BRANCH.search(t)
         if not m:
             continue
         tgt = int(m.group(1), 16)
@@ -65,7 +66,7 @@ def particle_loop(body, marker=None):
         if tgt < a and n_marks:
             # the hot loop is the one with the most sampler invocations per trip that is still innermost:
             # reject spans that contain another backward branch (outer loops)
-            inner_back = any(tgt < a2 < a and (mm := re.search(r"\bBRA\s+(?:\w+,\s*)?0x([0-9a-f]+)", t2)) and int(mm.group(1), 16) < a2
+            inner_back = any(tgt < a2 < a and (mm := BRANCH.search(t2)) and int(mm.group(1), 16) < a2
                              and int(mm.group(1), 16) >= tgt for a2, t2 in instr)
             if inner_back:
                 continue
