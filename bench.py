@@ -144,7 +144,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -295,7 +295,7 @@ def run_ours(args):
                 "dfma_peak_sm_mhz_equiv": est_mhz,
             }
             line["cpu_baseline"] = cpu_baseline(args)
-        print(json.dumps(line), flush=True)
+        emit(line)
     engine.close()
     if world > 1:
         dist.destroy_process_group()
@@ -312,7 +312,26 @@ def cpu_baseline(args):
             "fast_flavour_value": n / s_fast}
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner under
+    # NCCL_DEBUG=VERSION, for one) is sent to stderr instead
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

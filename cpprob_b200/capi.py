@@ -26,7 +26,7 @@ SYMBOLS = [
     "cpprob_sis_merge", "cpprob_sis_replay", "cpprob_sis_reduce_records", "cpprob_sis_logpdf",
     "cpprob_sis_sample", "cpprob_sis_philox", "cpprob_sis_dmath", "cpprob_sis_measure_dfma_peak",
     "cpprob_sis_measure_store_peak", "cpprob_sis_plan_shard", "cpprob_sis_probe_issue", "cpprob_sis_probe_dfma_chains", "cpprob_sis_run_multi", "cpprob_sis_write_summary",
-    "cpprob_sis_text_stage_stats",
+    "cpprob_sis_text_stage_stats", "cpprob_sis_plan_rows",
 ]
 
 
@@ -116,10 +116,18 @@ def lib():
         L.cpprob_sis_text_stage_stats.argtypes = [C.c_void_p, dp, dp, dp, C.POINTER(u64), C.POINTER(u64)]
         L.cpprob_sis_probe_issue.argtypes = [C.c_void_p, C.c_int, dp]
         L.cpprob_sis_probe_dfma_chains.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, dp]
+        L.cpprob_sis_plan_rows.argtypes = [u64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.cpprob_sis_plan_shard.argtypes = [u64, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                             C.POINTER(u64), C.POINTER(u64)]
         _lib = L
         return L
+
+
+def plan_rows(n_total, rank, world, rows_per_chunk=1):
+    """(row_first, n_rows_local, n_rows_total): the partial rows `rank` hands to the gather — host arithmetic only."""
+    rf, nl, nt = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    _check(lib().cpprob_sis_plan_rows(int(n_total), rank, world, int(rows_per_chunk), C.byref(rf), C.byref(nl), C.byref(nt)))
+    return rf.value, nl.value, nt.value
 
 
 def plan_shard(n_total, rank, world):

@@ -138,6 +138,28 @@ __global__ void __launch_bounds__(kBlock) k_row_hist(const int * __restrict__ in
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_fold_rows: super-chunk rows.  out[s][c] = rows [s*per, min((s+1)*per, n_rows)) of `in` combined in row
+// order by one thread (max columns with fmax, the others with +).  What a rank hands to the gather.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_fold_rows(const double * __restrict__ in, unsigned n_rows, unsigned per, int n_cols,
+                                                      unsigned long long max_mask, double * __restrict__ out, unsigned n_out_rows)
+{
+    const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(kBlock) + threadIdx.x;
+    if (i >= static_cast<unsigned long long>(n_out_rows) * n_cols) return;
+    const unsigned s = static_cast<unsigned>(i / n_cols);
+    const int c = static_cast<int>(i % n_cols);
+    const bool is_max = c < 64 && ((max_mask >> c) & 1ull);
+    const unsigned long long r0 = static_cast<unsigned long long>(s) * per;
+    const unsigned long long r1 = r0 + per < n_rows ? r0 + per : n_rows;
+    double v = is_max ? dm::neg_inf() : 0.0;
+    for (unsigned long long r = r0; r < r1; ++r) {
+        const double x = in[r * n_cols + c];
+        v = is_max ? fmax(v, x) : v + x;
+    }
+    out[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_merge_columns: out[col] = reduce over chunks (rows of `partials`) in a fixed order.
 // grid = n_cols CTAs.  Thread t folds rows t, t+256, ... sequentially, then the fixed CTA tree.
 // The input is the concatenation of every rank's partials in chunk order, so the result is

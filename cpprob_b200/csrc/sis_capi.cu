@@ -121,7 +121,7 @@ struct cpprob_sis_engine {
     cudaEvent_t ev_computed[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     cudaEvent_t ev_batch_begin[2] = {nullptr, nullptr};
 
-    device_buffer<double> d_obs, d_pilot, d_partials, d_warp_partials, d_merged, d_w[2], d_logw[2], d_real[2], d_gather;
+    device_buffer<double> d_obs, d_pilot, d_partials, d_super, d_warp_partials, d_merged, d_w[2], d_logw[2], d_real[2], d_gather;
     device_buffer<int> d_int[2];
     device_buffer<unsigned> d_counter;
     device_buffer<int_extra> d_int_extra;
@@ -189,14 +189,39 @@ int probe_structure(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, c
 struct shard_plan {
     uint32_t n_chunks_total = 0, chunk_first = 0, n_chunks_local = 0;
     uint64_t first_particle = 0, n_local = 0;
+    // the rows a shard hands to the gather: partial sums of super-chunks = `super` consecutive chunks
+    uint32_t super = 1, n_super_total = 0, super_first = 0, n_super_local = 0;
 };
 
+// Upper bound of the partial rows of a whole run (what is gathered and merged).  Test hook:
+// CPPROB_SIS_MAX_PARTIAL_ROWS, read once per process.
+uint32_t max_partial_rows()
+{
+    static const uint32_t v = [] {
+        const char * s = std::getenv("CPPROB_SIS_MAX_PARTIAL_ROWS");
+        const unsigned long x = s ? std::strtoul(s, nullptr, 10) : 4096ul;
+        return static_cast<uint32_t>(std::max<unsigned long>(1ul, std::min<unsigned long>(x, 1ul << 20)));
+    }();
+    return v;
+}
+
+// The C chunks of a run are grouped into super-chunks of S = 2^k chunks, S the smallest that leaves at most
+// max_partial_rows() of them: S depends on the run's size only, never on the GPU count.  A rank owns whole
+// super-chunks and reduces each to ONE partial row (its chunk rows added in chunk order) before the gather, so the
+// exchange is <= 4096 rows whatever the particle count, and the merged sums are still bit-identical for any world
+// size.  Up to 4096 chunks (1.3e8 particles) S = 1 and a rank owns plain chunks.
 shard_plan plan_shard(uint64_t n_total, int rank, int world)
 {
     shard_plan p;
     p.n_chunks_total = static_cast<uint32_t>((n_total + kChunk - 1) / kChunk);
-    const uint64_t c0 = static_cast<uint64_t>(p.n_chunks_total) * static_cast<uint64_t>(rank) / static_cast<uint64_t>(world);
-    const uint64_t c1 = static_cast<uint64_t>(p.n_chunks_total) * static_cast<uint64_t>(rank + 1) / static_cast<uint64_t>(world);
+    while ((p.n_chunks_total + p.super - 1) / p.super > max_partial_rows()) p.super <<= 1;
+    p.n_super_total = (p.n_chunks_total + p.super - 1) / p.super;
+    const uint64_t s0 = static_cast<uint64_t>(p.n_super_total) * static_cast<uint64_t>(rank) / static_cast<uint64_t>(world);
+    const uint64_t s1 = static_cast<uint64_t>(p.n_super_total) * static_cast<uint64_t>(rank + 1) / static_cast<uint64_t>(world);
+    p.super_first = static_cast<uint32_t>(s0);
+    p.n_super_local = static_cast<uint32_t>(s1 - s0);
+    const uint64_t c0 = std::min<uint64_t>(p.n_chunks_total, s0 * p.super);
+    const uint64_t c1 = std::min<uint64_t>(p.n_chunks_total, s1 * p.super);
     p.chunk_first = static_cast<uint32_t>(c0);
     p.n_chunks_local = static_cast<uint32_t>(c1 - c0);
     p.first_particle = c0 * kChunk;
@@ -286,7 +311,8 @@ struct shard_options {
 struct shard_result {
     shard_plan plan;
     uint32_t rows_per_chunk = 1;       // partial rows per kChunk particles: 1 (fused) or kChunk / kSubChunk (row path)
-    uint32_t n_rows_local = 0, n_rows_total = 0, row_first = 0;
+    uint32_t n_rows_local = 0, n_rows_total = 0, row_first = 0;   // the rows handed on (super-chunk rows, see plan_shard)
+    const double * rows = nullptr;                                // [n_rows_local][n_cols] on the device
     int n_cols = 0;
     hist_window hw;
     double m_ref = 0.0;
@@ -345,11 +371,32 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     // partial-sum rows: one per chunk on the fused path, one per sub-chunk on the row path (same on every rank)
     const unsigned row_particles = fused ? kChunk : kSubChunk;
     res->rows_per_chunk = kChunk / row_particles;
-    res->n_rows_total = static_cast<uint32_t>((n_total + row_particles - 1) / row_particles);
-    res->row_first = plan.chunk_first * res->rows_per_chunk;
-    res->n_rows_local = static_cast<uint32_t>((plan.n_local + row_particles - 1) / row_particles);
+    const uint32_t kernel_rows = static_cast<uint32_t>((plan.n_local + row_particles - 1) / row_particles);   // rows the kernels write
+    const uint32_t rows_per_super = plan.super * res->rows_per_chunk;
+    res->n_rows_total = plan.n_super_total;
+    res->row_first = plan.super_first;
+    res->n_rows_local = plan.n_super_local;
+    if (rows_per_super == 1) {                 // small run on the fused path: the kernel rows are the rows handed on
+        res->n_rows_total = plan.n_chunks_total;
+        res->row_first = plan.chunk_first;
+        res->n_rows_local = kernel_rows;
+    }
+    res->rows = nullptr;
     if (plan.n_chunks_local == 0) return 0;
-    CU_TRY(e->d_partials.reserve(static_cast<size_t>(res->n_rows_local) * n_cols));
+    CU_TRY(e->d_partials.reserve(static_cast<size_t>(kernel_rows) * n_cols));
+    res->rows = e->d_partials.ptr;
+    // kernel rows -> super-chunk rows (in row order), on the compute stream
+    auto fold_rows = [&]() -> int {
+        if (rows_per_super == 1) return 0;
+        CU_TRY(e->d_super.reserve(static_cast<size_t>(plan.n_super_local) * n_cols));
+        const unsigned long long n_out = static_cast<unsigned long long>(plan.n_super_local) * n_cols;
+        k_fold_rows<<<static_cast<unsigned>((n_out + kBlock - 1) / kBlock), kBlock, 0, e->compute>>>(
+            e->d_partials.ptr, kernel_rows, rows_per_super, n_cols, kMaxColsMask, e->d_super.ptr, plan.n_super_local);
+        CU_TRY(cudaGetLastError());
+        ++res->launches;
+        res->rows = e->d_super.ptr;
+        return 0;
+    };
 
     run_args a;
     std::memset(&a, 0, sizeof a);
@@ -383,8 +430,9 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         k_fold_warp_partials<<<static_cast<unsigned>((fold_n + kBlock - 1) / kBlock), kBlock, 0, e->compute>>>(
             e->d_warp_partials.ptr, plan.n_chunks_local, nv, e->d_partials.ptr, n_cols);
         CU_TRY(cudaGetLastError());
-        CU_TRY(cudaEventRecord(e->ev_end, e->compute));
         res->launches += 2;
+        if (int rc = fold_rows()) return rc;
+        CU_TRY(cudaEventRecord(e->ev_end, e->compute));
         CU_TRY(cudaStreamSynchronize(e->compute));
         float ms = 0.f;
         CU_TRY(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));
@@ -642,7 +690,10 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         const int last = static_cast<int>((n_batches - 1) & 1);
         if (int rc = deliver(last ^ 1)) return rc;
         if (int rc = deliver(last)) return rc;
+        if (int rc = fold_rows()) return rc;
+        CU_TRY(cudaStreamSynchronize(e->compute));
     } else {
+        if (int rc = fold_rows()) return rc;
         CU_TRY(cudaEventRecord(e->ev_end, e->compute));
         CU_TRY(cudaStreamSynchronize(e->compute));
         float ms = 0.f;
@@ -753,7 +804,7 @@ int run_full(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, const do
         total_ms += res.device_ms;
         launches += res.launches;
         double merge_ms = 0.0;
-        const int rc = merge_impl(e, e->d_partials.ptr, res.n_rows_total, res.n_cols, static_cast<int>(e->structure.n_real),
+        const int rc = merge_impl(e, res.rows, res.n_rows_total, res.n_cols, static_cast<int>(e->structure.n_real),
                                   static_cast<int>(e->structure.n_int), res.hw, res.m_ref, n, out, &launches, &merge_ms);
         if (rc < 0) return rc;
         total_ms += merge_ms;
@@ -844,6 +895,25 @@ int cpprob_sis_plan_shard(uint64_t n_particles_total, int rank, int world, uint3
     return 0;
 }
 
+int cpprob_sis_plan_rows(uint64_t n_particles_total, int rank, int world, int rows_per_chunk, uint32_t * row_first,
+                         uint32_t * n_rows_local, uint32_t * n_rows_total)
+{
+    if (world <= 0 || rank < 0 || rank >= world || n_particles_total == 0 || rows_per_chunk <= 0) {
+        return fail(CPPROB_SIS_EINVAL, "bad rank / world / n / rows_per_chunk");
+    }
+    const shard_plan p = plan_shard(n_particles_total, rank, world);
+    if (p.super * static_cast<uint32_t>(rows_per_chunk) == 1) {
+        if (row_first) *row_first = p.chunk_first;
+        if (n_rows_local) *n_rows_local = p.n_chunks_local;
+        if (n_rows_total) *n_rows_total = p.n_chunks_total;
+    } else {
+        if (row_first) *row_first = p.super_first;
+        if (n_rows_local) *n_rows_local = p.n_super_local;
+        if (n_rows_total) *n_rows_total = p.n_super_total;
+    }
+    return 0;
+}
+
 int cpprob_sis_create(const cpprob_sis_config * cfg, cpprob_sis_engine ** out)
 {
     if (!out) return fail(CPPROB_SIS_EINVAL, "null out pointer");
@@ -895,7 +965,7 @@ void cpprob_sis_destroy(cpprob_sis_engine * e)
     cudaSetDevice(e->device);
     if (e->compute) cudaStreamSynchronize(e->compute);
     if (e->copy) cudaStreamSynchronize(e->copy);
-    e->d_obs.release(); e->d_pilot.release(); e->d_partials.release(); e->d_warp_partials.release(); e->d_merged.release(); e->d_gather.release();
+    e->d_obs.release(); e->d_pilot.release(); e->d_partials.release(); e->d_super.release(); e->d_warp_partials.release(); e->d_merged.release(); e->d_gather.release();
     e->d_counter.release(); e->d_int_extra.release(); e->h_merged.release();
     e->d_text_len.release(); e->d_text_bsum.release(); e->d_text_meta.release(); e->d_text_flags.release(); e->h_text_flags.release();
     for (int i = 0; i < 2; ++i) {
@@ -959,7 +1029,7 @@ int cpprob_sis_run_shard(cpprob_sis_engine * e, int model_id, const double * obs
     shard_result res;
     shard_options so;
     if (int rc = run_shard_impl(e, vt, obs, n_obs, n_particles_total, rank, world, m_ref_override, nullptr, so, &res)) return rc;
-    out->device_ptr = e->d_partials.ptr;
+    out->device_ptr = const_cast<double *>(res.rows);
     out->n_chunks_local = res.n_rows_local;
     out->n_chunks_total = res.n_rows_total;
     out->chunk_first = res.row_first;
@@ -1026,7 +1096,7 @@ int cpprob_sis_run_multi(cpprob_sis_engine * const * engines, int n_engines, int
             launches += sr.launches;
             if (sr.n_rows_local == 0) continue;
             CU_TRY(cudaMemcpyPeerAsync(primary->d_gather.ptr + static_cast<size_t>(sr.row_first) * n_cols, primary->device,
-                                       engines[r]->d_partials.ptr, engines[r]->device,
+                                       sr.rows, engines[r]->device,
                                        static_cast<size_t>(sr.n_rows_local) * n_cols * sizeof(double), primary->compute));
         }
         double merge_ms = 0.0;

@@ -1,5 +1,5 @@
 """Multi-GPU plumbing: one process per GPU, particles sharded by whole chunks, and ONE small collective —
-an all-gather of the per-chunk partial sums in rank order (NCCL over NVLink on the GPU box, gloo in the CPU
+an all-gather of the per-(super-)chunk partial sums in rank order (NCCL over NVLink on the GPU box, gloo in the CPU
 tests).  Merging the gathered rows in chunk order (cpprob_sis_merge) gives bit-identical results on every
 rank and for every world size; there is no data-path collective because particles are i.i.d.
 (/root/reference include/cpprob/cpprob.hpp:194-201 has no inter-particle dependence)."""
@@ -13,10 +13,9 @@ from . import capi
 
 @functools.lru_cache(maxsize=64)
 def shard_sizes(n_total, world, rows_per_chunk=1):
-    """partial rows of every rank (host arithmetic of cpprob_sis_plan_shard); a rank's rows are
-    ceil(n_local / (CHUNK / rows_per_chunk))."""
-    row_particles = capi.CHUNK // rows_per_chunk
-    return tuple(-(-capi.plan_shard(n_total, r, world)[4] // row_particles) for r in range(world))
+    """partial rows of every rank (host arithmetic of cpprob_sis_plan_rows): chunk rows for runs of up to 4096
+    chunks, super-chunk rows (2^k chunks each, reduced on the owning rank) beyond that — never more than 4096 in all."""
+    return tuple(capi.plan_rows(n_total, r, world, rows_per_chunk)[1] for r in range(world))
 
 
 def gather_partials(local, n_total, world, scratch=None, rows_per_chunk=1):

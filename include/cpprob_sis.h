@@ -171,12 +171,21 @@ int cpprob_sis_text_stage_stats(cpprob_sis_engine * e, double * kernel_ms, doubl
  * collective is needed.  Each rank returns its per-chunk partial sums in DEVICE memory; the caller
  * all-gathers them in rank order (NCCL) and hands the concatenation to cpprob_sis_merge, which is
  * bit-identical on every rank and for every world size. */
+/* The rows a rank hands to the gather (host arithmetic only).  Runs of up to 4096 chunks hand on their chunk
+ * rows (times rows_per_chunk); larger runs group 2^k consecutive chunks into super-chunks (k from the run's size
+ * only), a rank owns whole super-chunks and reduces each to one row before the gather: at most 4096 rows are
+ * exchanged whatever the particle count, and the merged sums stay bit-identical for any world size.
+ * rows_per_chunk: the value cpprob_sis_run_shard reported (1 or 8). */
+int cpprob_sis_plan_rows(uint64_t n_particles_total, int rank, int world, int rows_per_chunk, uint32_t * row_first,
+                         uint32_t * n_rows_local, uint32_t * n_rows_total);
+
 typedef struct cpprob_sis_partials {
-    double * device_ptr;         /* [n_chunks_local][n_cols], engine-owned */
+    double * device_ptr;         /* [n_chunks_local][n_cols] partial rows (see cpprob_sis_plan_rows), engine-owned */
     uint32_t n_chunks_local;     /* partial rows of this rank ... */
     uint32_t n_chunks_total;     /* ... of the whole run ... */
     uint32_t chunk_first;        /* ... and the index of this rank's first row */
-    uint32_t rows_per_chunk;     /* partial rows per 32768-particle chunk: 1 (fused kernel) or 8 (row path) */
+    uint32_t rows_per_chunk;     /* rows the kernels wrote per 32768-particle chunk: 1 (fused kernel) or 8 (row path);
+                                    argument of cpprob_sis_plan_rows */
     int n_cols;
     double m_ref;
     double device_ms;

@@ -50,6 +50,27 @@ def test_shard_plan_host_arithmetic():
         capi.plan_shard(n, 2, 2)
 
 
+def test_super_chunk_rows_host_arithmetic():
+    """Large runs hand on super-chunk rows: 2^k chunks each, k from the run size only, ranks own whole super-chunks."""
+    n = 100_000 * capi.CHUNK + 123                 # 100001 chunks -> S = 32, 3126 rows
+    rows = {}
+    for world in (1, 2, 3, 8):
+        first_expected, covered = 0, 0
+        for r in range(world):
+            rf, nl, nt = capi.plan_rows(n, r, world)
+            cf, ncl, nct, fp, nloc = capi.plan_shard(n, r, world)
+            assert nt == 3126 and nct == 100001 and rf == first_expected
+            assert cf == rf * 32 and fp == cf * capi.CHUNK          # shard boundaries sit on super-chunk boundaries
+            assert ncl == min(nct, (rf + nl) * 32) - cf
+            first_expected += nl
+            covered += nloc
+        assert first_expected == 3126 and covered == n
+        rows[world] = first_expected
+    # small runs: one row per chunk (or per chunk for the 8-rows-per-chunk row path, folded on the rank)
+    assert capi.plan_rows(10 * capi.CHUNK + 17, 0, 1) == (0, 11, 11)
+    assert capi.plan_rows(10 * capi.CHUNK + 17, 1, 2, 8) == (5, 6, 11)
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():

@@ -243,6 +243,36 @@ def test_bitwise_reproducible_for_any_grid_and_shard_count(engine):
         assert st["real_mean"][0] == base["real_mean"][0]
 
 
+@pytest.mark.parametrize("model,obs", [("gaussian_unknown_mean", [3.0, 4.0]), ("hmm", None)])
+def test_super_chunk_rows_are_world_size_invariant(engine, model, obs):
+    """Beyond 4096 chunks a rank reduces super-chunks (2^k chunks) to one row each before the gather
+    (cpprob_sis_plan_rows): the exchange stays <= 4096 rows and the merged sums are still bit-identical for 1, 2, 3
+    and 8 ranks, on the fused path and on the row path (8 kernel rows per chunk)."""
+    import ctypes
+    import torch
+    obs = G["obs_hmm_64"][:3] if obs is None else obs
+    n = 5000 * capi.CHUNK + 777                      # 5001 chunks -> super-chunks of 2, 2501 rows
+    base = engine.run(model, obs, n)
+    for world in (1, 2, 3, 8):
+        parts, m_ref, n_cols, total_rows = [], None, None, None
+        for r in range(world):
+            p = engine.run_shard(model, obs, n, r, world)
+            m_ref, n_cols, total_rows = p.m_ref, p.n_cols, p.n_chunks_total
+            assert (p.chunk_first, p.n_chunks_local, p.n_chunks_total) == capi.plan_rows(n, r, world, p.rows_per_chunk)
+            t = torch.empty((p.n_chunks_local, p.n_cols), dtype=torch.float64, device="cuda")
+            if p.n_chunks_local:
+                ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(p.device_ptr),
+                                                       ctypes.c_size_t(t.numel() * 8), 3)
+            parts.append(t)
+        g = torch.cat(parts).contiguous()
+        torch.cuda.synchronize()
+        assert g.shape[0] == total_rows == 2501
+        st, rebase = engine.merge(model, obs, g.data_ptr(), g.shape[0], n_cols, m_ref, n)
+        assert not rebase
+        assert (st["sums"] == base["sums"]).all(), world
+    assert base["n_particles"] == n
+
+
 # ---------------------------------------------------------------------------------------------------
 # edge cases
 # ---------------------------------------------------------------------------------------------------
