@@ -8,10 +8,11 @@
 // (include/cpprob/postprocess/stats_printer.hpp:88-120, empirical_distribution.hpp:52-81,117-143).
 // Here the model body, the weight exp(log_w - m_ref) and the estimator sums are one kernel.
 //
-// Determinism: particles are grouped in fixed CHUNKs of 2^15 consecutive global indices.  A chunk is
-// always reduced by one CTA with a fixed thread->particle map and a fixed shuffle/shared-memory
-// tree, so a chunk's partial sums are bit-identical whatever the grid size, schedule (chunks are
-// handed out through an atomic counter) or GPU count.  Chunk partials are then merged in chunk order
+// Determinism: particles are grouped in fixed CHUNKs of 2^15 consecutive global indices with a fixed
+// (virtual thread, warp slot) -> particle map.  A chunk's partial sums are always formed by the same tree
+// (per-thread sums, warp shuffles, the 8 warp slots in slot order), so they are bit-identical whatever
+// the grid size, schedule (work units are handed out through an atomic counter) or GPU count.  Chunk
+// partials are folded into super-chunk rows in chunk order (k_fold_rows) and those are merged in row order
 // by k_merge_columns.  All weights are taken relative to one run-wide reference m_ref (max log_w of
 // a pilot over global particles [0, 4096), identical on every rank), so merging is plain addition.
 #ifndef CPPROB_B200_SIS_KERNELS_CUH
@@ -134,16 +135,6 @@ __device__ __forceinline__ bool is_nan(double x)
 {
     const unsigned hi = static_cast<unsigned>(__double2hiint(x)) & 0x7FFFFFFFu;
     return hi > 0x7FF00000u || (hi == 0x7FF00000u && __double2loint(x) != 0);
-}
-
-// Next chunk for this CTA (dynamic schedule; results do not depend on it).
-__device__ __forceinline__ unsigned fetch_chunk(unsigned * counter, unsigned * s_slot)
-{
-    if (threadIdx.x == 0) *s_slot = atomicAdd(counter, 1u);
-    __syncthreads();
-    const unsigned c = *s_slot;
-    __syncthreads();
-    return c;
 }
 
 // Runs body(rng, i) for the particles of [0, n_here) owned by virtual thread `vt` (0..255): in every tile of 512
