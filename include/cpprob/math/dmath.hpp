@@ -303,10 +303,15 @@ inline double fabs(double x) { return std::fabs(x); }
 // instruction make that a good trade).  `tab` is what exp2_table_load() returned.
 // Same contract as exp_weight_unchecked: x finite and the result normal; the caller tracks the smallest n
 // (n >= -1021 * 256) and recomputes with exp_weight otherwise.  Non-finite x gives NaN.
+// The shared-memory copy stores each entry with its high word pre-decremented by j << 12, so that adding n << 12
+// (n = 256 k + j) lands on hi(T[j]) + (k << 20): the 2^k scaling costs one integer multiply-add on the loaded word.
 __device__ __forceinline__ unsigned exp2_table_load()
 {
     __shared__ double t[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) t[i] = tbl::exp2_tab[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const double v = tbl::exp2_tab[i];
+        t[i] = __hiloint2double(__double2hiint(v) - (i << 12), __double2loint(v));
+    }
     __syncthreads();
     unsigned base;
     asm volatile("{ .reg .u64 p; cvta.to.shared.u64 p, %1; cvt.u32.u64 %0, p; }" : "=r"(base) : "l"(t));
@@ -320,14 +325,14 @@ __device__ __forceinline__ double exp_weight_tab(double x, unsigned tab, int & n
     const double kf = t - magic;
     double r = fma(kf, -tbl::k_ln2_hi_256, x);
     r = fma(kf, -tbl::k_ln2_lo_256, r);
-    double tj;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab + ((static_cast<unsigned>(n) << 3) & 0x7f8u)));
+    int t_lo, t_hi;
+    asm("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(t_lo), "=r"(t_hi) : "r"(tab + ((static_cast<unsigned>(n) << 3) & 0x7f8u)));
+    const double tj = __hiloint2double(t_hi + (n << 12), t_lo);          // 2^k 2^(j/256)
     double q = fma(tbl::k_exp_c2, r, tbl::k_exp_c1);
     q = fma(q, r, 0.5);
     const double p = fma(r * r, q, r);
-    const double e = fma(tj, p, tj);                                  // in [1, 2)
     n_out = n;
-    return __hiloint2double(__double2hiint(e) + ((n >> 8) << 20), __double2loint(e));
+    return fma(tj, p, tj);
 }
 #endif  // __CUDACC__
 

@@ -39,7 +39,8 @@ def classify(op):
 
 
 BRANCH = re.compile(r"\bBRA(?:\.\w+)*\s+(?:!?\w+,\s*)*0x([0-9a-f]+)")   # BRA 0x..., @P0 BRA P3, 0x..., BRA.U !UP0, 0x...
-MARKERS = ("CALL.REL.NOINC", "MUFU.RSQ64H")   # one per normal draw: the ziggurat's slow-path call / Box-Muller's sqrt seed
+MARKERS = ("LDS", "CALL.REL.NOINC", "MUFU.RSQ64H")   # what only the steady-state particle loop issues most of: the table
+# loads of the ziggurat / exp (current build), the slow-path call sites (first ziggurat build), Box-Muller's sqrt seed
 
 
 def loop_marker(body):
@@ -47,8 +48,8 @@ def loop_marker(body):
 
 
 def particle_loop(body, marker=None):
-    """(lo, hi) addresses of the innermost loop (backward branch span) that contains `marker`:
-    the steady-state particle loop of the SIS kernels (the normal sampler is only issued there)."""
+    """(lo, hi) addresses of the innermost loop (backward branch span) with the most `marker` instructions:
+    the steady-state particle loop of the SIS kernels."""
     marker = marker or loop_marker(body)
     instr = []
     for line in body.splitlines():
@@ -64,7 +65,6 @@ def particle_loop(body, marker=None):
         tgt = int(m.group(1), 16)
         n_marks = sum(1 for x in marks if tgt <= x <= a)
         if tgt < a and n_marks:
-            # the hot loop is the one with the most sampler invocations per trip that is still innermost:
             # reject spans that contain another backward branch (outer loops)
             inner_back = any(tgt < a2 < a and (mm := BRANCH.search(t2)) and int(mm.group(1), 16) < a2
                              and int(mm.group(1), 16) >= tgt for a2, t2 in instr)
@@ -89,7 +89,9 @@ def loop_budget(path, needle):
             if m.group(2).startswith("MUFU.RSQ64H"):
                 c["box_muller"] += 1            # one per stream pair = 2 particles
             if m.group(2).startswith("CALL.REL.NOINC"):
-                c["slow_calls"] += 1            # ziggurat: one slow-path call site per draw = per particle of the README model
+                c["calls"] += 1
+            if m.group(2).startswith("ISETP.GE.U32"):
+                c["zig_tests"] += 1             # ziggurat: one high-word fast test per draw = per particle of the README model
             if classify(m.group(2)) == "fp64":
                 c["fp64"] += 1
             if base in ("DFMA", "DADD", "DMUL", "DSETP"):
@@ -105,7 +107,7 @@ def loop_budget(path, needle):
                 j -= 1
             cold += i - j + 2                   # set-up, the call and the jump over the fast tail
     c["cold"] = cold
-    c["particles_per_trip"] = c["slow_calls"] if c["slow_calls"] else 2 * c["box_muller"]
+    c["particles_per_trip"] = c["zig_tests"] if c["zig_tests"] else 2 * c["box_muller"]
     return dict(c)
 
 
