@@ -138,6 +138,20 @@ __global__ void __launch_bounds__(kBlock) k_row_hist(const int * __restrict__ in
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_pilot_finalize: the host fold of run_pilot on the device, for models that need nothing else from the pilot.
+// raw[3 t] = max log_w of pilot tile t; raw[0] becomes m_ref: the override if given, else the maximum if it is
+// finite and sane, else 0 (every pilot weight was -inf / nan).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pilot_finalize(double * raw, int tiles, int has_override, double override_value)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double mx = dm::neg_inf();
+    for (int t = 0; t < tiles; ++t) mx = fmax(mx, raw[3 * t]);
+    const double m = (mx > -1.0e300 && mx < 1.0e300) ? mx : 0.0;
+    raw[0] = has_override ? override_value : m;
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_fold_rows: super-chunk rows.  out[s][c] = rows [s*per, min((s+1)*per, n_rows)) of `in` combined in row
 // order by one thread (max columns with fmax, the others with +).  What a rank hands to the gather.
 // ------------------------------------------------------------------------------------------------

@@ -138,7 +138,7 @@ struct cpprob_sis_engine {
     unsigned long long text_force_every = 0;                      // CPPROB_SIS_TEXT_FORCE_AMBIGUOUS (test hook)
     double text_kernel_ms = 0.0, text_copy_ms = 0.0, text_write_s = 0.0;   // stage times of the last emitting run
     uint64_t text_bytes = 0, text_fixups = 0;
-    pinned_buffer<double> h_real[2], h_logw[2], h_merged;
+    pinned_buffer<double> h_real[2], h_logw[2], h_merged, h_pilot;
     pinned_buffer<int> h_int[2];
 
     // results kept alive for the caller
@@ -347,9 +347,23 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     const philox_keys keys(e->seed);
     CU_TRY(cudaEventRecord(e->ev_begin, e->compute));
     double pilot[3] = {0, 0, 0};
-    if (int rc = run_pilot(e, vt, keys, n_obs, n_total, m_ref_override, pilot)) return rc;
-    ++res->launches;
-    const double m_ref = pilot[0];
+    // A model without int predicts needs nothing from the pilot on the host before its kernels start: the maxima are
+    // folded on the device and m_ref is read back with the results (one host round trip less per inference).
+    const bool fused_early = !opt.force_rows && opt.emit == CPPROB_SIS_EMIT_NONE && n_int == 0 && n_real <= kMaxFusedReal;
+    if (fused_early) {
+        const int n_pilot = static_cast<int>(std::min<uint64_t>(n_total, kPilot));
+        CU_TRY(e->h_pilot.reserve(1));
+        CU_TRY(vt->launch_pilot(e->compute, &keys, e->d_obs.ptr, static_cast<int>(n_obs), n_pilot, e->d_pilot.ptr));
+        k_pilot_finalize<<<1, 32, 0, e->compute>>>(e->d_pilot.ptr, (n_pilot + 511) / 512, m_ref_override ? 1 : 0,
+                                                  m_ref_override ? *m_ref_override : 0.0);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(e->h_pilot.ptr, e->d_pilot.ptr, sizeof(double), cudaMemcpyDeviceToHost, e->compute));
+        res->launches += 2;
+    } else {
+        if (int rc = run_pilot(e, vt, keys, n_obs, n_total, m_ref_override, pilot)) return rc;
+        ++res->launches;
+    }
+    const double m_ref = pilot[0];             // fused_early: filled in after the particle kernel's sync
     hist_window hw;
     if (n_int > 0) {
         if (hw_override) {
@@ -367,7 +381,7 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     res->m_ref = m_ref;
     const int n_cols = kBaseCols + 2 * n_real + n_int * hw.bins;
     res->n_cols = n_cols;
-    const bool fused = !opt.force_rows && opt.emit == CPPROB_SIS_EMIT_NONE && n_int == 0 && n_real <= kMaxFusedReal;
+    const bool fused = fused_early;
     // partial-sum rows: one per chunk on the fused path, one per sub-chunk on the row path (same on every rank)
     const unsigned row_particles = fused ? kChunk : kSubChunk;
     res->rows_per_chunk = kChunk / row_particles;
@@ -382,7 +396,13 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         res->n_rows_local = kernel_rows;
     }
     res->rows = nullptr;
-    if (plan.n_chunks_local == 0) return 0;
+    if (plan.n_chunks_local == 0) {
+        if (fused_early) {                     // a rank without particles still reports the run's m_ref
+            CU_TRY(cudaStreamSynchronize(e->compute));
+            res->m_ref = e->h_pilot.ptr[0];
+        }
+        return 0;
+    }
     CU_TRY(e->d_partials.reserve(static_cast<size_t>(kernel_rows) * n_cols));
     res->rows = e->d_partials.ptr;
     // kernel rows -> super-chunk rows (in row order), on the compute stream
@@ -434,6 +454,7 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         if (int rc = fold_rows()) return rc;
         CU_TRY(cudaEventRecord(e->ev_end, e->compute));
         CU_TRY(cudaStreamSynchronize(e->compute));
+        res->m_ref = e->h_pilot.ptr[0];
         float ms = 0.f;
         CU_TRY(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));
         res->device_ms = ms;
@@ -966,7 +987,7 @@ void cpprob_sis_destroy(cpprob_sis_engine * e)
     if (e->compute) cudaStreamSynchronize(e->compute);
     if (e->copy) cudaStreamSynchronize(e->copy);
     e->d_obs.release(); e->d_pilot.release(); e->d_partials.release(); e->d_super.release(); e->d_warp_partials.release(); e->d_merged.release(); e->d_gather.release();
-    e->d_counter.release(); e->d_int_extra.release(); e->h_merged.release();
+    e->d_counter.release(); e->d_int_extra.release(); e->h_merged.release(); e->h_pilot.release();
     e->d_text_len.release(); e->d_text_bsum.release(); e->d_text_meta.release(); e->d_text_flags.release(); e->h_text_flags.release();
     for (int i = 0; i < 2; ++i) {
         e->d_text_slots[i].release(); e->h_text_meta[i].release();
