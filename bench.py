@@ -33,7 +33,7 @@ SEED = 0x5EED
 def sass_budget():
     """Per-particle instruction budget of k_sis_fused<gaussian_unknown_mean_model, 1>, counted in the SASS of the particle
     loop when the library was built (cpprob_b200/build.py, tools/sass_mix.py).  `hot` excludes the call set-up that only
-    the ziggurat's slow draws (0.12 %) execute; the slow path itself is not counted at all, so the figures are lower
+    the ziggurat's slow draws (0.06 %) execute; the slow path itself is not counted at all, so the figures are lower
     bounds of the work done.  "flop" counts DFMA as 2, DADD / DMUL as 1, DSETP as 0.  An FP64-pipe instruction holds the
     sub-partition's issue port for two cycles (measured), every other instruction for one:
     issue slots = 2 F + O."""

@@ -38,6 +38,17 @@ struct cpprob_sis_model_vtable {
 namespace cpprob {
 namespace engine {
 
+// Dynamic shared memory of a model's kernels: the ziggurat table, if the model draws normals.  More than the 48 KB a
+// kernel may use without asking, hence the attribute (set at every launch: it is per device, and cheap).
+template<class Model>
+constexpr unsigned model_smem() { return model_draws_normals<Model>::value ? zig::kSharedBytes : 0u; }
+
+template<class Kernel>
+inline cudaError_t allow_smem(Kernel k, unsigned bytes)
+{
+    return bytes > 48u * 1024u ? cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)) : cudaSuccess;
+}
+
 template<class Model>
 struct model_launchers {
     static int probe(const double * obs, int n_obs, unsigned long long seed, void * out)
@@ -47,19 +58,29 @@ struct model_launchers {
     }
     static cudaError_t pilot(cudaStream_t s, const philox_keys * keys, const double * obs, int n_obs, int n_pilot, double * out)
     {
-        k_pilot<Model><<<(n_pilot + 511) / 512, kBlock, 0, s>>>(*keys, obs, n_obs, n_pilot, out);
+        if (cudaError_t err = allow_smem(k_pilot<Model>, model_smem<Model>())) return err;
+        k_pilot<Model><<<(n_pilot + 511) / 512, kBlock, model_smem<Model>(), s>>>(*keys, obs, n_obs, n_pilot, out);
         return cudaGetLastError();
     }
     static cudaError_t fused(cudaStream_t s, int grid, int nr, const run_args * a)
     {
-        if (nr <= 1)      k_sis_fused<Model, 1><<<grid, fused_block(1), 0, s>>>(*a);
-        else if (nr == 2) k_sis_fused<Model, 2><<<grid, fused_block(2), 0, s>>>(*a);
-        else              k_sis_fused<Model, 4><<<grid, fused_block(4), 0, s>>>(*a);
+        constexpr unsigned smem = model_smem<Model>();
+        if (nr <= 1) {
+            if (cudaError_t err = allow_smem(k_sis_fused<Model, 1>, smem)) return err;
+            k_sis_fused<Model, 1><<<grid, fused_block(1), smem, s>>>(*a);
+        } else if (nr == 2) {
+            if (cudaError_t err = allow_smem(k_sis_fused<Model, 2>, smem)) return err;
+            k_sis_fused<Model, 2><<<grid, fused_block(2), smem, s>>>(*a);
+        } else {
+            if (cudaError_t err = allow_smem(k_sis_fused<Model, 4>, smem)) return err;
+            k_sis_fused<Model, 4><<<grid, fused_block(4), smem, s>>>(*a);
+        }
         return cudaGetLastError();
     }
     static cudaError_t rows(cudaStream_t s, int grid, const run_args * a)
     {
-        k_sis_rows<Model><<<grid, kBlock, 0, s>>>(*a);
+        if (cudaError_t err = allow_smem(k_sis_rows<Model>, model_smem<Model>())) return err;
+        k_sis_rows<Model><<<grid, kBlock, model_smem<Model>(), s>>>(*a);
         return cudaGetLastError();
     }
     static cudaError_t replay(cudaStream_t s, int grid, const double * obs, int n_obs, const double * real_rows,
@@ -72,11 +93,24 @@ struct model_launchers {
     {
         int n = 0;
         cudaError_t err;
+        constexpr unsigned smem = model_smem<Model>();
         switch (which) {
-        case 0: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_sis_fused<Model, 1>, fused_block(1), 0); break;
-        case 1: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_sis_fused<Model, 2>, fused_block(2), 0); break;
-        case 2: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_sis_fused<Model, 4>, fused_block(4), 0); break;
-        default: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_sis_rows<Model>, kBlock, 0); break;
+        case 0:
+            allow_smem(k_sis_fused<Model, 1>, smem);
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_sis_fused<Model, 1>, fused_block(1), smem);
+            break;
+        case 1:
+            allow_smem(k_sis_fused<Model, 2>, smem);
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_sis_fused<Model, 2>, fused_block(2), smem);
+            break;
+        case 2:
+            allow_smem(k_sis_fused<Model, 4>, smem);
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_sis_fused<Model, 4>, fused_block(4), smem);
+            break;
+        default:
+            allow_smem(k_sis_rows<Model>, smem);
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_sis_rows<Model>, kBlock, smem);
+            break;
         }
         return err == cudaSuccess ? n : 0;
     }

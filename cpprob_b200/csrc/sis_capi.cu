@@ -1319,7 +1319,8 @@ int cpprob_sis_sample(cpprob_sis_engine * e, int kind, const double * params, in
     op.seed = seed;
     op.first = first_particle;
     op.out = e->d_w[0].ptr;
-    k_map<<<map_grid(e, n), kBlock, 0, e->compute>>>(n, op);
+    CU_TRY(cudaFuncSetAttribute(k_map<sample_op>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(zig::kSharedBytes)));
+    k_map<<<map_grid(e, n), kBlock, zig::kSharedBytes, e->compute>>>(n, op);
     CU_TRY(cudaGetLastError());
     ++e->launches;
     CU_TRY(cudaMemcpyAsync(out, e->d_w[0].ptr, n * sizeof(double), cudaMemcpyDeviceToHost, e->compute));

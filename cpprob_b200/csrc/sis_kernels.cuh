@@ -30,7 +30,7 @@ namespace engine {
 #define CPPROB_TILES_PER_TRIP 2             // stream tiles (pairs of particles per thread) per loop trip
 #endif
 // The fused kernel's warps are autonomous, so its CTA size is only a register budget: one CTA of 768 threads per
-// SM = 32 warps at 64 registers and ONE copy of the 32 KB ziggurat table (measured best of 256x2, 256x3,
+// SM = 32 warps at 64 registers and ONE copy of the 64 KB ziggurat table (measured best of 256x2, 256x3,
 // 512 ... 1024: profiles/r01_notes.md).  Kernels that stage more predicts keep 256 threads.
 #ifndef CPPROB_FUSED_MIN_BLOCKS
 #define CPPROB_FUSED_MIN_BLOCKS 1           // resident CTAs per SM the one-predict fused kernel is compiled for
@@ -182,7 +182,7 @@ __device__ __forceinline__ void for_each_owned_particle(const philox_keys & keys
 }
 
 // A model that never draws a normal (directly or through gamma / beta) may say so with
-// `static constexpr bool draws_normals = false;`: its kernels then skip the 32 KB shared-memory ziggurat table,
+// `static constexpr bool draws_normals = false;`: its kernels then skip the 64 KB shared-memory ziggurat table,
 // which would otherwise cap their resident CTAs.  Absent = true (always safe).
 template<class Model, class = void>
 struct model_draws_normals : std::true_type {};

@@ -25,8 +25,8 @@
 //   * next_u32()      takes one 32-bit word from the current block (4 per block);
 //   * next_uniform()  takes an aligned pair of words (52 random mantissa bits, result in (0,1));
 //   * next_std_normal() takes an aligned pair of words (a, b) and runs one ziggurat trial on them
-//     (4096 layers, tools/gen_ziggurat.py): layer = bits 3..14 of a, sign = bit 0 of a, u = (b : a >> 12)
-//     * 2^-52.  99.88 % of the draws end there.  The others (wedges, the tail, rejected trials) take
+//     (8192 layers, tools/gen_ziggurat.py): layer = bits 3..15 of a, sign = bit 0 of a, u = (b : a >> 12)
+//     * 2^-52.  99.94 % of the draws end there.  The others (wedges, the tail, rejected trials) take
 //     all further randomness from a SIDE stream — same stream id, counter word 3 = tag | 0x80000000,
 //     counter word 2 = (block index << 2 | word position) of the pair, key rotated by the trial
 //     number — so the main stream's position never depends on how a draw went.
@@ -126,18 +126,19 @@ CPPROB_HD double u52_to_open01(std::uint32_t hi_word, std::uint32_t lo_word)
 // shared-memory copy (zig::load_shared() at kernel start, returns the table's shared-space address, which
 // the streams keep in a register); X and F in global memory are only touched by the slow path.
 //
-// One trial on the word pair (a, b):   layer i = bits 3..14 of a (so that `a & 0x7ff8` IS the byte offset of
-// X[i]), sign = bit 0 of a, u = 0.m with the 52-bit mantissa m = b : (a >> 12) — 49 independent bits; the last
-// three are also the top layer bits, i.e. a per-layer offset below 2^-49 that saves an instruction per draw —
+// One trial on the word pair (a, b):   layer i = bits 3..15 of a (so that `a & 0xfff8` IS the byte offset of
+// X[i]), sign = bit 0 of a, u = 0.m with the 52-bit mantissa m = b : (a >> 12) — 48 independent bits; the last
+// four are also the top layer bits, i.e. a per-layer offset below 2^-48 that saves an instruction per draw —
 // x = u X[i] rounded once, as fma(1 + u, X[i], -X[i]).  Fast accept: the high word of x is below the high word
-// of X[i+1].  4096 layers make the fast path settle 99.88 % of the draws: what is left is warp-divergent work
+// of X[i+1].  8192 layers make the fast path settle 99.94 % of the draws: what is left is warp-divergent work
 // (a full warp waits for its one slow lane), so the table is sized to make it rare rather than cheap.
 // ------------------------------------------------------------------------------------------------
 namespace zig {
 #include "cpprob/random/ziggurat_table.inc"
 constexpr int N = CPPROB_ZIG_N;
 constexpr double R = CPPROB_ZIG_R;
-static_assert(N == 4096, "the bit layout of a trial (layer = bits 3..14 of the first word) is written for 4096 layers");
+static_assert(N == 8192, "the bit layout of a trial (layer = bits 3..15 of the first word) is written for 8192 layers");
+constexpr unsigned kSharedBytes = (N + 1) * sizeof(double);   // dynamic shared memory a kernel that draws normals is launched with
 
 #if defined(__CUDACC__)
 static __device__ const double d_x[N + 1] = {CPPROB_ZIG_X_ROWS};
@@ -152,7 +153,8 @@ inline const double * h_f() { static const double t[N + 1] = {CPPROB_ZIG_F_ROWS}
 // instead of being re-derived (S2UR/ULEA...) at every table access.
 __device__ __forceinline__ unsigned load_shared()
 {
-    __shared__ double t[N + 1];
+    extern __shared__ double cpprob_zig_shared[];      // zig::kSharedBytes, asked for at launch (64 KB: beyond the static limit)
+    double * const t = cpprob_zig_shared;
     for (int i = threadIdx.x; i <= N; i += blockDim.x) t[i] = d_x[i];
     __syncthreads();
     unsigned base;
@@ -227,7 +229,7 @@ CPPROB_HD double gauss_kernel(double x)
 #endif
 }
 
-// The 0.12 % of draws the fast test does not settle.  Pure function of its arguments (the main stream is
+// The 0.06 % of draws the fast test does not settle.  Pure function of its arguments (the main stream is
 // not advanced); not inlined, so the particle loops carry only a call.  Everything comes in by value — the key
 // as its two seed words, from which the round keys are re-derived with integer adds — so that the call touches
 // no memory but the two table reads of a wedge.
@@ -326,7 +328,7 @@ public:
         pos_ += 2;
 #if CPPROB_ON_DEVICE
         double xi, xn;
-        const unsigned addr = zig_base_ + (a & 0x7ff8u);
+        const unsigned addr = zig_base_ + (a & 0xfff8u);
         asm("ld.shared.f64 %0, [%1];" : "=d"(xi) : "r"(addr));
         asm("ld.shared.f64 %0, [%1+8];" : "=d"(xn) : "r"(addr));
 #else

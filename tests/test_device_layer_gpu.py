@@ -164,7 +164,7 @@ def test_sampler_normal(engine):
 
 def test_sampler_normal_ziggurat_is_exact(engine):
     """The ziggurat (include/cpprob/random/philox.hpp) at 6.4e7 draws: equiprobable-bin chi-square, the tail beyond
-    r = 4.3859 (only produced by the slow path's exponential rejection), the region around the layer edges, the
+    r = 4.5486 (only produced by the slow path's exponential rejection), the region around the layer edges, the
     moments up to the 4th and the sign balance, all within 5 sigma of N(0,1)."""
     n = 64_000_000
     s = engine.sample("normal", [0.0, 1.0], n, seed=20240607)
@@ -173,7 +173,7 @@ def test_sampler_normal_ziggurat_is_exact(engine):
     counts = np.bincount(np.searchsorted(edges, s), minlength=512)
     assert stats.chisquare(counts).pvalue > 1e-4
     a = np.abs(s)
-    for lo, hi in ((4.385945034871305, np.inf), (3.0, 4.385945034871305), (4.5, np.inf), (0.0, 0.01), (4.3, 4.5)):
+    for lo, hi in ((4.548600609949139, np.inf), (3.0, 4.548600609949139), (4.8, np.inf), (0.0, 0.01), (4.4, 4.6)):
         p = 2 * (stats.norm.sf(lo) - stats.norm.sf(hi))
         got = np.count_nonzero((a >= lo) & (a < hi))
         assert abs(got - n * p) < 5 * math.sqrt(n * p) + 1, (lo, hi, got, n * p)
@@ -191,16 +191,16 @@ def test_sampler_normal_ziggurat_is_exact(engine):
 
 def test_sampler_normal_matches_host_twin(engine):
     """Same header, same bits: the GPU's normals equal the host twin's (examples/zig_check.cpp).  The fast path is
-    integer work plus one fma; only the 0.12 % slow-path draws call exp / log, where libm and the device may differ
+    integer work plus one fma; only the 0.06 % slow-path draws call exp / log, where libm and the device may differ
     in the last place."""
     import test_ziggurat
-    n = 300_000
+    n = 3_000_000                                          # ~16 draws beyond r expected
     host = test_ziggurat.host_normals(99, 1000, n)
     dev = engine.sample("normal", [0.0, 1.0], n, seed=99, first=1000)
     same = host == dev
     assert same.mean() > 0.9999
     np.testing.assert_allclose(dev[~same], host[~same], rtol=1e-14)
-    assert np.abs(dev).max() > 4.385945034871305          # the tail branch was exercised
+    assert np.abs(dev).max() > 4.548600609949139          # the tail branch was exercised
 
 
 def test_sampler_uniform_real(engine):

@@ -20,7 +20,7 @@ def test_particle_loop_budget():
     per = saved["particles_per_trip"]
     assert per == b["particles_per_trip"] and per in (2, 4)
     # per particle: <= 27 FP64-pipe instructions and <= 74 hot instructions in all (the ziggurat draw is one DFMA, the
-    # weight's exp nine; `cold` = call set-up that only the 0.12 % slow draws execute)
+    # weight's exp nine; `cold` = call set-up that only the 0.06 % slow draws execute)
     hot = b["total"] - b["cold"]
     assert b["fp64"] / per <= 27 and hot / per <= 74
     # every FP64 instruction holds the issue port for two cycles ("issue model"): issue slots per

@@ -97,7 +97,7 @@ def loop_budget(path, needle):
             if base in ("DFMA", "DADD", "DMUL", "DSETP"):
                 c[base.lower()] += 1
     # instructions that only run on the slow path of a draw (argument set-up between the fast-accept branch and
-    # the call): static, but executed by 0.12 % of the draws
+    # the call): static, but executed by 0.06 % of the draws
     lines = [l for l in body.splitlines() if (mm := re.match(r"\s*/\*([0-9a-f]{4,})\*/", l)) and lo <= int(mm.group(1), 16) <= hi]
     cold = 0
     for i, l in enumerate(lines):
