@@ -159,7 +159,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from cpprob_b200 import Engine
-    from cpprob_b200.dist import gather_partials
+    from cpprob_b200.dist import gather_padded
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -191,16 +191,17 @@ def run_ours(args):
             if world == 1:
                 ptr, n_chunks = p.device_ptr, p.n_chunks_total
             else:
-                # the one collective of the path: all-gather of the per-chunk partial sums in rank order (NCCL over NVLink)
-                local = (torch.as_tensor(_DeviceArray(p.device_ptr, (p.n_chunks_local, p.n_cols)), device="cuda") if p.n_chunks_local
-                         else torch.empty((0, p.n_cols), dtype=torch.float64, device="cuda"))
-                if "scratch" not in gathered_buf:
-                    max_local = -(-p.n_chunks_total // world)
-                    gathered_buf["scratch"] = (torch.zeros((max_local, p.n_cols), dtype=torch.float64, device="cuda"),
-                                               torch.empty((world, max_local, p.n_cols), dtype=torch.float64, device="cuda"))
-                g = gather_partials(local, total, world, gathered_buf["scratch"], p.rows_per_chunk)
+                # the one collective of the path: all-gather of the per-(super-)chunk partial rows in rank order (NCCL over
+                # NVLink), straight from the engine's buffer; the engine compacts and merges the gathered segments
+                g, rows_per_rank = gather_padded(p, total, world, gathered_buf)
                 torch.cuda.synchronize()
-                ptr, n_chunks = g.data_ptr(), g.shape[0]
+                st, rebase = engine.merge_padded(MODEL, OBS, g.data_ptr(), world, rows_per_rank, p.rows_per_chunk, p.n_cols, p.m_ref, total)
+                kernel_ms += st["device_ms"]
+                launches += st["kernel_launches"]
+                if not rebase:
+                    return st, kernel_ms, launches
+                m_ref = st["max_log_w"]
+                continue
             st, rebase = engine.merge(MODEL, OBS, ptr, n_chunks, p.n_cols, p.m_ref, total)
             kernel_ms += st["device_ms"]
             launches += st["kernel_launches"]

@@ -26,7 +26,7 @@ SYMBOLS = [
     "cpprob_sis_merge", "cpprob_sis_replay", "cpprob_sis_reduce_records", "cpprob_sis_logpdf",
     "cpprob_sis_sample", "cpprob_sis_philox", "cpprob_sis_dmath", "cpprob_sis_measure_dfma_peak",
     "cpprob_sis_measure_store_peak", "cpprob_sis_plan_shard", "cpprob_sis_probe_issue", "cpprob_sis_probe_dfma_chains", "cpprob_sis_run_multi", "cpprob_sis_write_summary",
-    "cpprob_sis_text_stage_stats", "cpprob_sis_plan_rows",
+    "cpprob_sis_text_stage_stats", "cpprob_sis_plan_rows", "cpprob_sis_merge_padded",
 ]
 
 
@@ -103,6 +103,8 @@ def lib():
         L.cpprob_sis_run_shard.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t, u64, C.c_int, C.c_int, dp, C.POINTER(Partials)]
         L.cpprob_sis_merge.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t, C.c_void_p, C.c_uint32, C.c_int, C.c_double, u64,
                                        C.POINTER(Stats)]
+        L.cpprob_sis_merge_padded.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t, C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_double, u64,
+                                              C.POINTER(Stats)]
         L.cpprob_sis_replay.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t, dp, C.POINTER(C.c_int32), u64, u64, dp]
         L.cpprob_sis_reduce_records.argtypes = [C.c_void_p, dp, C.c_int, C.POINTER(C.c_int32), C.c_int, dp, u64, u64, C.POINTER(Stats)]
         L.cpprob_sis_logpdf.argtypes = [C.c_void_p, C.c_int, dp, C.c_int, dp, u64, dp]
@@ -276,6 +278,14 @@ class Engine:
         st = Stats()
         rc = _check(self._L.cpprob_sis_merge(self._h, self.model_id(model), _dptr(obs), obs.size, C.c_void_p(gathered_ptr),
                                              n_chunks_total, n_cols, m_ref, int(n_total), C.byref(st)))
+        return stats_to_dict(st), rc == 1
+
+    def merge_padded(self, model, obs, gathered_ptr, world, rows_per_rank, rows_per_chunk, n_cols, m_ref, n_total):
+        """gathered_ptr: device address of the raw all-gather output, `world` segments of rows_per_rank rows."""
+        obs = _f64(obs)
+        st = Stats()
+        rc = _check(self._L.cpprob_sis_merge_padded(self._h, self.model_id(model), _dptr(obs), obs.size, C.c_void_p(int(gathered_ptr)),
+                                                    world, rows_per_rank, rows_per_chunk, n_cols, m_ref, int(n_total), C.byref(st)))
         return stats_to_dict(st), rc == 1
 
     def replay(self, model, obs, real_rows=None, int_rows=None):

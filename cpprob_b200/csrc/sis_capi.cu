@@ -403,12 +403,12 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         }
         return 0;
     }
-    CU_TRY(e->d_partials.reserve(static_cast<size_t>(kernel_rows) * n_cols));
+    CU_TRY(e->d_partials.reserve(static_cast<size_t>(kernel_rows + 1) * n_cols));   // + 1: see cpprob_sis_merge_padded
     res->rows = e->d_partials.ptr;
     // kernel rows -> super-chunk rows (in row order), on the compute stream
     auto fold_rows = [&]() -> int {
         if (rows_per_super == 1) return 0;
-        CU_TRY(e->d_super.reserve(static_cast<size_t>(plan.n_super_local) * n_cols));
+        CU_TRY(e->d_super.reserve(static_cast<size_t>(plan.n_super_local + 1) * n_cols));
         const unsigned long long n_out = static_cast<unsigned long long>(plan.n_super_local) * n_cols;
         k_fold_rows<<<static_cast<unsigned>((n_out + kBlock - 1) / kBlock), kBlock, 0, e->compute>>>(
             e->d_partials.ptr, kernel_rows, rows_per_super, n_cols, kMaxColsMask, e->d_super.ptr, plan.n_super_local);
@@ -1140,6 +1140,28 @@ int cpprob_sis_run_multi(cpprob_sis_engine * const * engines, int n_engines, int
     out->kernel_launches = launches;
     primary->launches += launches;
     return 0;
+}
+
+int cpprob_sis_merge_padded(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs, const double * gathered,
+                            int world, uint32_t rows_per_rank, int rows_per_chunk, int n_cols, double m_ref,
+                            uint64_t n_particles_total, cpprob_sis_stats * out)
+{
+    if (!e || !gathered || world <= 0 || n_cols <= 0) return fail(CPPROB_SIS_EINVAL, "bad argument");
+    if (int rc = use_device(e)) return rc;
+    // rank r's rows sit at gathered[r * rows_per_rank ...]; its count is host arithmetic (cpprob_sis_plan_rows)
+    uint32_t n_total_rows = 0, seen = 0;
+    for (int r = 0; r < world; ++r) {
+        uint32_t first = 0, n_local = 0;
+        if (int rc = cpprob_sis_plan_rows(n_particles_total, r, world, rows_per_chunk, &first, &n_local, &n_total_rows)) return rc;
+        if (n_local > rows_per_rank || first != seen) return fail(CPPROB_SIS_EINVAL, "rows_per_rank is smaller than a rank's row count");
+        if (r == 0) CU_TRY(e->d_gather.reserve(static_cast<size_t>(n_total_rows) * n_cols));
+        if (n_local) {
+            CU_TRY(cudaMemcpyAsync(e->d_gather.ptr + static_cast<size_t>(first) * n_cols, gathered + static_cast<size_t>(r) * rows_per_rank * n_cols,
+                                   static_cast<size_t>(n_local) * n_cols * sizeof(double), cudaMemcpyDeviceToDevice, e->compute));
+        }
+        seen += n_local;
+    }
+    return cpprob_sis_merge(e, model_id, obs, n_obs, e->d_gather.ptr, n_total_rows, n_cols, m_ref, n_particles_total, out);
 }
 
 int cpprob_sis_merge(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs, const double * gathered,

@@ -34,3 +34,27 @@ def gather_partials(local, n_total, world, scratch=None, rows_per_chunk=1):
     padded[:local.shape[0]].copy_(local)
     dist.all_gather_into_tensor(allbuf.view(world * max_local, n_cols), padded)
     return torch.cat([allbuf[r, :sizes[r]] for r in range(world)]).contiguous()
+
+
+class _DeviceRows:
+    """zero-copy view of an engine-owned device buffer"""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def gather_padded(p, n_total, world, cache):
+    """The exchange of an inference with the fewest host-side steps: every rank contributes rows_per_rank = max over
+    ranks of its row count, straight from the buffer cpprob_sis_run_shard returned (which always has room for one row
+    more than it holds), in ONE all_gather_into_tensor; cpprob_sis_merge_padded compacts the segments on the device.
+    p: the Partials of this rank.  cache: a dict the caller keeps between steps.  Returns (gathered tensor, rows_per_rank)."""
+    key = (n_total, world, p.rows_per_chunk, p.n_cols)
+    if cache.get("key") != key:
+        m = max(shard_sizes(n_total, world, p.rows_per_chunk))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        cache.update(key=key, m=m, out=torch.empty((world * m, p.n_cols), dtype=torch.float64, device=dev),
+                     empty=torch.zeros((m, p.n_cols), dtype=torch.float64, device=dev))
+    m = cache["m"]
+    local = torch.as_tensor(_DeviceRows(p.device_ptr, (m, p.n_cols)), device="cuda") if p.n_chunks_local else cache["empty"]
+    dist.all_gather_into_tensor(cache["out"], local)
+    return cache["out"], m

@@ -218,6 +218,15 @@ int cpprob_sis_merge(cpprob_sis_engine * e, int model_id, const double * obs, si
                      const double * gathered, uint32_t n_chunks_total, int n_cols, double m_ref,
                      uint64_t n_particles_total, cpprob_sis_stats * out);
 
+/* Same, on the raw output of an all-gather: `gathered` holds `world` segments of rows_per_rank rows, segment r
+ * starting with rank r's rows (cpprob_sis_plan_rows gives how many; the rest of a segment is ignored).  The buffer
+ * a shard returns always has room for one row more than it holds, so a rank may contribute
+ * rows_per_rank = max over ranks of n_rows_local rows straight from cpprob_sis_partials.device_ptr.  The rows are
+ * compacted on the device and merged exactly as cpprob_sis_merge does: same bits. */
+int cpprob_sis_merge_padded(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs, const double * gathered,
+                            int world, uint32_t rows_per_rank, int rows_per_chunk, int n_cols, double m_ref,
+                            uint64_t n_particles_total, cpprob_sis_stats * out);
+
 /* ---- replay ------------------------------------------------------------------------------------
  * Recomputes log_w for n recorded traces (host SoA rows as in cpprob_sis_block) by re-running the
  * model with every sample statement returning the recorded value.  Parity gate for

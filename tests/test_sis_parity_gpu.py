@@ -270,6 +270,14 @@ def test_super_chunk_rows_are_world_size_invariant(engine, model, obs):
         st, rebase = engine.merge(model, obs, g.data_ptr(), g.shape[0], n_cols, m_ref, n)
         assert not rebase
         assert (st["sums"] == base["sums"]).all(), world
+        # the raw all-gather layout (segments padded to the largest shard, padding never initialised) merges to the same bits
+        m = max(t.shape[0] for t in parts)
+        padded = torch.full((world, m, n_cols), float("nan"), dtype=torch.float64, device="cuda")
+        for r, t in enumerate(parts):
+            padded[r, :t.shape[0]] = t
+        torch.cuda.synchronize()
+        st2, rebase2 = engine.merge_padded(model, obs, padded.data_ptr(), world, m, p.rows_per_chunk, n_cols, m_ref, n)
+        assert not rebase2 and (st2["sums"] == base["sums"]).all(), world
     assert base["n_particles"] == n
 
 
