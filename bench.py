@@ -184,6 +184,10 @@ def run_ours(args):
 
     def step():
         """One inference pass of `total` particles over `world` GPUs.  Returns (stats, kernel_ms, launches)."""
+        if world == 1:
+            # cpprob_sis_run: pilot, particle kernel, folds and merge queued back to back, one synchronisation
+            st = engine.run(MODEL, OBS, total)
+            return st, st["device_ms"], st["kernel_launches"]
         m_ref = None
         for _attempt in range(3):
             p = engine.run_shard(MODEL, OBS, total, rank, world, m_ref=m_ref)

@@ -117,7 +117,7 @@ struct cpprob_sis_engine {
     uint64_t seed = 0;
     uint64_t max_batch = 0;
     cudaStream_t compute = nullptr, copy = nullptr;
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_merge_begin = nullptr, ev_merge_end = nullptr;
     cudaEvent_t ev_computed[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     cudaEvent_t ev_batch_begin[2] = {nullptr, nullptr};
 
@@ -306,6 +306,7 @@ struct shard_options {
     cpprob_sis_block_fn on_block = nullptr;
     void * user = nullptr;
     cpprob::text::posterior_writer * text_writer = nullptr;   // EMIT_ALL with the records formatted on the GPU
+    bool no_wait = false;    // fused path only: return right after the launches; merge_impl(..., pending) collects m_ref and the time
 };
 
 struct shard_result {
@@ -313,6 +314,7 @@ struct shard_result {
     uint32_t rows_per_chunk = 1;       // partial rows per kChunk particles: 1 (fused) or kChunk / kSubChunk (row path)
     uint32_t n_rows_local = 0, n_rows_total = 0, row_first = 0;   // the rows handed on (super-chunk rows, see plan_shard)
     const double * rows = nullptr;                                // [n_rows_local][n_cols] on the device
+    bool waiting = false;                                         // launched with no_wait: m_ref / device_ms not collected yet
     int n_cols = 0;
     hist_window hw;
     double m_ref = 0.0;
@@ -453,6 +455,10 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         res->launches += 2;
         if (int rc = fold_rows()) return rc;
         CU_TRY(cudaEventRecord(e->ev_end, e->compute));
+        if (opt.no_wait) {
+            res->waiting = true;
+            return 0;
+        }
         CU_TRY(cudaStreamSynchronize(e->compute));
         res->m_ref = e->h_pilot.ptr[0];
         float ms = 0.f;
@@ -726,22 +732,31 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
 
 // Merge [n_chunks][n_cols] partials (device) and turn the sums into estimators.
 // Returns 1 if the weights must be re-based to out->max_log_w.
+// `pending`: a fused shard of this engine that was launched without waiting (shard_options::no_wait); its m_ref and
+// device time are collected here, after the one synchronisation of the inference.
 int merge_impl(cpprob_sis_engine * e, const double * gathered, uint32_t n_chunks, int n_cols, int n_real, int n_int,
-               hist_window hw, double m_ref, uint64_t n_total, cpprob_sis_stats * out, uint64_t * launches, double * ms_out)
+               hist_window hw, double m_ref, uint64_t n_total, cpprob_sis_stats * out, uint64_t * launches, double * ms_out,
+               shard_result * pending = nullptr)
 {
     if (n_cols != kBaseCols + 2 * n_real + n_int * hw.bins) return fail(CPPROB_SIS_EINVAL, "n_cols does not match the model structure");
     CU_TRY(e->d_merged.reserve(static_cast<size_t>(n_cols)));
     CU_TRY(e->h_merged.reserve(static_cast<size_t>(n_cols)));
-    CU_TRY(cudaEventRecord(e->ev_begin, e->compute));
+    CU_TRY(cudaEventRecord(e->ev_merge_begin, e->compute));
     k_merge_columns<<<n_cols, kBlock, 0, e->compute>>>(gathered, n_chunks, n_cols, kMaxColsMask, e->d_merged.ptr);
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaEventRecord(e->ev_end, e->compute));
+    CU_TRY(cudaEventRecord(e->ev_merge_end, e->compute));
     ++*launches;
     CU_TRY(cudaMemcpyAsync(e->h_merged.ptr, e->d_merged.ptr, n_cols * sizeof(double), cudaMemcpyDeviceToHost, e->compute));
     CU_TRY(cudaStreamSynchronize(e->compute));
     float ms = 0.f;
-    CU_TRY(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));
+    CU_TRY(cudaEventElapsedTime(&ms, e->ev_merge_begin, e->ev_merge_end));
     *ms_out = ms;
+    if (pending && pending->waiting) {
+        pending->waiting = false;
+        pending->m_ref = m_ref = e->h_pilot.ptr[0];
+        CU_TRY(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));
+        pending->device_ms = ms;
+    }
 
     const double * s = e->h_merged.ptr;
     e->sums.assign(s, s + n_cols);
@@ -819,16 +834,17 @@ int run_full(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, const do
     double total_ms = 0.0;
     uint64_t launches = 0;
     int passes = 0;
+    opt.no_wait = true;      // one synchronisation per inference on the fused path: after the merge
     for (;;) {
+        res.waiting = false;
         if (int rc = run_shard_impl(e, vt, obs, n_obs, n, 0, 1, mo, ho, opt, &res)) return rc;
         ++passes;
-        total_ms += res.device_ms;
         launches += res.launches;
         double merge_ms = 0.0;
         const int rc = merge_impl(e, res.rows, res.n_rows_total, res.n_cols, static_cast<int>(e->structure.n_real),
-                                  static_cast<int>(e->structure.n_int), res.hw, res.m_ref, n, out, &launches, &merge_ms);
+                                  static_cast<int>(e->structure.n_int), res.hw, res.m_ref, n, out, &launches, &merge_ms, &res);
         if (rc < 0) return rc;
-        total_ms += merge_ms;
+        total_ms += res.device_ms + merge_ms;
         bool again = false;
         if (rc == 1 && passes < 3) {
             m_ref_override = out->max_log_w;
@@ -968,6 +984,8 @@ int cpprob_sis_create(const cpprob_sis_config * cfg, cpprob_sis_engine ** out)
     if ((c = cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
     if ((c = cudaEventCreate(&e->ev_begin)) != cudaSuccess) return bail(c, "cudaEventCreate");
     if ((c = cudaEventCreate(&e->ev_end)) != cudaSuccess) return bail(c, "cudaEventCreate");
+    if ((c = cudaEventCreate(&e->ev_merge_begin)) != cudaSuccess) return bail(c, "cudaEventCreate");
+    if ((c = cudaEventCreate(&e->ev_merge_end)) != cudaSuccess) return bail(c, "cudaEventCreate");
     for (int i = 0; i < 2; ++i) {
         if ((c = cudaEventCreate(&e->ev_computed[i])) != cudaSuccess) return bail(c, "cudaEventCreate");
         if ((c = cudaEventCreate(&e->ev_copied[i])) != cudaSuccess) return bail(c, "cudaEventCreate");
@@ -1002,6 +1020,8 @@ void cpprob_sis_destroy(cpprob_sis_engine * e)
         if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]);
         if (e->ev_batch_begin[i]) cudaEventDestroy(e->ev_batch_begin[i]);
     }
+    if (e->ev_merge_begin) cudaEventDestroy(e->ev_merge_begin);
+    if (e->ev_merge_end) cudaEventDestroy(e->ev_merge_end);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
     if (e->ev_end) cudaEventDestroy(e->ev_end);
     if (e->compute) cudaStreamDestroy(e->compute);
