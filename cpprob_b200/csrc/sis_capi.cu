@@ -126,8 +126,8 @@ struct cpprob_sis_engine {
     device_buffer<unsigned> d_counter;
     device_buffer<int_extra> d_int_extra;
     // device-side text stage: per-record lengths, CTA sums / offsets, the text itself, slot descriptors, ambiguity list
-    device_buffer<unsigned> d_text_len;
-    device_buffer<unsigned long long> d_text_bsum, d_text_meta;   // meta: [kind]{total bytes, #ambiguous}
+    device_buffer<unsigned> d_text_len[2];                        // [kind]
+    device_buffer<unsigned long long> d_text_bsum[2], d_text_meta;   // meta: [kind]{total bytes, #ambiguous}
     device_buffer<char> d_text[2][2];                             // [double buffer][kind: 0 real, 1 int]
     device_buffer<text_slot> d_text_slots[2];
     device_buffer<text_flag> d_text_flags;                        // [kind][kMaxTextFlags]
@@ -494,8 +494,7 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     if (occ <= 0) occ = 1;
     if (e->blocks_per_sm > 0) occ = std::min(occ, e->blocks_per_sm);
 
-    // text stage set-up: slot descriptors on the device, worst-case line length per kind
-    size_t max_line[2] = {0, 0};
+    // text stage set-up: slot descriptors and per-record length / CTA offset arrays on the device
     int n_text_slots[2] = {0, 0};
     if (text_mode) {
         e->text_kernel_ms = e->text_copy_ms = e->text_write_s = 0.0;
@@ -504,22 +503,13 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
             const std::vector<cpprob_sis_slot> & sl = opt.text_writer->slots(kind == 1);
             if (sl.empty()) continue;
             std::vector<text_slot> h;
-            size_t line = 4 + 24 + 2;                                  // "([" ... "] " logw ")\n"
-            for (const auto & s : sl) {
-                h.push_back(text_slot{s.id, s.row, s.width});
-                line += 16 + (kind == 1 ? 12 : static_cast<size_t>(s.width) * 25 + 2);   // "(id " value ") "
-            }
+            for (const auto & s : sl) h.push_back(text_slot{s.id, s.row, s.width});
             n_text_slots[kind] = static_cast<int>(h.size());
-            max_line[kind] = line;
             CU_TRY(e->d_text_slots[kind].reserve(h.size()));
             CU_TRY(cudaMemcpy(e->d_text_slots[kind].ptr, h.data(), h.size() * sizeof(text_slot), cudaMemcpyHostToDevice));
-            for (int b = 0; b < 2; ++b) {
-                CU_TRY(e->d_text[b][kind].reserve(line * cap));
-                CU_TRY(e->h_text[b][kind].reserve(line * cap));
-            }
+            CU_TRY(e->d_text_len[kind].reserve(cap));
+            CU_TRY(e->d_text_bsum[kind].reserve((cap + kTextBlock - 1) / kTextBlock));
         }
-        CU_TRY(e->d_text_len.reserve(cap));
-        CU_TRY(e->d_text_bsum.reserve((cap + kTextBlock - 1) / kTextBlock));
         CU_TRY(e->d_text_meta.reserve(4));
         CU_TRY(e->d_text_flags.reserve(2 * kMaxTextFlags));
         CU_TRY(e->h_text_flags.reserve(4 * kMaxTextFlags));
@@ -643,33 +633,50 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
             CU_TRY(cudaEventRecord(e->ev_computed[buf], e->compute));
             CU_TRY(cudaMemsetAsync(e->d_text_meta.ptr, 0, 4 * sizeof(unsigned long long), e->compute));
             const unsigned text_blocks = static_cast<unsigned>((n_here + kTextBlock - 1) / kTextBlock);
+            text_args ta[2];
+            // pass 1: every record's length, the CTA offsets and the batch's text size, per kind
             for (int kind = 0; kind < 2; ++kind) {
                 if (!n_text_slots[kind]) continue;
-                text_args ta;
-                ta.slots = e->d_text_slots[kind].ptr;
-                ta.n_slots = n_text_slots[kind];
-                ta.is_int = kind;
-                ta.real_rows = a.real_rows;
-                ta.int_rows = a.int_rows;
-                ta.logw = a.logw;
-                ta.stride = cap;
-                ta.n = n_here;
-                ta.first_particle = plan.first_particle + off;
-                ta.force_every = e->text_force_every;
-                k_text_lengths<<<text_blocks, kTextBlock, 0, e->compute>>>(ta, e->d_text_len.ptr, e->d_text_bsum.ptr);
+                ta[kind].slots = e->d_text_slots[kind].ptr;
+                ta[kind].n_slots = n_text_slots[kind];
+                ta[kind].is_int = kind;
+                ta[kind].real_rows = a.real_rows;
+                ta[kind].int_rows = a.int_rows;
+                ta[kind].logw = a.logw;
+                ta[kind].stride = cap;
+                ta[kind].n = n_here;
+                ta[kind].first_particle = plan.first_particle + off;
+                ta[kind].force_every = e->text_force_every;
+                k_text_lengths<<<text_blocks, kTextBlock, 0, e->compute>>>(ta[kind], e->d_text_len[kind].ptr, e->d_text_bsum[kind].ptr);
                 CU_TRY(cudaGetLastError());
-                k_text_scan<<<1, 1024, 0, e->compute>>>(e->d_text_bsum.ptr, text_blocks, e->d_text_meta.ptr + 2 * kind);
+                k_text_scan<<<1, 1024, 0, e->compute>>>(e->d_text_bsum[kind].ptr, text_blocks, e->d_text_meta.ptr + 2 * kind);
                 CU_TRY(cudaGetLastError());
-                k_text_write<<<text_blocks, kTextBlock, 0, e->compute>>>(ta, e->d_text_len.ptr, e->d_text_bsum.ptr, e->d_text[buf][kind].ptr,
-                                                                         e->d_text_flags.ptr + kind * kMaxTextFlags,
+                res->launches += 2;
+            }
+            CU_TRY(cudaMemcpyAsync(e->h_text_meta[buf].ptr, e->d_text_meta.ptr, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->compute));
+            CU_TRY(cudaStreamSynchronize(e->compute));
+            // the text buffers are sized from the measured totals (grow-only, 1/16 head room), not from a worst case:
+            // an hmm<1000> line is 6 KB, its worst case 28 KB
+            for (int kind = 0; kind < 2; ++kind) {
+                if (!n_text_slots[kind]) continue;
+                const size_t total = e->h_text_meta[buf].ptr[2 * kind];
+                pending[buf].text_bytes[kind] = total;
+                if (total > e->d_text[buf][kind].cap) CU_TRY(e->d_text[buf][kind].reserve(total + total / 16 + 4096));
+                if (total > e->h_text[buf][kind].cap) CU_TRY(e->h_text[buf][kind].reserve(total + total / 16 + 4096));
+            }
+            // pass 2: every record formatted again at its final offset
+            for (int kind = 0; kind < 2; ++kind) {
+                if (!n_text_slots[kind]) continue;
+                k_text_write<<<text_blocks, kTextBlock, 0, e->compute>>>(ta[kind], e->d_text_len[kind].ptr, e->d_text_bsum[kind].ptr,
+                                                                         e->d_text[buf][kind].ptr, e->d_text_flags.ptr + kind * kMaxTextFlags,
                                                                          e->d_text_meta.ptr + 2 * kind + 1, kMaxTextFlags);
                 CU_TRY(cudaGetLastError());
-                res->launches += 3;
+                ++res->launches;
             }
             CU_TRY(cudaMemcpyAsync(e->h_text_meta[buf].ptr, e->d_text_meta.ptr, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->compute));
             CU_TRY(cudaEventRecord(e->ev_text[buf], e->compute));
-            // the sizes of the copies below are only known now; the batch before this one is still crossing PCIe /
-            // being written meanwhile
+            // the number of records to re-format is only known now; the batch before this one is still crossing
+            // PCIe / being written meanwhile
             CU_TRY(cudaEventSynchronize(e->ev_text[buf]));
             float tms = 0.f;
             CU_TRY(cudaEventElapsedTime(&tms, e->ev_computed[buf], e->ev_text[buf]));
@@ -677,15 +684,13 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
             CU_TRY(cudaEventRecord(e->ev_copy_begin[buf], e->copy));
             for (int kind = 0; kind < 2; ++kind) {
                 if (!n_text_slots[kind]) continue;
-                const unsigned long long total = e->h_text_meta[buf].ptr[2 * kind], nf = e->h_text_meta[buf].ptr[2 * kind + 1];
-                if (total > max_line[kind] * cap) return fail(CPPROB_SIS_EIO, "device text stage: line longer than its bound");
+                const unsigned long long total = pending[buf].text_bytes[kind], nf = e->h_text_meta[buf].ptr[2 * kind + 1];
                 if (nf > kMaxTextFlags) return fail(CPPROB_SIS_EIO, "device text stage: too many ambiguous records in one batch");
                 CU_TRY(cudaMemcpyAsync(e->h_text[buf][kind].ptr, e->d_text[buf][kind].ptr, total, cudaMemcpyDeviceToHost, e->copy));
                 if (nf) {
                     CU_TRY(cudaMemcpyAsync(e->h_text_flags.ptr + (2 * buf + kind) * kMaxTextFlags, e->d_text_flags.ptr + kind * kMaxTextFlags,
                                            nf * sizeof(text_flag), cudaMemcpyDeviceToHost, e->copy));
                 }
-                pending[buf].text_bytes[kind] = total;
                 pending[buf].text_flags[kind] = nf;
             }
             CU_TRY(cudaEventRecord(e->ev_copied[buf], e->copy));
@@ -1006,9 +1011,9 @@ void cpprob_sis_destroy(cpprob_sis_engine * e)
     if (e->copy) cudaStreamSynchronize(e->copy);
     e->d_obs.release(); e->d_pilot.release(); e->d_partials.release(); e->d_super.release(); e->d_warp_partials.release(); e->d_merged.release(); e->d_gather.release();
     e->d_counter.release(); e->d_int_extra.release(); e->h_merged.release(); e->h_pilot.release();
-    e->d_text_len.release(); e->d_text_bsum.release(); e->d_text_meta.release(); e->d_text_flags.release(); e->h_text_flags.release();
+    e->d_text_meta.release(); e->d_text_flags.release(); e->h_text_flags.release();
     for (int i = 0; i < 2; ++i) {
-        e->d_text_slots[i].release(); e->h_text_meta[i].release();
+        e->d_text_slots[i].release(); e->h_text_meta[i].release(); e->d_text_len[i].release(); e->d_text_bsum[i].release();
         for (int k = 0; k < 2; ++k) { e->d_text[i][k].release(); e->h_text[i][k].release(); }
         if (e->ev_text[i]) cudaEventDestroy(e->ev_text[i]);
         if (e->ev_copy_begin[i]) cudaEventDestroy(e->ev_copy_begin[i]);
