@@ -356,6 +356,12 @@ def test_single_process_multi_gpu_is_bit_identical():
         assert (st["sums"] == base["sums"]).all() and st["real_mean"][0] == base["real_mean"][0]
         st = capi.run_multi(engines, "hmm", G["obs_hmm_64"][:9], n // 8)
         assert (st["sums"] == base_hmm["sums"]).all()
+        # beyond 4096 chunks every GPU hands on super-chunk rows (cpprob_sis_plan_rows)
+        n_big = 5000 * capi.CHUNK + 777
+        with Engine(device=0, seed=77) as ref:
+            base_big = ref.run("gaussian_unknown_mean", [3.0, 4.0], n_big)
+        st = capi.run_multi(engines, "gaussian_unknown_mean", [3.0, 4.0], n_big)
+        assert (st["sums"] == base_big["sums"]).all()
     finally:
         for e in engines:
             e.close()
