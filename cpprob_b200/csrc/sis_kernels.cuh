@@ -239,6 +239,7 @@ struct null_policy {
 template<int NR, bool Lenient = false>
 struct reg_policy {
     static constexpr bool lenient_logpdf = Lenient;
+    static constexpr bool first_observe_stores = true;      // see particle::observe
     double v[NR];
     int k;
     __device__ __forceinline__ reg_policy() : k(0)
