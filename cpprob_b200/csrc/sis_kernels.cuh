@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(fused_block(NR), NR == 1 ? CPPROB_FUSED_MIN_BL
         unsigned n_neginf, n_nan;
         double s1[NR], s2[NR];
         // Fast pass: weights by exp_weight_tab, no per-particle special-case handling; only the
-        // smallest scaled exponent n = 256 k + j is tracked (one ALU instruction per particle).  A non-finite log_w needs no
+        // smallest scaled exponent n = 4096 k + j is tracked (one ALU instruction per particle).  A non-finite log_w needs no
         // tracking: -inf, +inf and NaN all come out of exp_weight_tab as NaN (inf - inf in its range
         // reduction) and poison the unit's weight sum.  If any particle of the unit had a non-finite
         // log_w or a weight below the normal range, the whole unit is recomputed by the careful pass.
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(fused_block(NR), NR == 1 ? CPPROB_FUSED_MIN_BL
             k_min = min(k_min, n);
             accumulate(lw, w, pol.v);
         });
-        if (__any_sync(0xffffffffu, k_min < -1021 * 256 || is_nan(s0))) {
+        if (__any_sync(0xffffffffu, k_min < dm::kExpTabMinN || is_nan(s0))) {
             reset();
             for_each_owned_particle(a.keys, zig_base, vt, a.first_particle + base, n_here, [&](philox_stream & rng, unsigned) {
                 reg_policy<NR> pol;

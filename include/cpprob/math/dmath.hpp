@@ -58,14 +58,15 @@ static __constant__ double k_ln2_lo = 1.90821492927058770002e-10;
 static __constant__ double k_log2e = 1.4426950408889634074;
 static __constant__ double k_round_magic = 6755399441055744.0;      // 2^52 + 2^51: x + magic rounds x to an integer
 static __constant__ double k_pi = 3.141592653589793238462643383279502884;
-// exp_weight_tab: 2^(j/256) (tools/gen_exp2_table.py), copied to shared memory by exp2_table_load()
+// exp_weight_tab: 2^(j/4096) (tools/gen_exp2_table.py), copied to shared memory by exp2_table_load()
 #include "cpprob/math/exp2_table.inc"
-static __device__ const double exp2_tab[256] = {CPPROB_EXP2_TABLE_ROWS};
-static __constant__ double k_log2e_256 = 1.4426950408889634074 * 256.0;
-static __constant__ double k_ln2_hi_256 = 6.93147180369123816490e-01 / 256.0;   // exact scalings of k_ln2_hi / k_ln2_lo
-static __constant__ double k_ln2_lo_256 = 1.90821492927058770002e-10 / 256.0;
+constexpr int kExpTabBits = 12;
+constexpr int kExpTabSize = 1 << kExpTabBits;
+static __device__ const double exp2_tab[kExpTabSize] = {CPPROB_EXP2_TABLE_ROWS};
+static __constant__ double k_log2e_tab = 1.4426950408889634074 * kExpTabSize;
+static __constant__ double k_ln2_hi_tab = 6.93147180369123816490e-01 / kExpTabSize;   // exact scalings of k_ln2_hi / k_ln2_lo
+static __constant__ double k_ln2_lo_tab = 1.90821492927058770002e-10 / kExpTabSize;
 static __constant__ double k_exp_c1 = 1.0 / 6.0;
-static __constant__ double k_exp_c2 = 1.0 / 24.0;
 }  // namespace tbl
 #endif
 
@@ -297,20 +298,22 @@ inline double fabs(double x) { return std::fabs(x); }
 #endif
 
 #if defined(__CUDACC__)
-// Table-assisted variant of exp_weight_unchecked for the fused kernel: exp(x) = 2^k 2^(j/256) e^r with
-// n = rint(256 x / ln 2) = 256 k + j and |r| <= ln2/512, so e^r - 1 = r + r^2 (1/2 + r/6 + r^2/24) to 2^-54.5:
-// 9 FP64-pipe instructions instead of 16, plus one shared-memory load (the FP64 pipe's two issue cycles per
-// instruction make that a good trade).  `tab` is what exp2_table_load() returned.
-// Same contract as exp_weight_unchecked: x finite and the result normal; the caller tracks the smallest n
-// (n >= -1021 * 256) and recomputes with exp_weight otherwise.  Non-finite x gives NaN.
-// The shared-memory copy stores each entry with its high word pre-decremented by j << 12, so that adding n << 12
-// (n = 256 k + j) lands on hi(T[j]) + (k << 20): the 2^k scaling costs one integer multiply-add on the loaded word.
+// Table-assisted variant of exp_weight_unchecked for the fused kernel: exp(x) = 2^k 2^(j/4096) e^r with
+// n = rint(4096 x / ln 2) = 4096 k + j and |r| <= ln2/8192, so e^r - 1 = r + r^2 (1/2 + r/6) to 2e-18:
+// 8 FP64-pipe instructions instead of 16, plus one shared-memory load from a 32 KB table (the FP64 pipe's two
+// issue cycles per instruction make that a good trade).  `tab` is what exp2_table_load()
+// returned.  Same contract as exp_weight_unchecked: x finite and the result normal; the caller tracks the smallest
+// n (n >= -1021 * 4096) and recomputes with exp_weight otherwise.  Non-finite x gives NaN.
+// The shared-memory copy stores each entry with its high word pre-decremented by j << 8, so that adding n << 8
+// (n = 4096 k + j) lands on hi(T[j]) + (k << 20): the 2^k scaling costs one integer multiply-add on the loaded word.
+constexpr unsigned kExpTabBytes = tbl::kExpTabSize * sizeof(double);
+
 __device__ __forceinline__ unsigned exp2_table_load()
 {
-    __shared__ double t[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    __shared__ double t[tbl::kExpTabSize];
+    for (int i = threadIdx.x; i < tbl::kExpTabSize; i += blockDim.x) {
         const double v = tbl::exp2_tab[i];
-        t[i] = __hiloint2double(__double2hiint(v) - (i << 12), __double2loint(v));
+        t[i] = __hiloint2double(__double2hiint(v) - (i << (20 - tbl::kExpTabBits)), __double2loint(v));
     }
     __syncthreads();
     unsigned base;
@@ -320,20 +323,21 @@ __device__ __forceinline__ unsigned exp2_table_load()
 __device__ __forceinline__ double exp_weight_tab(double x, unsigned tab, int & n_out)
 {
     const double magic = tbl::k_round_magic;
-    const double t = fma(x, tbl::k_log2e_256, magic);
+    const double t = fma(x, tbl::k_log2e_tab, magic);
     const int n = __double2loint(t);
     const double kf = t - magic;
-    double r = fma(kf, -tbl::k_ln2_hi_256, x);
-    r = fma(kf, -tbl::k_ln2_lo_256, r);
+    double r = fma(kf, -tbl::k_ln2_hi_tab, x);
+    r = fma(kf, -tbl::k_ln2_lo_tab, r);
     int t_lo, t_hi;
-    asm("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(t_lo), "=r"(t_hi) : "r"(tab + ((static_cast<unsigned>(n) << 3) & 0x7f8u)));
-    const double tj = __hiloint2double(t_hi + (n << 12), t_lo);          // 2^k 2^(j/256)
-    double q = fma(tbl::k_exp_c2, r, tbl::k_exp_c1);
-    q = fma(q, r, 0.5);
+    asm("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(t_lo), "=r"(t_hi)
+        : "r"(tab + ((static_cast<unsigned>(n) << 3) & ((tbl::kExpTabSize - 1u) << 3))));
+    const double tj = __hiloint2double(t_hi + (n << (20 - tbl::kExpTabBits)), t_lo);          // 2^k 2^(j/4096)
+    const double q = fma(r, tbl::k_exp_c1, 0.5);
     const double p = fma(r * r, q, r);
     n_out = n;
     return fma(tj, p, tj);
 }
+constexpr int kExpTabMinN = -1021 * tbl::kExpTabSize;     // below this the result is not a normal number
 #endif  // __CUDACC__
 
 }  // namespace dm

@@ -61,12 +61,12 @@ def test_exp_weight(engine):
 
 
 def test_exp_weight_tab(engine):
-    """The fused kernel's table-assisted exp (2^(j/256) table + degree-4 tail, 9 FP64 instructions): <= 2 ulp wherever
+    """The fused kernel's table-assisted exp (2^(j/4096) table + degree-3 tail, 8 FP64 instructions): <= 2 ulp wherever
     its contract holds (finite argument, normal result); NaN for non-finite arguments (which is what poisons a unit's
     weight sum and sends it to the careful pass)."""
     rng = np.random.default_rng(5)
     x = np.concatenate([rng.uniform(-707.0, 707.0, 200_000), rng.uniform(-40, 5, 200_000), rng.uniform(-1e-3, 1e-3, 1000),
-                        [0.0, -0.0, 1e-300, -1e-17, math.log(2) / 512, -math.log(2) / 512, math.log(2) / 256]])
+                        [0.0, -0.0, 1e-300, -1e-17, math.log(2) / 8192, -math.log(2) / 8192, math.log(2) / 4096]])
     got = engine.dmath(9, x)
     exact = np.array([float(mpmath.exp(mpmath.mpf(v))) for v in x[-25_000:]])
     assert ulp_err(got[-25_000:], exact).max() <= 2.0
