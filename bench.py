@@ -285,14 +285,14 @@ def run_ours(args):
             slots = budget["issue_slots"] * per_gpu / k_s / 1e12        # thread-level issue slots per second, in T/s
             line["roofline"] = {
                 "bound": "issue", "achieved": slots, "peak": peak_tflops, "unit": "Tslot/s", "frac": slots / peak_tflops,
-                "traffic": 176128,
+                "traffic": 206592,
                 "note": "dominant kernel k_sis_fused streams nothing from HBM and has no dense contraction: it is bound by the SM "
                         "sub-partitions' issue ports, where an FP64-pipe instruction holds the port for 2 cycles and any other for 1 "
                         "(cpprob_sis_probe_issue, DESIGN.md section 5).  unit = thread-level issue slots per second; peak = the DFMA "
                         "chain micro-benchmark of this run (one DFMA = 2 flop = 2 slots, so the figure equals its TFLOP/s; "
                         "MEASURED_PEAKS.json has no FP64 entry); achieved = (2 F + O) slots per particle from the SASS of the "
                         "particle loop x particles/s, slow ziggurat draws not counted.  traffic = dram bytes of one launch from "
-                        "ncu --set full (profiles/): 176 KB read (the shared-memory tables of 148 CTAs), 0 written",
+                        "ncu --set full (profiles/): 207 KB read (the shared-memory tables of 148 CTAs), 0 written",
                 "issue_slots_per_particle": budget["issue_slots"], "loop_instr_per_particle": budget["loop_instr"],
                 "fp64_pipe_instr_per_particle": budget["fp64_instr"], "flop_per_particle": budget["flop"],
                 "fp64_tflops": achieved, "fp64_frac_of_dfma_peak": achieved / peak_tflops,
