@@ -127,7 +127,7 @@ struct dmath_op {
         case 6: r = dm::log(x[i]); break;
         case 7: r = dm::cos_2pi(x[i]); break;
         case 8: r = dm::sin_2pi(x[i]); break;
-        case 9: { int n; r = dm::exp_weight_tab(x[i], zig_base, n); } break;
+        case 9: r = dm::exp_weight_tab(x[i], zig_base); break;
         case 5: {
             const double rad = dm::sqrt_pos(-2.0 * dm::log_unit(x[2 * i]));
             dm::sincos_2pi(x[2 * i + 1], s, c);

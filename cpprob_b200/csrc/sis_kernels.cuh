@@ -414,12 +414,12 @@ __global__ void __launch_bounds__(fused_block(NR), NR == 1 ? CPPROB_FUSED_MIN_BL
         unsigned n_neginf, n_nan;
         double s1[NR], s2[NR];
         // Fast pass: weights by exp_weight_tab, no per-particle special-case handling; only the
-        // smallest scaled exponent n = 4096 k + j is tracked (one ALU instruction per particle).  A non-finite log_w needs no
+        // lowest exp argument is tracked, on its high word (one ALU instruction per particle).  A non-finite log_w needs no
         // tracking: -inf, +inf and NaN all come out of exp_weight_tab as NaN (inf - inf in its range
         // reduction) and poison the unit's weight sum.  If any particle of the unit had a non-finite
         // log_w or a weight below the normal range, the whole unit is recomputed by the careful pass.
         // The choice depends only on the unit's own data, so results stay deterministic.
-        int k_min = 0;
+        unsigned arg_key = 0;
         auto reset = [&] {
             max_lw = dm::neg_inf(); s0 = 0.0; s00 = 0.0; n_neginf = 0; n_nan = 0;
 #pragma unroll
@@ -442,12 +442,12 @@ __global__ void __launch_bounds__(fused_block(NR), NR == 1 ? CPPROB_FUSED_MIN_BL
             particle<reg_policy<NR, true>> p(rng, pol);
             invoke_model(model, p, oc.data(), a.n_obs);
             const double lw = p.log_w();
-            int n;
-            const double w = dm::exp_weight_tab(lw - m_ref, exp_tab, n);
-            k_min = min(k_min, n);
+            const double arg = lw - m_ref;
+            const double w = dm::exp_weight_tab(arg, exp_tab);
+            arg_key = max(arg_key, dm::exp_arg_key(arg));
             accumulate(lw, w, pol.v);
         });
-        if (__any_sync(0xffffffffu, k_min < dm::kExpTabMinN || is_nan(s0))) {
+        if (__any_sync(0xffffffffu, arg_key > dm::kExpArgKeyLimit || is_nan(s0))) {
             reset();
             for_each_owned_particle(a.keys, zig_base, vt, a.first_particle + base, n_here, [&](philox_stream & rng, unsigned) {
                 reg_policy<NR> pol;

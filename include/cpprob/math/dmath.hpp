@@ -302,8 +302,10 @@ inline double fabs(double x) { return std::fabs(x); }
 // n = rint(4096 x / ln 2) = 4096 k + j and |r| <= ln2/8192, so e^r - 1 = r + r^2 (1/2 + r/6) to 2e-18:
 // 8 FP64-pipe instructions instead of 16, plus one shared-memory load from a 32 KB table (the FP64 pipe's two
 // issue cycles per instruction make that a good trade).  `tab` is what exp2_table_load()
-// returned.  Same contract as exp_weight_unchecked: x finite and the result normal; the caller tracks the smallest
-// n (n >= -1021 * 4096) and recomputes with exp_weight otherwise.  Non-finite x gives NaN.
+// returned.  Contract: x finite and the result a normal number, i.e. x >= -707 (and below the overflow range, which
+// the engine's re-base pass takes care of).  The caller checks that on the high word of x itself
+// (exp_arg_too_low) — not on n, which is only the low 32 bits of rint(4096 x / ln 2) and wraps for |x| > 3.6e5 —
+// and recomputes with exp_weight otherwise.  Non-finite x gives NaN.
 // The shared-memory copy stores each entry with its high word pre-decremented by j << 8, so that adding n << 8
 // (n = 4096 k + j) lands on hi(T[j]) + (k << 20): the 2^k scaling costs one integer multiply-add on the loaded word.
 constexpr unsigned kExpTabBytes = tbl::kExpTabSize * sizeof(double);
@@ -320,7 +322,7 @@ __device__ __forceinline__ unsigned exp2_table_load()
     asm volatile("{ .reg .u64 p; cvta.to.shared.u64 p, %1; cvt.u32.u64 %0, p; }" : "=r"(base) : "l"(t));
     return base;
 }
-__device__ __forceinline__ double exp_weight_tab(double x, unsigned tab, int & n_out)
+__device__ __forceinline__ double exp_weight_tab(double x, unsigned tab)
 {
     const double magic = tbl::k_round_magic;
     const double t = fma(x, tbl::k_log2e_tab, magic);
@@ -334,10 +336,13 @@ __device__ __forceinline__ double exp_weight_tab(double x, unsigned tab, int & n
     const double tj = __hiloint2double(t_hi + (n << (20 - tbl::kExpTabBits)), t_lo);          // 2^k 2^(j/4096)
     const double q = fma(r, tbl::k_exp_c1, 0.5);
     const double p = fma(r * r, q, r);
-    n_out = n;
     return fma(tj, p, tj);
 }
-constexpr int kExpTabMinN = -1021 * tbl::kExpTabSize;     // below this the result is not a normal number
+// Negative doubles order like their unsigned high words: the running maximum of exp_arg_key(x) over a set of
+// arguments exceeds kExpArgKeyLimit iff one of them is below -707 (or is -inf / a negative NaN), whatever its
+// magnitude.  Non-negative arguments have keys below 0x80000000 and never matter.
+__device__ __forceinline__ unsigned exp_arg_key(double x) { return static_cast<unsigned>(__double2hiint(x)); }
+constexpr unsigned kExpArgKeyLimit = 0xC0861800u;         // high word of -707.0
 #endif  // __CUDACC__
 
 }  // namespace dm

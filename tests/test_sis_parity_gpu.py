@@ -304,6 +304,21 @@ def test_all_weights_minus_infinity(engine):
     assert math.isnan(st["real_mean"][0])                                  # the reference yields NaN too (0/0)
 
 
+@pytest.mark.parametrize("x2", [4.0e3, 1.0e6, 3.0e6])
+def test_widely_spread_log_weights(engine, x2):
+    """Log-weights spread over up to 1e12 below the maximum: the fused kernel's table-assisted exp only holds for
+    arguments >= -707 and its integer exponent wraps for |argument| > 3.6e5, so the units must be caught on the
+    argument itself and redone by the careful pass; the row path (plain exp_weight) is the cross-check."""
+    n = 2_000_000
+    a = engine.run("gaussian_unknown_mean", [3.0, x2], n)
+    b = engine.run("gaussian_unknown_mean", [3.0, x2], n, force_rows=True)
+    assert a["n_nan"] == 0 and b["n_nan"] == 0
+    np.testing.assert_allclose(a["real_mean"], b["real_mean"], rtol=1e-12)
+    np.testing.assert_allclose(a["log_evidence"], b["log_evidence"], rtol=1e-12)
+    np.testing.assert_allclose(a["ess"], b["ess"], rtol=1e-9)
+    assert a["max_log_w"] == b["max_log_w"]
+
+
 def test_rebase_when_reference_is_far_off(engine):
     n = 4 * capi.CHUNK
     base = engine.run("gaussian_unknown_mean", [3.0, 4.0], n)
