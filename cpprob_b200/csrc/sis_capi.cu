@@ -335,6 +335,9 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     const int n_real = static_cast<int>(e->structure.n_real);
     const int n_int = static_cast<int>(e->structure.n_int);
     const shard_plan plan = plan_shard(n_total, rank, world);
+    if (plan.n_chunks_local > (1u << 28)) {      // the fused kernel counts (chunk, warp slot) units in 32 bits
+        return fail(CPPROB_SIS_EINVAL, "more than 2^43 (8.8e12) particles per GPU in one call");
+    }
     res->plan = plan;
     res->launches = 0;
     res->device_ms = 0.0;
