@@ -380,3 +380,67 @@ def test_single_process_multi_gpu_is_bit_identical():
     finally:
         for e in engines:
             e.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# C5: hmm with the 1000-step observation sequence (BASELINE.json configs[4])
+# ---------------------------------------------------------------------------------------------------
+OBS_1000 = G["obs_hmm_1000"]
+
+
+def test_c5_replay_of_reference_traces(engine, oracle, tmp_path):
+    prefix = str(tmp_path / "ref1000")
+    n = 1500
+    oracle.run("hmm", OBS_1000, n, prefix, how="fast", seed=41)
+    _, values, logw_file = oracle.parse_records(prefix + ".int", "int", 1000, n)
+    got = engine.replay("hmm", OBS_1000, int_rows=np.ascontiguousarray(values.T))
+    np.testing.assert_allclose(got, logw_file, rtol=REL)
+    exact = oracle.replay_logw("hmm", OBS_1000, values)
+    np.testing.assert_allclose(got, exact, rtol=REL)
+    assert np.abs(got - exact).max() <= 1e-13 * np.abs(exact).max()
+
+
+def test_c5_gpu_text_equals_host_text(tmp_path, monkeypatch):
+    import os
+    from cpprob_b200 import Engine
+    n = capi.CHUNK + 333                           # two batches of 6 KB lines
+    with Engine(seed=0xC5, max_batch=capi.CHUNK) as e:
+        monkeypatch.delenv("CPPROB_SIS_TEXT", raising=False)
+        e.infer_to_files("hmm", OBS_1000, n, str(tmp_path / "gpu"))
+        monkeypatch.setenv("CPPROB_SIS_TEXT", "host")
+        e.infer_to_files("hmm", OBS_1000, n, str(tmp_path / "host"))
+    a = open(tmp_path / "gpu.int", "rb").read()
+    assert a == open(tmp_path / "host.int", "rb").read()
+    lines = a.splitlines()
+    assert len(lines) == n and all(l.count(b"(0 ") == 1000 for l in lines[:20])
+    assert not os.path.exists(tmp_path / "gpu.real") and open(tmp_path / "gpu.ids").read() == "State\n"
+
+
+def test_c5_prefix_vs_forward_backward(engine):
+    obs = OBS_1000[:12]
+    n = 1 << 24
+    st = engine.run("hmm", obs, n)
+    post, le = analytic.hmm_forward_backward(obs)
+    tol = ess_tolerance(st, 1.0)
+    assert tol < 0.02
+    np.testing.assert_allclose(st["int_prob"], post, atol=tol)
+    assert abs(st["log_evidence"] - le) < 3 * tol
+
+
+def test_c5_all_addresses_have_estimators(engine):
+    """1000 (id, k) keys: every one gets a histogram that sums to 1, the first steps agree with forward-backward on the
+    WHOLE sequence (smoothing marginals) as far as the collapsed effective sample allows, and the emitting and the
+    estimator-only path give the same bits."""
+    n = 1 << 20
+    st = engine.run("hmm", OBS_1000, n)
+    assert st["n_int"] == 1000 and st["int_bins"] == 3 and st["int_lo"] == 0 and st["n_particles"] == n
+    assert st["int_prob"].shape == (1000, 3)
+    np.testing.assert_allclose(st["int_prob"].sum(1), 1.0, rtol=1e-12)
+    assert ((st["int_map"] >= 0) & (st["int_map"] <= 2)).all()
+    assert np.isfinite(st["log_evidence"]) and st["n_neg_inf"] == 0 and 1.0 <= st["ess"] <= n
+    _, le = analytic.hmm_forward_backward(OBS_1000)
+    # importance sampling from the prior over 1000 steps: the estimate of the evidence is dominated by the best particle
+    # and biased low; it cannot exceed the truth by more than noise
+    assert st["log_evidence"] < le + 5.0
+    rows = engine.run("hmm", OBS_1000, n, force_rows=True)
+    assert (rows["sums"] == st["sums"]).all()
