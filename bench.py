@@ -45,6 +45,26 @@ def sass_budget():
             "issue_slots": (hot + b["fp64"]) / per}
 
 
+def measured_peaks():
+    """HBM copy bandwidth the rooflines are quoted against: MEASURED_PEAKS.json (driver-written) or the profiling
+    recipe's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def kernel_costs():
+    """Per-kernel figures taken from the committed ncu captures (profiles/kernel_costs.json, written by
+    tools/summarise_profiles.py): DRAM bytes and executed instructions per particle.  Absent entries read as None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "kernel_costs.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 # ---------------------------------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------------------------------
@@ -299,11 +319,110 @@ def run_ours(args):
                 "fp64_pipe_util": budget["fp64_instr"] * per_gpu / k_s / (peak_tflops * 1e12 / 2.0),
                 "dfma_peak_sm_mhz_equiv": est_mhz,
             }
+            line["roofline"]["traffic"] = kernel_costs().get("C2", {}).get("dram_bytes_per_launch", line["roofline"]["traffic"])
             line["cpu_baseline"] = cpu_baseline(args)
+            if not args.no_configs:
+                line["configs"] = secondary_configs(engine, args)
+                cf = line["configs"]["C2_files"]
+                cb = line["cpu_baseline"]
+                # the three ratios against the CPU arm of this run (1 thread; the driver computes the all-core ones itself)
+                line["e2e_files"] = {"value": cf["value"], "unit": "particles/s", "particles": cf["particles"],
+                                     "what": "cpprob_sis_infer_to_files, wall clock, files complete: like for like with the reference's inference()"}
+                line["vs_cpu_1thread"] = {"files_vs_faithful": cf["value"] / cb["value"], "files_vs_buffered": cf["value"] / cb["fast_flavour_value"],
+                                          "estimators_only_vs_faithful": line["e2e"]["value"] / cb["value"],
+                                          "note": "faithful = 3 file appends per trace as the reference; buffered = one ofstream per file kept open; "
+                                                  "estimators only = cpprob_sis_run (CPPROB_SIS_EMIT=none), which writes no posterior file"}
         emit(line)
     engine.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def timed_runs(fn, reps=3, warm=1):
+    """best-of-`reps` of fn() -> (stats, wall seconds); the engine's own CUDA events give stats['device_ms']"""
+    best = None
+    for i in range(warm + reps):
+        t0 = time.perf_counter()
+        st = fn()
+        wall = time.perf_counter() - t0
+        if i >= warm and (best is None or st["device_ms"] < best[0]["device_ms"]):
+            best = (st, wall)
+    return best
+
+
+def secondary_configs(engine, args):
+    """BASELINE.json configs[2..4] and the file-emitting form of configs[1], on one GPU.  Each entry: particles/s from the
+    engine's CUDA events around its particle + reduction kernels (best of 3 after a warm-up; every run regenerates
+    all particles, and the row buffers of C3-C5 are far larger than L2), the same through the public call with host
+    buffers (wall clock), and the roofline of the path that ran."""
+    import analytic
+    g = analytic.golden()
+    hbm, hbm_src = measured_peaks()
+    costs = kernel_costs()
+    out = {}
+
+    def entry(label, model, obs, n, note):
+        st, wall = timed_runs(lambda: engine.run(model, obs, n))
+        k_s = st["device_ms"] * 1e-3
+        row_bytes = 8 * st["n_real"] + 4 * st["n_int"] + 16                  # SoA rows + log_w + w, written then read once
+        e = {"workload": note, "particles": n, "value": n / k_s, "unit": "particles/s", "device_ms": st["device_ms"],
+             "e2e_value": n / wall, "launches": int(st["kernel_launches"]), "passes": int(st["passes"]), "path": st.get("path", "rows"),
+             "steps_per_s": n * max(st["n_real"], st["n_int"]) / k_s, "ess": st["ess"], "log_evidence": st["log_evidence"]}
+        if e["path"] == "rows":
+            algo = 2.0 * row_bytes * n                                       # each row element written once, read once
+            e["roofline"] = {"bound": "hbm", "achieved": algo / k_s / 1e9, "peak": hbm, "unit": "GB/s", "frac": algo / k_s / 1e9 / hbm,
+                             "peak_source": hbm_src, "algorithmic_bytes_per_particle": 2 * row_bytes,
+                             "traffic": costs.get(label, {}).get("dram_bytes_per_particle")}
+        else:
+            c = costs.get(label, {})
+            slots = c.get("issue_slots_per_particle")
+            peak_t, _ = engine.dfma_peak()
+            e["roofline"] = {"bound": "issue", "achieved": None if slots is None else slots * n / k_s / 1e12, "peak": peak_t, "unit": "Tslot/s",
+                             "frac": None if slots is None else slots * n / k_s / 1e12 / peak_t,
+                             "issue_slots_per_particle": slots, "traffic": c.get("dram_bytes_per_particle"),
+                             "note": "no trace row touches HBM on this path; slots per particle from the committed ncu capture "
+                                     "(executed warp instructions + FP64-pipe instructions, per particle), peak = DFMA probe of this run"}
+        out[label] = e
+        return e
+
+    entry("C3", "linear_gaussian_1d", g["obs_linear_gaussian_32"], args.c3_particles,
+          "linear_gaussian_1d, 32 synthetic observations (BASELINE.json configs[2]), per-(id,k) mean/variance")
+    entry("C4", "hmm", g["obs_hmm_64"], args.c4_particles,
+          "hmm, 3 states, 64-step synthetic observation sequence (configs[3]), per-address histograms / MAP")
+    entry("C5_estimators", "hmm", g["obs_hmm_1000"], args.c5_particles,
+          "hmm, 1000-step sequence (configs[4]), estimators only (no record leaves the GPU)")
+
+    # configs[4] proper and the like-for-like form of configs[1]: every record written to the reference's posterior file
+    def files(label, model, obs, n, note):
+        d = scratch_dir()
+        with tempfile.TemporaryDirectory(dir=d) as tmp:
+            engine.infer_to_files(model, obs, max(n // 8, 1), os.path.join(tmp, "warm"))      # pinned buffers, page cache
+            prefix = os.path.join(tmp, "post")
+            t0 = time.perf_counter()
+            st = engine.infer_to_files(model, obs, n, prefix)
+            wall = time.perf_counter() - t0
+            ts = engine.text_stage_stats()
+            size = sum(os.path.getsize(prefix + ext) for ext in (".real", ".int") if os.path.exists(prefix + ext))
+        row_bytes = 8 * st["n_real"] + 4 * st["n_int"] + 16
+        k_s = st["device_ms"] * 1e-3
+        out[label] = {
+            "workload": note, "particles": n, "value": n / wall, "unit": "records/s (wall, files complete)", "wall_s": wall,
+            "text_bytes": size, "text_GBps_wall": size / wall / 1e9, "particle_kernels_ms": st["device_ms"],
+            "stages": {"text_kernels_ms": ts["kernel_ms"], "text_kernels_GBps": ts["bytes"] / max(ts["kernel_ms"], 1e-9) / 1e6,
+                       "d2h_ms": ts["copy_ms"], "d2h_GBps": ts["bytes"] / max(ts["copy_ms"], 1e-9) / 1e6,
+                       "file_write_s": ts["write_s"], "file_write_GBps": ts["bytes"] / max(ts["write_s"], 1e-9) / 1e9, "fixups": ts["fixups"]},
+            "roofline": {"bound": "hbm", "achieved": row_bytes * n / k_s / 1e9, "peak": hbm, "unit": "GB/s", "frac": row_bytes * n / k_s / 1e9 / hbm,
+                         "peak_source": hbm_src, "algorithmic_bytes_per_particle": row_bytes,
+                         "note": "device stage only (rows written once by k_sis_rows + estimator kernels); the end-to-end rate is "
+                                 "bounded by the file append on " + d, "traffic": costs.get(label, {}).get("dram_bytes_per_particle")},
+            "files_on": d}
+
+    files("C5", "hmm", g["obs_hmm_1000"], args.c5_file_particles,
+          "hmm, 1000-step sequence, FULL trace emission to <prefix>.int in the reference's text format (configs[4])")
+    files("C2_files", MODEL, OBS, args.file_particles,
+          "gaussian_unknown_mean x=(3,4) through cpprob_sis_infer_to_files: every record appended to <prefix>.real, .ids written - "
+          "the same work as the reference's cpprob::inference(..., outfile)")
+    return out
 
 
 def cpu_baseline(args):
@@ -345,6 +464,12 @@ def main():
     ap.add_argument("--particles", type=int, default=1_000_000_000, help="particles per GPU per step")
     ap.add_argument("--cpu-particles", type=int, default=1_000_000, help="particles of the cpu_baseline sample")
     ap.add_argument("--ref-particles", type=int, default=50_000, help="particles per process per step of --impl reference")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C3/C4/C5/file-emission block")
+    ap.add_argument("--c3-particles", type=int, default=100_000_000)
+    ap.add_argument("--c4-particles", type=int, default=100_000_000)
+    ap.add_argument("--c5-particles", type=int, default=4_000_000)
+    ap.add_argument("--c5-file-particles", type=int, default=1_000_000)
+    ap.add_argument("--file-particles", type=int, default=20_000_000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("CPPROB_SIS_LIB") or os.path.join(_HERE, "lib", "libcp
 
 EMIT_NONE, EMIT_ALL = 0, 1
 DIST = {"normal": 0, "uniform_real": 1, "uniform_smallint": 2, "discrete": 3, "poisson": 4, "gamma": 5, "beta": 6}
+PATHS = ("fused", "staged", "rows")      # cpprob_sis_stats.path (CPPROB_SIS_PATH_*)
 BASE_COLS = 8
 CHUNK = 1 << 15
 
@@ -52,7 +53,7 @@ class Stats(C.Structure):
                 ("int_lo", C.c_longlong), ("int_bins", C.c_int),
                 ("int_prob", C.POINTER(C.c_double)), ("int_map", C.POINTER(C.c_longlong)),
                 ("n_cols", C.c_int), ("sums", C.POINTER(C.c_double)),
-                ("device_ms", C.c_double), ("kernel_launches", C.c_uint64), ("passes", C.c_int)]
+                ("device_ms", C.c_double), ("kernel_launches", C.c_uint64), ("passes", C.c_int), ("path", C.c_int)]
 
 
 class Block(C.Structure):
@@ -164,6 +165,7 @@ def stats_to_dict(st, structure=None):
     d = {k: getattr(st, k) for k in ("n_particles", "n_neg_inf", "n_nan", "m_ref", "max_log_w", "log_sum_exp",
                                       "log_evidence", "ess", "n_real", "n_int", "int_lo", "int_bins", "n_cols",
                                       "device_ms", "kernel_launches", "passes")}
+    d["path"] = PATHS[st.path] if 0 <= st.path < len(PATHS) else str(st.path)
     d["real_mean"] = np.array([st.real_mean[i] for i in range(st.n_real)])
     d["real_var"] = np.array([st.real_var[i] for i in range(st.n_real)])
     d["int_prob"] = np.array([st.int_prob[i] for i in range(st.n_int * st.int_bins)]).reshape(st.n_int, st.int_bins or 1)[:, :st.int_bins]

@@ -15,6 +15,7 @@
 
 #include "cpprob_sis.h"
 #include "sis_kernels.cuh"
+#include "staged_kernels.cuh"
 
 extern "C" {
 struct cpprob_sis_model_vtable {
@@ -26,12 +27,16 @@ struct cpprob_sis_model_vtable {
     int (*probe)(const double * obs, int n_obs, unsigned long long seed, void * out);
     cudaError_t (*launch_pilot)(cudaStream_t s, const cpprob::philox_keys * keys, const double * obs, int n_obs, int n_pilot, double * out);
     // nr = register-staged real predict slots (1, 2 or 4)
-    cudaError_t (*launch_fused)(cudaStream_t s, int grid, int nr, const cpprob::engine::run_args * a);
-    cudaError_t (*launch_rows)(cudaStream_t s, int grid, const cpprob::engine::run_args * a);
+    cudaError_t (*launch_fused)(cudaStream_t s, int grid, int nr, cpprob::engine::run_args * a);
+    cudaError_t (*launch_rows)(cudaStream_t s, int grid, cpprob::engine::run_args * a);
     cudaError_t (*launch_replay)(cudaStream_t s, int grid, const double * obs, int n_obs, const double * real_rows,
                                  const int * int_rows, unsigned long long stride, unsigned long long n, double * logw_out);
     // resident CTAs per SM: which = 0 fused(nr=1), 1 fused(nr=2), 2 fused(nr=4), 3 rows
-    int (*occupancy)(int which);
+    int (*occupancy)(int which, int n_obs);
+    // staged kernel (staged_kernels.cuh): warps per CTA its staging areas allow for this trace structure (0: does not
+    // fit, use the row path), and the launch (one CTA of `warps` warps per grid entry; a->n_real/n_int/hist_* set)
+    int (*staged_warps)(int n_obs, int n_real, int n_int, int bins);
+    cudaError_t (*launch_staged)(cudaStream_t s, int grid, int warps, cpprob::engine::run_args * a);
 };
 }
 
@@ -40,8 +45,20 @@ namespace engine {
 
 // Dynamic shared memory of a model's kernels: the ziggurat table, if the model draws normals.  More than the 48 KB a
 // kernel may use without asking, hence the attribute (set at every launch: it is per device, and cheap).
+// plus the model's per-launch table (particle.hpp "Per-launch model tables"), when it fits kScratchBudget
+constexpr unsigned kScratchBudget = 96u * 1024u;
 template<class Model>
-constexpr unsigned model_smem() { return model_draws_normals<Model>::value ? zig::kSharedBytes : 0u; }
+inline int model_scratch_doubles(int n_obs)
+{
+    if (!model_scratch<Model>::present) return 0;
+    const int n = model_scratch<Model>::doubles(n_obs);
+    return (n > 0 && static_cast<unsigned>(n) * sizeof(double) <= kScratchBudget) ? ((n + 1) & ~1) : 0;     // even: keeps 16-byte alignment
+}
+template<class Model>
+inline unsigned model_smem(int n_obs)
+{
+    return zig_smem_doubles<Model>() * static_cast<unsigned>(sizeof(double)) + static_cast<unsigned>(model_scratch_doubles<Model>(n_obs)) * static_cast<unsigned>(sizeof(double));
+}
 
 template<class Kernel>
 inline cudaError_t allow_smem(Kernel k, unsigned bytes)
@@ -58,13 +75,14 @@ struct model_launchers {
     }
     static cudaError_t pilot(cudaStream_t s, const philox_keys * keys, const double * obs, int n_obs, int n_pilot, double * out)
     {
-        if (cudaError_t err = allow_smem(k_pilot<Model>, model_smem<Model>())) return err;
-        k_pilot<Model><<<(n_pilot + 511) / 512, kBlock, model_smem<Model>(), s>>>(*keys, obs, n_obs, n_pilot, out);
+        if (cudaError_t err = allow_smem(k_pilot<Model>, model_smem<Model>(n_obs))) return err;
+        k_pilot<Model><<<(n_pilot + 511) / 512, kBlock, model_smem<Model>(n_obs), s>>>(*keys, obs, n_obs, n_pilot, model_scratch_doubles<Model>(n_obs), out);
         return cudaGetLastError();
     }
-    static cudaError_t fused(cudaStream_t s, int grid, int nr, const run_args * a)
+    static cudaError_t fused(cudaStream_t s, int grid, int nr, run_args * a)
     {
-        constexpr unsigned smem = model_smem<Model>();
+        const unsigned smem = model_smem<Model>(a->n_obs);
+        a->scratch_doubles = model_scratch_doubles<Model>(a->n_obs);
         if (nr <= 1) {
             if (cudaError_t err = allow_smem(k_sis_fused<Model, 1>, smem)) return err;
             k_sis_fused<Model, 1><<<grid, fused_block(1), smem, s>>>(*a);
@@ -77,23 +95,46 @@ struct model_launchers {
         }
         return cudaGetLastError();
     }
-    static cudaError_t rows(cudaStream_t s, int grid, const run_args * a)
+    static cudaError_t rows(cudaStream_t s, int grid, run_args * a)
     {
-        if (cudaError_t err = allow_smem(k_sis_rows<Model>, model_smem<Model>())) return err;
-        k_sis_rows<Model><<<grid, kBlock, model_smem<Model>(), s>>>(*a);
+        a->scratch_doubles = model_scratch_doubles<Model>(a->n_obs);
+        if (cudaError_t err = allow_smem(k_sis_rows<Model>, model_smem<Model>(a->n_obs))) return err;
+        k_sis_rows<Model><<<grid, kBlock, model_smem<Model>(a->n_obs), s>>>(*a);
         return cudaGetLastError();
     }
     static cudaError_t replay(cudaStream_t s, int grid, const double * obs, int n_obs, const double * real_rows,
                               const int * int_rows, unsigned long long stride, unsigned long long n, double * logw_out)
     {
-        k_replay<Model><<<grid, kBlock, 0, s>>>(obs, n_obs, real_rows, int_rows, stride, n, logw_out);
+        // only the model table: replayed traces draw nothing, so the ziggurat part stays unused (but keeps its offset)
+        if (cudaError_t err = allow_smem(k_replay<Model>, model_smem<Model>(n_obs))) return err;
+        k_replay<Model><<<grid, kBlock, model_smem<Model>(n_obs), s>>>(obs, n_obs, model_scratch_doubles<Model>(n_obs), real_rows, int_rows, stride, n, logw_out);
         return cudaGetLastError();
     }
-    static int occupancy(int which)
+    // warps per CTA of the staged kernel: as many as the per-warp staging areas leave room for next to the tables
+    static int staged_warps(int n_obs, int n_real, int n_int, int bins)
+    {
+        if (bins > kStagedMaxBins || (n_int > 0 && bins <= 0)) return 0;
+        const unsigned fixed = model_smem<Model>(n_obs);
+        const unsigned per_warp = make_stage_layout(n_real, n_int, bins).bytes;
+        if (fixed + 4u * per_warp > kSmemBudget) return 0;
+        const unsigned w = (kSmemBudget - fixed) / per_warp;
+        constexpr unsigned max_warps = staged_threads<Model>() / 32u;
+        return static_cast<int>(w > max_warps ? max_warps : w);
+    }
+    static cudaError_t staged(cudaStream_t s, int grid, int warps, run_args * a)
+    {
+        a->scratch_doubles = model_scratch_doubles<Model>(a->n_obs);
+        a->stage_base = model_smem<Model>(a->n_obs);
+        const unsigned smem = a->stage_base + static_cast<unsigned>(warps) * make_stage_layout(a->n_real, a->n_int, a->hist_bins).bytes;
+        if (cudaError_t err = allow_smem(k_sis_staged<Model>, smem)) return err;
+        k_sis_staged<Model><<<grid, warps * 32, smem, s>>>(*a);
+        return cudaGetLastError();
+    }
+    static int occupancy(int which, int n_obs)
     {
         int n = 0;
         cudaError_t err;
-        constexpr unsigned smem = model_smem<Model>();
+        const unsigned smem = model_smem<Model>(n_obs);
         switch (which) {
         case 0:
             allow_smem(k_sis_fused<Model, 1>, smem);
@@ -118,7 +159,7 @@ struct model_launchers {
     {
         static const cpprob_sis_model_vtable vt = {
             CPPROB_SIS_ABI_VERSION, Model::name(), Model::n_scalar_obs, Model::replayable ? 1 : 0,
-            &probe, &pilot, &fused, &rows, &replay, &occupancy};
+            &probe, &pilot, &fused, &rows, &replay, &occupancy, &staged_warps, &staged};
         return &vt;
     }
 };

@@ -7,6 +7,7 @@
 #define CPPROB_B200_REDUCE_KERNELS_CUH
 
 #include "sis_kernels.cuh"
+#include "staged_kernels.cuh"
 
 namespace cpprob {
 namespace engine {
@@ -18,122 +19,130 @@ __global__ void __launch_bounds__(kBlock) k_init_int_extra(int_extra * __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4a k_row_moments: S1 = sum w x, S2 = sum w x^2 for kMomTile real rows of one chunk.
-// 1-D grid of n_sub_chunks * ceil(n_real / kMomTile) CTAs, tile index fastest.  Each row element is
-// read once (coalesced 8 B/lane); w is re-read once per tile from L2 (a sub-chunk of w is 32 KB).
-// Output: partials[chunk][kBaseCols + 2*row + {0,1}].
+// K4a k_rows_moments: S1 = sum w x, S2 = sum w x^2 for 32 real rows of one sub-chunk, in the canonical order of
+// staged_kernels.cuh.  1-D grid of n_sub_chunks * ceil(n_real / 32) CTAs, row group fastest.  Warp s of the CTA is warp
+// slot s: for each of its 16 rounds it loads the round's 32 particles of the group's 32 rows (32 coalesced 256-byte
+// loads in flight per warp) into its staging area, and lane q adds the round to the sums of row q with the same
+// moments_round the staged kernel uses.  The 8 slots are then added in slot order.  Each row element is read from
+// HBM once; w comes from L2 after its first read.
+// Output: partials[sub_chunk][kBaseCols + 2*row + {0,1}].
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_row_moments(const double * __restrict__ real_rows, const double * __restrict__ w,
-                                                        unsigned long long stride, unsigned long long n_particles,
-                                                        int n_real, double * __restrict__ partials, int n_cols)
+constexpr unsigned kRowsMomentsSmem = kWarps * (32u * kStageRealStride + 32u) * sizeof(double) + kWarps * 64u * sizeof(double);
+
+__global__ void __launch_bounds__(kBlock) k_rows_moments(const double * __restrict__ real_rows, const double * __restrict__ w,
+                                                         unsigned long long stride, unsigned long long n_particles,
+                                                         int n_real, double * __restrict__ partials, int n_cols)
 {
-    __shared__ double smem[kWarps * 2 * kMomTile];
-    const unsigned n_tiles = static_cast<unsigned>((n_real + kMomTile - 1) / kMomTile);
-    const unsigned c = blockIdx.x / n_tiles;
-    const int row0 = static_cast<int>(blockIdx.x % n_tiles) * kMomTile;
+    extern __shared__ double cpprob_zig_shared[];
+    const unsigned lane = threadIdx.x & 31u, slot = threadIdx.x >> 5;
+    double * const stage = cpprob_zig_shared + slot * (32u * kStageRealStride + 32u);
+    double * const wst = stage + 32u * kStageRealStride;
+    double * const slot_sums = cpprob_zig_shared + kWarps * (32u * kStageRealStride + 32u);      // [kWarps][32][2]
+    const unsigned n_groups = static_cast<unsigned>((n_real + 31) / 32);
+    const unsigned c = blockIdx.x / n_groups;
+    const int row0 = static_cast<int>(blockIdx.x % n_groups) * 32;
     const unsigned long long base = static_cast<unsigned long long>(c) * kSubChunk;
     const unsigned long long left = n_particles - base;
     const unsigned n_here = left < kSubChunk ? static_cast<unsigned>(left) : kSubChunk;
+    const int rows_here = min(32, n_real - row0);
 
-    double acc[2 * kMomTile];
-#pragma unroll
-    for (int j = 0; j < 2 * kMomTile; ++j) acc[j] = 0.0;
-
-    if (n_here == kSubChunk && row0 + kMomTile <= n_real) {
-        // whole sub-chunk, whole tile: compile-time offsets, 8 row loads in flight per element
-        constexpr int kPer = kSubChunk / kBlock;
-        const double * __restrict__ q = w + base + threadIdx.x;
-        const double * __restrict__ p = real_rows + static_cast<unsigned long long>(row0) * stride + base + threadIdx.x;
-#pragma unroll 4
-        for (int k = 0; k < kPer; ++k) {
-            const double wi = q[k * kBlock];
-            double x[kMomTile];
-#pragma unroll
-            for (int j = 0; j < kMomTile; ++j) x[j] = __ldcs(p + static_cast<unsigned long long>(j) * stride + k * kBlock);
-#pragma unroll
-            for (int j = 0; j < kMomTile; ++j) {
-                const double wx = wi * x[j];
-                acc[2 * j] += wx;
-                acc[2 * j + 1] = fma(wx, x[j], acc[2 * j + 1]);
+    double s1 = 0.0, s2 = 0.0;
+    for (unsigned round = 0; round < kSubChunk / kBlock; ++round) {
+        const unsigned i0 = round * kBlock + slot * 32u;              // first particle of this slot's round within the sub-chunk
+        if (i0 >= n_here) break;
+        const bool valid = i0 + lane < n_here;
+        const unsigned long long colidx = base + i0 + lane;
+        wst[lane] = valid ? w[colidx] : 0.0;
+        const double * __restrict__ src = real_rows + static_cast<unsigned long long>(row0) * stride + colidx;
+        if (valid && rows_here == 32) {
+#pragma unroll 16
+            for (int q = 0; q < 32; ++q) stage[q * kStageRealStride + lane] = __ldcs(src + static_cast<unsigned long long>(q) * stride);
+        } else {
+            for (int q = 0; q < 32; ++q) {
+                stage[q * kStageRealStride + lane] = (valid && q < rows_here) ? __ldcs(src + static_cast<unsigned long long>(q) * stride) : 0.0;
             }
         }
-    } else {
-        for (unsigned i = threadIdx.x; i < n_here; i += kBlock) {
-            const unsigned long long colidx = base + i;
-            const double wi = w[colidx];
-#pragma unroll
-            for (int j = 0; j < kMomTile; ++j) {
-                if (row0 + j < n_real) {
-                    const double x = __ldcs(real_rows + static_cast<unsigned long long>(row0 + j) * stride + colidx);
-                    const double wx = wi * x;
-                    acc[2 * j] += wx;
-                    acc[2 * j + 1] = fma(wx, x, acc[2 * j + 1]);
-                }
-            }
-        }
+        __syncwarp();
+        moments_round(stage + lane * kStageRealStride, wst, s1, s2);
+        __syncwarp();
     }
-    const double r = block_reduce<2 * kMomTile>(acc, 0ull, smem);
-    if (threadIdx.x < 2 * kMomTile && row0 + static_cast<int>(threadIdx.x >> 1) < n_real) {
+    slot_sums[(slot * 32u + lane) * 2u] = s1;
+    slot_sums[(slot * 32u + lane) * 2u + 1u] = s2;
+    __syncthreads();
+    if (threadIdx.x < 64u && static_cast<int>(threadIdx.x >> 1) < rows_here) {
+        double r = slot_sums[threadIdx.x];
+#pragma unroll
+        for (unsigned sl = 1; sl < kWarps; ++sl) r = __dadd_rn(r, slot_sums[sl * 64u + threadIdx.x]);     // slots in slot order
         partials[static_cast<size_t>(c) * n_cols + kBaseCols + 2 * row0 + threadIdx.x] = r;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4b k_row_hist<V>: weighted histogram sum_i w_i [x_i == lo + b], b < V, for one int row of one
-// sub-chunk.  1-D grid of n_sub_chunks * n_int CTAs with the row index fastest, so the CTAs that share
-// a sub-chunk's weights run together and w (32 KB) is served by L2: DRAM sees each int once.
-// V <= 8 bins live in registers; wider windows are covered by several launches with shifted `lo`
-// (bin_offset selects the output columns).
+// K4b k_rows_hist<V>: weighted histogram sum_i w_i [x_i == lo + b], b < V, for 32 int rows of one sub-chunk, canonical
+// order as above (hist_round of staged_kernels.cuh).  1-D grid of n_sub_chunks * ceil(n_int / 32) CTAs.  V <= 8 bins live
+// in registers; wider windows are covered by several launches with shifted `lo` (bin_offset selects the output
+// columns).  States are staged as bytes relative to `lo`; anything outside [0, 255) is staged as 255 and matches no bin.
 // Output: partials[sub_chunk][hist_col0 + row*hist_bins + bin_offset + b].
 // ------------------------------------------------------------------------------------------------
 template<int V>
-__global__ void __launch_bounds__(kBlock) k_row_hist(const int * __restrict__ int_rows, const double * __restrict__ w,
-                                                     unsigned long long stride, unsigned long long n_particles, int n_int,
-                                                     long long lo, int bin_offset, int hist_bins, int hist_col0,
-                                                     double * __restrict__ partials, int n_cols)
+__global__ void __launch_bounds__(kBlock) k_rows_hist(const int * __restrict__ int_rows, const double * __restrict__ w,
+                                                      unsigned long long stride, unsigned long long n_particles, int n_int,
+                                                      long long lo, int bin_offset, int hist_bins, int hist_col0,
+                                                      double * __restrict__ partials, int n_cols)
 {
-    __shared__ double smem[kWarps * V];
-    const unsigned c = blockIdx.x / static_cast<unsigned>(n_int);
-    const int row = static_cast<int>(blockIdx.x % static_cast<unsigned>(n_int));
+    __shared__ __align__(16) unsigned char stage_all[kWarps][32 * kStageIntStride];
+    __shared__ __align__(16) double wst_all[kWarps][32];
+    __shared__ double slot_sums[kWarps][32][V];
+    const unsigned lane = threadIdx.x & 31u, slot = threadIdx.x >> 5;
+    unsigned char * const stage = stage_all[slot];
+    double * const wst = wst_all[slot];
+    const unsigned n_groups = static_cast<unsigned>((n_int + 31) / 32);
+    const unsigned c = blockIdx.x / n_groups;
+    const int row0 = static_cast<int>(blockIdx.x % n_groups) * 32;
     const unsigned long long base = static_cast<unsigned long long>(c) * kSubChunk;
     const unsigned long long left = n_particles - base;
     const unsigned n_here = left < kSubChunk ? static_cast<unsigned>(left) : kSubChunk;
-    const int * __restrict__ src = int_rows + static_cast<unsigned long long>(row) * stride + base;
-    const double * __restrict__ wsrc = w + base;
-
+    const int rows_here = min(32, n_int - row0);
     const unsigned lo32 = static_cast<unsigned>(static_cast<int>(lo));
+
     double h[V];
 #pragma unroll
     for (int b = 0; b < V; ++b) h[b] = 0.0;
-    if (n_here == kSubChunk) {
-        // whole sub-chunk: 16 elements per thread at compile-time offsets (no per-element address arithmetic),
-        // all loads issued up front
-        constexpr int kPer = kSubChunk / kBlock;
-        const int * __restrict__ p = src + threadIdx.x;
-        const double * __restrict__ q = wsrc + threadIdx.x;
-        unsigned x[kPer];
-        double wi[kPer];
-#pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-            x[k] = static_cast<unsigned>(__ldcs(p + k * kBlock)) - lo32;
-            wi[k] = q[k * kBlock];
+    for (unsigned round = 0; round < kSubChunk / kBlock; ++round) {
+        const unsigned i0 = round * kBlock + slot * 32u;
+        if (i0 >= n_here) break;
+        const bool valid = i0 + lane < n_here;
+        const unsigned long long colidx = base + i0 + lane;
+        wst[lane] = valid ? w[colidx] : 0.0;
+        const int * __restrict__ src = int_rows + static_cast<unsigned long long>(row0) * stride + colidx;
+        if (valid && rows_here == 32) {
+#pragma unroll 16
+            for (int q = 0; q < 32; ++q) {
+                const unsigned x = static_cast<unsigned>(__ldcs(src + static_cast<unsigned long long>(q) * stride)) - lo32;
+                stage[q * kStageIntStride + lane] = static_cast<unsigned char>(x < 255u ? x : 255u);
+            }
+        } else {
+            for (int q = 0; q < 32; ++q) {
+                unsigned x = 255u;
+                if (valid && q < rows_here) x = static_cast<unsigned>(__ldcs(src + static_cast<unsigned long long>(q) * stride)) - lo32;
+                stage[q * kStageIntStride + lane] = static_cast<unsigned char>(x < 255u ? x : 255u);
+            }
         }
-#pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-#pragma unroll
-            for (int b = 0; b < V; ++b) h[b] += (x[k] == static_cast<unsigned>(b)) ? wi[k] : 0.0;   // select, not a branch
-        }
-    } else {
-        for (unsigned i = threadIdx.x; i < n_here; i += kBlock) {
-            const unsigned x = static_cast<unsigned>(__ldcs(src + i)) - lo32;
-            const double wi = wsrc[i];
-#pragma unroll
-            for (int b = 0; b < V; ++b) h[b] += (x == static_cast<unsigned>(b)) ? wi : 0.0;
-        }
+        __syncwarp();
+        hist_round<V>(stage + lane * kStageIntStride, wst, 0u, h);       // `lo` already is the first bin of this launch
+        __syncwarp();
     }
-    const double r = block_reduce<V>(h, 0ull, smem);
-    if (threadIdx.x < V && bin_offset + static_cast<int>(threadIdx.x) < hist_bins) {
-        partials[static_cast<size_t>(c) * n_cols + hist_col0 + row * hist_bins + bin_offset + threadIdx.x] = r;
+#pragma unroll
+    for (int b = 0; b < V; ++b) slot_sums[slot][lane][b] = h[b];
+    __syncthreads();
+    for (unsigned t = threadIdx.x; t < 32u * V; t += kBlock) {
+        const unsigned q = t / V, b = t % V;
+        if (static_cast<int>(q) < rows_here && bin_offset + static_cast<int>(b) < hist_bins) {
+            double r = slot_sums[0][q][b];
+#pragma unroll
+            for (unsigned sl = 1; sl < kWarps; ++sl) r = __dadd_rn(r, slot_sums[sl][q][b]);
+            partials[static_cast<size_t>(c) * n_cols + hist_col0 + (row0 + static_cast<int>(q)) * hist_bins + bin_offset + static_cast<int>(b)] = r;
+        }
     }
 }
 

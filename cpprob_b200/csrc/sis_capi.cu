@@ -130,7 +130,7 @@ struct cpprob_sis_engine {
     device_buffer<unsigned long long> d_text_bsum[2], d_text_meta;   // meta: [kind]{total bytes, #ambiguous}
     device_buffer<char> d_text[2][2];                             // [double buffer][kind: 0 real, 1 int]
     device_buffer<text_slot> d_text_slots[2];
-    device_buffer<text_flag> d_text_flags;                        // [kind][kMaxTextFlags]
+    device_buffer<text_flag> d_text_flags;                        // [double buffer][kind][kMaxTextFlags]
     pinned_buffer<char> h_text[2][2];
     pinned_buffer<unsigned long long> h_text_meta[2];
     pinned_buffer<text_flag> h_text_flags;
@@ -239,7 +239,17 @@ template<int V>
 cudaError_t launch_hist(cudaStream_t s, unsigned grid, int n_int, const int * rows, const double * w, unsigned long long stride,
                         unsigned long long n, long long lo, int off, int bins, int col0, double * partials, int n_cols)
 {
-    k_row_hist<V><<<grid, kBlock, 0, s>>>(rows, w, stride, n, n_int, lo, off, bins, col0, partials, n_cols);
+    k_rows_hist<V><<<grid, kBlock, 0, s>>>(rows, w, stride, n, n_int, lo, off, bins, col0, partials, n_cols);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rows_moments(cudaStream_t s, unsigned n_sub_chunks, const double * rows, const double * w, unsigned long long stride,
+                                unsigned long long n, int n_real, double * partials, int n_cols)
+{
+    // 70 KB of staging areas per CTA: beyond the default limit (the attribute is per device, and cheap to set)
+    if (cudaError_t err = cudaFuncSetAttribute(k_rows_moments, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kRowsMomentsSmem))) return err;
+    const unsigned grid = n_sub_chunks * static_cast<unsigned>((n_real + 31) / 32);
+    k_rows_moments<<<grid, kBlock, kRowsMomentsSmem, s>>>(rows, w, stride, n, n_real, partials, n_cols);
     return cudaGetLastError();
 }
 
@@ -248,7 +258,7 @@ cudaError_t launch_hist_all(cudaStream_t s, unsigned n_chunks, int n_int, const 
                             unsigned long long stride, unsigned long long n, hist_window hw, int col0,
                             double * partials, int n_cols, uint64_t * launches)
 {
-    const unsigned grid = n_chunks * static_cast<unsigned>(n_int);
+    const unsigned grid = n_chunks * static_cast<unsigned>((n_int + 31) / 32);        // one CTA per (sub-chunk, group of 32 rows)
     for (int off = 0; off < hw.bins; off += 8) {
         const int left = hw.bins - off;
         cudaError_t err;
@@ -309,7 +319,20 @@ struct shard_options {
     bool no_wait = false;    // fused path only: return right after the launches; merge_impl(..., pending) collects m_ref and the time
 };
 
+constexpr int kMinStagedWarps = 4;          // fewer resident warps than this: the row path is the better choice
+
+// test / A-B hook: CPPROB_SIS_STAGED=0 sends estimator-only runs of long traces through the row path, as before
+bool staged_enabled()
+{
+    static const bool on = [] {
+        const char * s = std::getenv("CPPROB_SIS_STAGED");
+        return !(s && std::strcmp(s, "0") == 0);
+    }();
+    return on;
+}
+
 struct shard_result {
+    int path = CPPROB_SIS_PATH_ROWS;
     shard_plan plan;
     uint32_t rows_per_chunk = 1;       // partial rows per kChunk particles: 1 (fused) or kChunk / kSubChunk (row path)
     uint32_t n_rows_local = 0, n_rows_total = 0, row_first = 0;   // the rows handed on (super-chunk rows, see plan_shard)
@@ -354,7 +377,14 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     double pilot[3] = {0, 0, 0};
     // A model without int predicts needs nothing from the pilot on the host before its kernels start: the maxima are
     // folded on the device and m_ref is read back with the results (one host round trip less per inference).
-    const bool fused_early = !opt.force_rows && opt.emit == CPPROB_SIS_EMIT_NONE && n_int == 0 && n_real <= kMaxFusedReal;
+    // Paths: estimator-only runs keep the trace off HBM — in registers when the model has at most
+    // kMaxFusedReal real predicts and no int predicts (k_sis_fused), else in per-warp shared-memory staging areas
+    // (k_sis_staged) as long as those fit; emitting runs, forced runs and very long traces write SoA rows (k_sis_rows).
+    const bool est_only = !opt.force_rows && opt.emit == CPPROB_SIS_EMIT_NONE;
+    const bool fused = est_only && n_int == 0 && n_real <= kMaxFusedReal;
+    int staged_warps = 0;
+    if (est_only && !fused && n_int == 0 && staged_enabled()) staged_warps = vt->staged_warps(static_cast<int>(n_obs), n_real, 0, 0);
+    const bool fused_early = fused || staged_warps >= kMinStagedWarps;
     if (fused_early) {
         const int n_pilot = static_cast<int>(std::min<uint64_t>(n_total, kPilot));
         CU_TRY(e->h_pilot.reserve(1));
@@ -386,7 +416,9 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     res->m_ref = m_ref;
     const int n_cols = kBaseCols + 2 * n_real + n_int * hw.bins;
     res->n_cols = n_cols;
-    const bool fused = fused_early;
+    if (est_only && !fused && n_int > 0 && staged_enabled()) staged_warps = vt->staged_warps(static_cast<int>(n_obs), n_real, n_int, hw.bins);
+    const bool staged = !fused && staged_warps >= kMinStagedWarps;
+    res->path = fused ? CPPROB_SIS_PATH_FUSED : (staged ? CPPROB_SIS_PATH_STAGED : CPPROB_SIS_PATH_ROWS);
     // partial-sum rows: one per chunk on the fused path, one per sub-chunk on the row path (same on every rank)
     const unsigned row_particles = fused ? kChunk : kSubChunk;
     res->rows_per_chunk = kChunk / row_particles;
@@ -434,9 +466,42 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     a.hist_lo = hw.lo;
     a.hist_bins = hw.bins;
 
+    if (staged) {
+        // one CTA per SM, as many warps as the staging areas allow; any warp takes any (sub-chunk, slot) unit
+        const uint64_t units = static_cast<uint64_t>(kernel_rows) * kSlotsPerChunk;
+        const int grid = static_cast<int>(std::min<uint64_t>((units + staged_warps - 1) / staged_warps, static_cast<uint64_t>(e->sm_count)));
+        a.first_particle = plan.first_particle;
+        a.n_particles = plan.n_local;
+        a.n_chunks = kernel_rows;
+        a.partials = e->d_partials.ptr;
+        a.n_real = n_real;
+        a.n_int = n_int;
+        CU_TRY(e->d_warp_partials.reserve(static_cast<size_t>(units) * n_cols));
+        a.warp_partials = e->d_warp_partials.ptr;
+        CU_TRY(cudaMemsetAsync(e->d_counter.ptr, 0, sizeof(unsigned), e->compute));
+        CU_TRY(vt->launch_staged(e->compute, grid, staged_warps, &a));
+        const unsigned long long fold_n = static_cast<unsigned long long>(kernel_rows) * n_cols;
+        k_fold_warp_partials<<<static_cast<unsigned>((fold_n + kBlock - 1) / kBlock), kBlock, 0, e->compute>>>(
+            e->d_warp_partials.ptr, kernel_rows, n_cols, e->d_partials.ptr, n_cols);
+        CU_TRY(cudaGetLastError());
+        res->launches += 2;
+        if (int rc = fold_rows()) return rc;
+        CU_TRY(cudaEventRecord(e->ev_end, e->compute));
+        if (opt.no_wait && fused_early) {          // m_ref still on the device: collected after the merge
+            res->waiting = true;
+            return 0;
+        }
+        CU_TRY(cudaStreamSynchronize(e->compute));
+        if (fused_early) res->m_ref = e->h_pilot.ptr[0];
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));
+        res->device_ms = ms;
+        return 0;
+    }
+
     if (fused) {
         const int nr = n_real <= 1 ? 1 : (n_real == 2 ? 2 : 4);
-        int occ = vt->occupancy(nr == 1 ? 0 : (nr == 2 ? 1 : 2));
+        int occ = vt->occupancy(nr == 1 ? 0 : (nr == 2 ? 1 : 2), static_cast<int>(n_obs));
         if (occ <= 0) occ = 1;
         if (e->blocks_per_sm > 0) occ = std::min(occ, e->blocks_per_sm);
         // warp-autonomous kernel: enough CTAs to give every (chunk, warp slot) unit a warp, at most the resident set
@@ -493,7 +558,7 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         }
     }
     if (n_int > 0) CU_TRY(e->d_int_extra.reserve(static_cast<size_t>(cap / kSubChunk)));
-    int occ = vt->occupancy(3);
+    int occ = vt->occupancy(3, static_cast<int>(n_obs));
     if (occ <= 0) occ = 1;
     if (e->blocks_per_sm > 0) occ = std::min(occ, e->blocks_per_sm);
 
@@ -514,7 +579,7 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
             CU_TRY(e->d_text_bsum[kind].reserve((cap + kTextBlock - 1) / kTextBlock));
         }
         CU_TRY(e->d_text_meta.reserve(4));
-        CU_TRY(e->d_text_flags.reserve(2 * kMaxTextFlags));
+        CU_TRY(e->d_text_flags.reserve(4 * kMaxTextFlags));       // [double buffer][kind]: batch b+1 must not overwrite the list batch b is still copying
         CU_TRY(e->h_text_flags.reserve(4 * kMaxTextFlags));
         for (int b = 0; b < 2; ++b) CU_TRY(e->h_text_meta[b].reserve(4));
     }
@@ -623,9 +688,7 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         CU_TRY(cudaGetLastError());
         ++res->launches;
         if (n_real > 0) {
-            const unsigned g = subs_here * static_cast<unsigned>((n_real + kMomTile - 1) / kMomTile);
-            k_row_moments<<<g, kBlock, 0, e->compute>>>(a.real_rows, a.w, cap, n_here, n_real, a.partials, n_cols);
-            CU_TRY(cudaGetLastError());
+            CU_TRY(launch_rows_moments(e->compute, subs_here, a.real_rows, a.w, cap, n_here, n_real, a.partials, n_cols));
             ++res->launches;
         }
         if (n_int > 0) {
@@ -671,7 +734,7 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
             for (int kind = 0; kind < 2; ++kind) {
                 if (!n_text_slots[kind]) continue;
                 k_text_write<<<text_blocks, kTextBlock, 0, e->compute>>>(ta[kind], e->d_text_len[kind].ptr, e->d_text_bsum[kind].ptr,
-                                                                         e->d_text[buf][kind].ptr, e->d_text_flags.ptr + kind * kMaxTextFlags,
+                                                                         e->d_text[buf][kind].ptr, e->d_text_flags.ptr + (2 * buf + kind) * kMaxTextFlags,
                                                                          e->d_text_meta.ptr + 2 * kind + 1, kMaxTextFlags);
                 CU_TRY(cudaGetLastError());
                 ++res->launches;
@@ -691,7 +754,7 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
                 if (nf > kMaxTextFlags) return fail(CPPROB_SIS_EIO, "device text stage: too many ambiguous records in one batch");
                 CU_TRY(cudaMemcpyAsync(e->h_text[buf][kind].ptr, e->d_text[buf][kind].ptr, total, cudaMemcpyDeviceToHost, e->copy));
                 if (nf) {
-                    CU_TRY(cudaMemcpyAsync(e->h_text_flags.ptr + (2 * buf + kind) * kMaxTextFlags, e->d_text_flags.ptr + kind * kMaxTextFlags,
+                    CU_TRY(cudaMemcpyAsync(e->h_text_flags.ptr + (2 * buf + kind) * kMaxTextFlags, e->d_text_flags.ptr + (2 * buf + kind) * kMaxTextFlags,
                                            nf * sizeof(text_flag), cudaMemcpyDeviceToHost, e->copy));
                 }
                 pending[buf].text_flags[kind] = nf;
@@ -737,6 +800,8 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     }
     return 0;
 }
+
+constexpr double kRebaseLimit = 300.0;
 
 // Merge [n_chunks][n_cols] partials (device) and turn the sums into estimators.
 // Returns 1 if the weights must be re-based to out->max_log_w.
@@ -813,9 +878,11 @@ int merge_impl(cpprob_sis_engine * e, const double * gathered, uint32_t n_chunks
     out->n_cols = n_cols;
     out->sums = e->sums.data();
 
-    // re-base if exp(log_w - m_ref) could have overflowed / underflowed the interesting weights
+    // re-base if exp(log_w - m_ref) could have overflowed / underflowed the interesting weights.  The tightest
+    // quantity is sum w^2 (the ESS denominator): w^2 overflows a double once log_w - m_ref exceeds 354.9, so the
+    // limit is 300 (weights up to e^300, squares up to e^600, 2^43 of them still finite)
     const double mx = out->max_log_w;
-    if (std::isfinite(mx) && std::fabs(mx - m_ref) > 600.0) return 1;
+    if (std::isfinite(mx) && std::fabs(mx - m_ref) > kRebaseLimit) return 1;
     return 0;
 }
 
@@ -876,6 +943,7 @@ int run_full(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, const do
     out->device_ms = total_ms;
     out->kernel_launches = launches;
     out->passes = passes;
+    out->path = res.path;
     e->launches += launches;
     return 0;
 }
@@ -1091,9 +1159,20 @@ int cpprob_sis_run_shard(cpprob_sis_engine * e, int model_id, const double * obs
     return 0;
 }
 
+namespace {
+// An estimator-only run leaves no record file, and must not leave an older run's either: StatsPrinter reads the record
+// files first and the .stats sidecar only when there are none, so stale records would be printed against the new .ids.
+// (The reference's finish_infer removes the kinds that stayed empty, src/cpprob/state.cpp:167-175; here all of them did.)
+void remove_record_files(const char * prefix)
+{
+    for (const char * ext : {".real", ".int", ".any"}) std::remove((std::string(prefix) + ext).c_str());
+}
+}  // namespace
+
 int cpprob_sis_write_summary(cpprob_sis_engine * e, const char * prefix, const cpprob_sis_stats * stats)
 {
     if (!e || !prefix || !stats) return fail(CPPROB_SIS_EINVAL, "null argument");
+    remove_record_files(prefix);
     if (!cpprob::text::write_ids(prefix, e->structure.ids)) return fail(CPPROB_SIS_EIO, std::string("cannot write ") + prefix + ".ids");
     if (!cpprob::text::write_stats_sidecar(prefix, *stats, e->slots, e->structure.ids)) {
         return fail(CPPROB_SIS_EIO, std::string("cannot write ") + prefix + ".stats");
@@ -1298,9 +1377,7 @@ int cpprob_sis_reduce_records(cpprob_sis_engine * e, const double * real_rows, i
     CU_TRY(cudaGetLastError());
     launches += 2;
     if (n_real > 0) {
-        const unsigned g = n_chunks * static_cast<unsigned>((n_real + kMomTile - 1) / kMomTile);
-        k_row_moments<<<g, kBlock, 0, e->compute>>>(e->d_real[0].ptr, e->d_w[0].ptr, stride, n, n_real, e->d_partials.ptr, n_cols);
-        CU_TRY(cudaGetLastError());
+        CU_TRY(launch_rows_moments(e->compute, n_chunks, e->d_real[0].ptr, e->d_w[0].ptr, stride, n, n_real, e->d_partials.ptr, n_cols));
         ++launches;
     }
     if (n_int > 0) {
@@ -1552,6 +1629,7 @@ int cpprob_sis_infer_to_files(cpprob_sis_engine * e, int model_id, const double 
     if (emit == CPPROB_SIS_EMIT_NONE) {
         shard_options none;
         if (int rc = run_full(e, vt, obs, n_obs, n_particles, none, out)) return rc;
+        remove_record_files(prefix);
         if (!cpprob::text::write_ids(prefix, e->structure.ids)) return fail(CPPROB_SIS_EIO, std::string("cannot write ") + prefix + ".ids");
         if (!cpprob::text::write_stats_sidecar(prefix, *out, e->slots, e->structure.ids)) {
             return fail(CPPROB_SIS_EIO, std::string("cannot write ") + prefix + ".stats");

@@ -85,6 +85,11 @@ struct run_args {
     // row path: particles per partial row (sub-chunk) and the per-sub-chunk int bookkeeping
     unsigned chunk;
     struct int_extra * int_extras;       // [n_sub_chunks] or nullptr when the model has no int predicts
+    // model table (Model::fill_scratch) in shared memory: its size in doubles, 0 = none (absent / beyond the budget)
+    int scratch_doubles;
+    // staged kernel: the trace structure and the byte offset of the per-warp staging areas in dynamic shared memory
+    int n_real, n_int;
+    unsigned stage_base;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -196,6 +201,24 @@ __device__ __forceinline__ unsigned zig_prepare()
     return 0u;
 }
 
+// Dynamic shared memory of a model kernel: [ziggurat table, if the model draws normals][model table][kernel-specific].
+// The ziggurat part is rounded up to 16 bytes so that what follows can be read with 128-bit loads.
+template<class Model>
+constexpr unsigned zig_smem_doubles() { return model_draws_normals<Model>::value ? ((zig::N + 1 + 1) & ~1u) : 0u; }
+
+// Fills the model's per-launch table (particle.hpp, "Per-launch model tables") cooperatively, once per CTA.
+// Returns nullptr when the model has none or the launch was given no room for it (scratch_doubles == 0).
+template<class Model>
+__device__ __forceinline__ const double * model_scratch_prepare(const double * __restrict__ obs, int n_obs, int scratch_doubles)
+{
+    if (!model_scratch<Model>::present || scratch_doubles <= 0) return nullptr;
+    extern __shared__ double cpprob_zig_shared[];
+    double * const t = cpprob_zig_shared + zig_smem_doubles<Model>();
+    model_scratch<Model>::fill(t, obs, n_obs, static_cast<int>(threadIdx.x), static_cast<int>(blockDim.x));
+    __syncthreads();
+    return t;
+}
+
 // Observations of scalar-argument models are read once into registers; array models read theirs
 // through the read-only path as they go (the same address in every lane: one L1 hit per warp).
 template<class Model, bool Scalars = (Model::n_scalar_obs >= 0)>
@@ -259,6 +282,21 @@ struct reg_policy {
     template<class S> __device__ __forceinline__ void begin_vector(int, const S &) {}
 };
 
+// Integral predicts are recorded as 32-bit values (StatsPrinter parses the .int file as `int`, stats_printer.hpp:83).
+// A wider value that does not fit is never truncated silently: it drives the tracked range to the whole of int32, which
+// no histogram window covers, so the run ends with CPPROB_SIS_ERANGE.
+template<class T>
+__device__ __forceinline__ int narrow_int(T x, int & imin, int & imax)
+{
+    if (sizeof(T) > sizeof(int)) {
+        if (static_cast<T>(static_cast<int>(x)) != x) {
+            imin = static_cast<int>(0x80000000u);
+            imax = 0x7fffffff;
+        }
+    }
+    return static_cast<int>(x);
+}
+
 // Row kernel: address-major SoA rows in HBM; consecutive threads own consecutive columns, so each
 // predict statement is one fully coalesced store per warp.
 struct row_policy {
@@ -270,9 +308,9 @@ struct row_policy {
         : real_col(rc), int_col(ic), stride(s), imin(0x7fffffff), imax(static_cast<int>(0x80000000u)) {}
     template<class D>
     __device__ __forceinline__ typename D::result_type sample(const D & d, philox_stream & rng) { return d(rng); }
-    template<class S> __device__ __forceinline__ void predict_int(long long x, const S &)
+    template<class T, class S> __device__ __forceinline__ void predict_int(T x, const S &)
     {
-        const int xi = static_cast<int>(x);
+        const int xi = narrow_int(x, imin, imax);
         *int_col = xi;
         int_col += stride;
         imin = min(imin, xi);
@@ -349,19 +387,20 @@ private:
 // ------------------------------------------------------------------------------------------------
 template<class Model>
 __global__ void __launch_bounds__(kBlock) k_pilot(const __grid_constant__ philox_keys keys, const double * __restrict__ obs,
-                                                  int n_obs, int n_pilot, double * __restrict__ out)
+                                                  int n_obs, int n_pilot, int scratch_doubles, double * __restrict__ out)
 {
     constexpr unsigned kTile = 2 * kPairStride;
     __shared__ double smem[kWarps * 3];
     const Model model{};
     const obs_cache<Model> oc(obs, n_obs);
     const unsigned zig_base = zig_prepare<Model>();
+    const double * const scratch = model_scratch_prepare<Model>(obs, n_obs, scratch_doubles);
     double v[3] = {dm::neg_inf(), dm::neg_inf(), dm::neg_inf()};   // max lw, max(-imin), max(imax)
     const unsigned base = blockIdx.x * kTile;
     const unsigned n_here = static_cast<unsigned>(n_pilot) > base ? min(static_cast<unsigned>(n_pilot) - base, kTile) : 0u;
     for_each_owned_particle(keys, zig_base, threadIdx.x, static_cast<unsigned long long>(base), n_here, [&](philox_stream & rng, unsigned) {
         null_policy pol;
-        particle<null_policy> p(rng, pol);
+        particle<null_policy> p(rng, pol, scratch);
         invoke_model(model, p, oc.data(), n_obs);
         v[0] = fmax(v[0], p.log_w());
         if (pol.imin <= pol.imax) {
@@ -395,6 +434,7 @@ __global__ void __launch_bounds__(fused_block(NR), NR == 1 ? CPPROB_FUSED_MIN_BL
     const double m_ref = *a.m_ref;
     const obs_cache<Model> oc(a.obs, a.n_obs);
     const unsigned zig_base = zig_prepare<Model>();
+    const double * const scratch = model_scratch_prepare<Model>(a.obs, a.n_obs, a.scratch_doubles);
     const unsigned exp_tab = dm::exp2_table_load();
     const unsigned lane = threadIdx.x & 31u;
     const unsigned n_units = a.n_chunks * kSlotsPerChunk;
@@ -439,7 +479,7 @@ __global__ void __launch_bounds__(fused_block(NR), NR == 1 ? CPPROB_FUSED_MIN_BL
         reset();
         for_each_owned_particle(a.keys, zig_base, vt, a.first_particle + base, n_here, [&](philox_stream & rng, unsigned) {
             reg_policy<NR, true> pol;
-            particle<reg_policy<NR, true>> p(rng, pol);
+            particle<reg_policy<NR, true>> p(rng, pol, scratch);
             invoke_model(model, p, oc.data(), a.n_obs);
             const double lw = p.log_w();
             const double arg = lw - m_ref;
@@ -451,7 +491,7 @@ __global__ void __launch_bounds__(fused_block(NR), NR == 1 ? CPPROB_FUSED_MIN_BL
             reset();
             for_each_owned_particle(a.keys, zig_base, vt, a.first_particle + base, n_here, [&](philox_stream & rng, unsigned) {
                 reg_policy<NR> pol;
-                particle<reg_policy<NR>> p(rng, pol);
+                particle<reg_policy<NR>> p(rng, pol, scratch);
                 invoke_model(model, p, oc.data(), a.n_obs);
                 const double lw = p.log_w();
                 const double w = dm::exp_weight(lw - m_ref);
@@ -528,6 +568,7 @@ __global__ void __launch_bounds__(kBlock) k_sis_rows(const __grid_constant__ run
     const unsigned n_tiles = static_cast<unsigned>((a.n_particles + kTile - 1) / kTile);
     const unsigned long long stream0 = stream_of_particle(a.first_particle) + threadIdx.x;
     const unsigned zig_base = zig_prepare<Model>();
+    const double * const scratch = model_scratch_prepare<Model>(a.obs, a.n_obs, a.scratch_doubles);
 
     for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const unsigned long long base = static_cast<unsigned long long>(tile) * kTile;
@@ -542,7 +583,7 @@ __global__ void __launch_bounds__(kBlock) k_sis_rows(const __grid_constant__ run
                 if (i < n_here) {
                     const unsigned long long colidx = base + i;
                     row_policy pol(a.real_rows + colidx, a.int_rows + colidx, a.row_stride);
-                    particle<row_policy> p(rng, pol);
+                    particle<row_policy> p(rng, pol, scratch);
                     invoke_model(model, p, oc.data(), a.n_obs);
                     a.logw[colidx] = p.log_w();
                     vmin = min(vmin, pol.imin);
@@ -568,19 +609,20 @@ __global__ void __launch_bounds__(kBlock) k_sis_rows(const __grid_constant__ run
 // the reference/oracle log-weights).
 // ------------------------------------------------------------------------------------------------
 template<class Model>
-__global__ void __launch_bounds__(kBlock) k_replay(const double * __restrict__ obs, int n_obs,
+__global__ void __launch_bounds__(kBlock) k_replay(const double * __restrict__ obs, int n_obs, int scratch_doubles,
                                                    const double * __restrict__ real_rows, const int * __restrict__ int_rows,
                                                    unsigned long long stride, unsigned long long n,
                                                    double * __restrict__ logw_out)
 {
     const Model model{};
     const obs_cache<Model> oc(obs, n_obs);
+    const double * const scratch = model_scratch_prepare<Model>(obs, n_obs, scratch_doubles);
     const philox_keys keys(0u, 0u);   // never drawn from: every sample statement returns a recorded value
     for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(kBlock) + threadIdx.x; i < n;
          i += static_cast<unsigned long long>(gridDim.x) * kBlock) {
         replay_policy pol(real_rows + i, int_rows + i, stride);
         philox_stream rng(keys, i);
-        particle<replay_policy> p(rng, pol);
+        particle<replay_policy> p(rng, pol, scratch);
         invoke_model(model, p, oc.data(), n_obs);
         logw_out[i] = p.log_w();
     }

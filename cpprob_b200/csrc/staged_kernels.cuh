@@ -1,0 +1,282 @@
+// cpprob-b200: K1s k_sis_staged — model body + weight + per-(address, k) estimator sums in ONE kernel for models with
+// many predicts per trace (linear_gaussian_1d<32>: 32 reals, hmm<64>: 64 ints), with no trace row in HBM.
+//
+// The weight of a particle is known only after its last observe (cpprob.hpp:87-89 accumulates log_w over the whole
+// trace), but the sums StatsPrinter needs are per predict statement: sum_p w_p x_{p,k}, sum_p w_p x_{p,k}^2 and
+// sum_p w_p [x_{p,k} == v] for every (id, k) (stats_printer.hpp:88-120, empirical_distribution.hpp:30-40,52-81).  That is a
+// transposition: lanes own particles while a trace is generated, and must own rows (id, k) when the sums are formed.
+//
+// Each warp does it through its own staging area in shared memory:
+//   1. the 32 lanes run 32 particles; every predict is one store into stage[k][lane] (one conflict-free wavefront);
+//   2. each lane computes w = exp(log_w - m_ref) of its particle and stores it into wst[lane];
+//   3. lane k walks row k of the stage (32 particles, 128-bit loads) with the broadcast weights and adds the round's
+//      contribution to the sums of row k (and k + 32, ... for longer traces).
+// No barrier is shared with another warp, no row reaches HBM, and a round costs 3 FP64 instructions + 1 shared-memory
+// load per (particle, real predict), or one compare + predicated add per bin per (particle, int predict).
+//
+// Canonical summation order (what makes results bit-identical for any grid / GPU count, and equal to the row path):
+//   work unit = (sub-chunk c of 4096 particles, warp slot s) = the 512 particles p = 512 t + 256 u + 32 s + l
+//   (tile t < 8, turn u < 2, lane l) that slot s of a 256-thread CTA owns; the unit's sums are formed sequentially over
+//   those particles in (t, u, l) order, per row and per bin; the 8 slots are then added in slot order
+//   (k_fold_warp_partials), sub-chunks in order (k_fold_rows, k_merge_columns).  Base columns (max log_w, sum w, sum w^2,
+//   counts) keep the order of k_row_base: per (slot, lane) over the 16 rounds, then the xor tree over lanes, then slots.
+//   The row path's reduction kernels (k_rows_moments / k_rows_hist in reduce_kernels.cuh) stage the rows they read from
+//   HBM the same way and call the same round functions, so both paths produce the same bits.
+#ifndef CPPROB_B200_STAGED_KERNELS_CUH
+#define CPPROB_B200_STAGED_KERNELS_CUH
+
+#include "sis_kernels.cuh"
+
+namespace cpprob {
+namespace engine {
+
+constexpr int kStageRealStride = 34;        // doubles per staged real row: 32 lanes + 2, so lane k's 128-bit reads of row k are conflict-free
+constexpr int kStageIntStride = 32;         // bytes per staged int row: one state byte per lane
+constexpr int kStagedMaxBins = 8;           // histogram bins the staged kernel keeps in registers
+// CTA size the staged kernel is compiled for (it is launched with as many warps as the staging areas allow, at most
+// this).  A model that draws normals carries the 64 KB ziggurat table, which leaves room for about 16 staging areas of a
+// 32-predict trace: 512 threads, and the 128 registers that go with them keep the normal sampler's state out of local
+// memory.  Models without it (hmm) are integer-bound and want every warp they can get: 1024 threads at 64 registers.
+template<class Model>
+constexpr int staged_threads() { return model_draws_normals<Model>::value ? 512 : 1024; }
+constexpr unsigned kSmemBudget = 227u * 1024u;
+
+// One warp's staging area.  All offsets are multiples of 16 bytes.
+struct stage_layout {
+    unsigned real_off, int_off, w_off, macc_off, hacc_off, bytes;
+};
+__host__ __device__ inline stage_layout make_stage_layout(int n_real, int n_int, int bins)
+{
+    stage_layout L;
+    unsigned o = 0;
+    L.real_off = o;  o += static_cast<unsigned>(n_real) * kStageRealStride * 8u;
+    L.int_off = o;   o += static_cast<unsigned>(n_int) * kStageIntStride;
+    o = (o + 15u) & ~15u;
+    L.w_off = o;     o += 32u * 8u;
+    L.macc_off = o;  o += static_cast<unsigned>(n_real) * 16u;
+    L.hacc_off = o;  o += static_cast<unsigned>(n_int) * static_cast<unsigned>(bins > 0 ? bins : 0) * 8u;
+    L.bytes = (o + 15u) & ~15u;
+    return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Round functions: the contribution of 32 staged particles to the sums of the row this lane owns.
+// Explicitly rounded operations (no FMA contraction left to the compiler): the staged kernel and the row path's
+// reduction kernels must produce the same bits.  Lanes beyond the end of a ragged round have w = 0 and x = 0 / an
+// unmatched state staged for them, so they add exactly nothing.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void moments_round(const double * __restrict__ row, const double * __restrict__ wst, double & s1, double & s2)
+{
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+        const double2 x = *reinterpret_cast<const double2 *>(row + j);
+        const double2 w = *reinterpret_cast<const double2 *>(wst + j);
+        const double wx0 = __dmul_rn(w.x, x.x);              // empirical_distribution.hpp:52-71: sum w x, sum w x^2
+        s1 = __dadd_rn(s1, wx0);
+        s2 = __fma_rn(wx0, x.x, s2);
+        const double wx1 = __dmul_rn(w.y, x.y);
+        s1 = __dadd_rn(s1, wx1);
+        s2 = __fma_rn(wx1, x.y, s2);
+    }
+}
+
+// states are staged as bytes (value - window start); a byte that matches no bin (outside the window, or the 255 of a
+// lane beyond the end) adds nothing
+template<int V>
+__device__ __forceinline__ void hist_round(const unsigned char * __restrict__ row, const double * __restrict__ wst, unsigned first_bin, double (&h)[V])
+{
+    const uint4 a = *reinterpret_cast<const uint4 *>(row), b = *reinterpret_cast<const uint4 *>(row + 16);
+    const unsigned words[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const double2 w01 = *reinterpret_cast<const double2 *>(wst + 4 * q), w23 = *reinterpret_cast<const double2 *>(wst + 4 * q + 2);
+        const double w[4] = {w01.x, w01.y, w23.x, w23.y};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const unsigned s = ((words[q] >> (8 * e)) & 0xffu) - first_bin;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                if (s == static_cast<unsigned>(v)) h[v] = __dadd_rn(h[v], w[e]);   // empirical_distribution.hpp:30-40
+            }
+        }
+    }
+}
+
+template<int V>
+__device__ __forceinline__ void hist_round_acc(const unsigned char * __restrict__ row, const double * __restrict__ wst, double * __restrict__ acc)
+{
+    double h[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) h[v] = acc[v];
+    hist_round<V>(row, wst, 0u, h);
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = h[v];
+}
+
+__device__ __forceinline__ void hist_round_dispatch(int bins, const unsigned char * __restrict__ row, const double * __restrict__ wst, double * __restrict__ acc)
+{
+    switch (bins) {            // warp-uniform
+    case 1: hist_round_acc<1>(row, wst, acc); break;
+    case 2: hist_round_acc<2>(row, wst, acc); break;
+    case 3: hist_round_acc<3>(row, wst, acc); break;
+    case 4: hist_round_acc<4>(row, wst, acc); break;
+    case 5: hist_round_acc<5>(row, wst, acc); break;
+    case 6: hist_round_acc<6>(row, wst, acc); break;
+    case 7: hist_round_acc<7>(row, wst, acc); break;
+    default: hist_round_acc<8>(row, wst, acc); break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Policy: predicts go to this lane's column of the warp's staging area.
+// ------------------------------------------------------------------------------------------------
+struct staged_policy {
+    double * real_col;             // &stage_real[k][lane], k = next real predict
+    unsigned char * int_col;       // &stage_int[k][lane]
+    int lo;                        // start of the histogram window
+    int imin, imax;                // range of the int predicts of this particle
+    __device__ __forceinline__ staged_policy(double * rc, unsigned char * ic, int lo_)
+        : real_col(rc), int_col(ic), lo(lo_), imin(0x7fffffff), imax(static_cast<int>(0x80000000u)) {}
+    template<class D>
+    __device__ __forceinline__ typename D::result_type sample(const D & d, philox_stream & rng) { return d(rng); }
+    template<class T, class S> __device__ __forceinline__ void predict_int(T x, const S &)
+    {
+        const int xi = narrow_int(x, imin, imax);
+        // the low byte is enough: a value outside [lo, lo + bins) makes the run repeat with a wider window (run_full)
+        *int_col = static_cast<unsigned char>(xi - lo);
+        int_col += kStageIntStride;
+        imin = min(imin, xi);
+        imax = max(imax, xi);
+    }
+    template<class S> __device__ __forceinline__ void predict_real(double x, const S &)
+    {
+        *real_col = x;
+        real_col += kStageRealStride;
+    }
+    template<class S> __device__ __forceinline__ void begin_vector(int, const S &) {}
+};
+
+// ------------------------------------------------------------------------------------------------
+// K1s k_sis_staged.  a.n_chunks = number of sub-chunks (kSubChunk particles) of this launch; a.warp_partials =
+// [n_chunks * 8][n_cols]; a.stage_base = byte offset of the per-warp staging areas in dynamic shared memory.
+// Any warp takes any (sub-chunk, slot) unit from the atomic counter.
+// ------------------------------------------------------------------------------------------------
+template<class Model>
+__global__ void __launch_bounds__(staged_threads<Model>(), 1) k_sis_staged(const __grid_constant__ run_args a)
+{
+    extern __shared__ double cpprob_zig_shared[];
+    constexpr unsigned kTile = 2 * kPairStride;
+    const Model model{};
+    const double m_ref = *a.m_ref;
+    const obs_cache<Model> oc(a.obs, a.n_obs);
+    const unsigned zig_base = zig_prepare<Model>();
+    const double * const scratch = model_scratch_prepare<Model>(a.obs, a.n_obs, a.scratch_doubles);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int n_real = a.n_real, n_int = a.n_int, bins = a.hist_bins;
+    const int lo = static_cast<int>(a.hist_lo);
+    const stage_layout L = make_stage_layout(n_real, n_int, bins);
+    char * const area = reinterpret_cast<char *>(cpprob_zig_shared) + a.stage_base + static_cast<size_t>(warp) * L.bytes;
+    double * const stage_real = reinterpret_cast<double *>(area + L.real_off);
+    unsigned char * const stage_int = reinterpret_cast<unsigned char *>(area + L.int_off);
+    double * const wst = reinterpret_cast<double *>(area + L.w_off);
+    double * const macc = reinterpret_cast<double *>(area + L.macc_off);
+    double * const hacc = reinterpret_cast<double *>(area + L.hacc_off);
+    const unsigned n_units = a.n_chunks * kSlotsPerChunk;
+    const int n_cols = a.n_cols;
+
+    for (;;) {
+        unsigned unit = 0;
+        if (lane == 0) unit = atomicAdd(a.chunk_counter, 1u);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= n_units) break;
+        const unsigned c = unit / kSlotsPerChunk;
+        const unsigned vt = (unit % kSlotsPerChunk) * 32u + lane;
+        const unsigned long long base = static_cast<unsigned long long>(c) * kSubChunk;
+        const unsigned long long left = a.n_particles - base;
+        const unsigned n_here = left < kSubChunk ? static_cast<unsigned>(left) : kSubChunk;
+
+        for (int k = static_cast<int>(lane); k < 2 * n_real; k += 32) macc[k] = 0.0;
+        for (int k = static_cast<int>(lane); k < n_int * bins; k += 32) hacc[k] = 0.0;
+        double max_lw = dm::neg_inf(), s0 = 0.0, s00 = 0.0;
+        unsigned n_neginf = 0, n_nan = 0;
+        int imin = 0x7fffffff, imax = static_cast<int>(0x80000000u);
+        __syncwarp();
+
+        const unsigned long long stream0 = stream_of_particle(a.first_particle + base) + vt;
+        const unsigned n_tiles = (n_here + kTile - 1) / kTile;
+        for (unsigned tile = 0; tile < n_tiles; ++tile) {
+            philox_stream rng(a.keys, stream0 + static_cast<unsigned long long>(tile) * kPairStride, zig_base);
+#pragma unroll 1
+            for (unsigned turn = 0; turn < 2; ++turn) {
+                const unsigned i = tile * kTile + turn * kPairStride + vt;
+                const bool valid = i < n_here;
+                if (!__any_sync(0xffffffffu, valid)) break;          // the whole round lies beyond the end
+                double w = 0.0;
+                if (valid) {
+                    staged_policy pol(stage_real + lane, stage_int + lane, lo);
+                    particle<staged_policy> p(rng, pol, scratch);
+                    invoke_model(model, p, oc.data(), a.n_obs);
+                    const double lw = p.log_w();
+                    w = dm::exp_weight(lw - m_ref);
+                    // the base sums of k_row_base, same operations in the same order
+                    max_lw = lw > max_lw ? lw : max_lw;
+                    s0 += w;
+                    s00 = fma(w, w, s00);
+                    n_neginf += is_neg_inf(lw) ? 1u : 0u;
+                    n_nan += is_nan(lw) ? 1u : 0u;
+                    imin = min(imin, pol.imin);
+                    imax = max(imax, pol.imax);
+                } else {
+                    for (int k = 0; k < n_real; ++k) stage_real[k * kStageRealStride + lane] = 0.0;
+                    for (int k = 0; k < n_int; ++k) stage_int[k * kStageIntStride + lane] = 0xffu;
+                }
+                wst[lane] = w;
+                __syncwarp();
+                for (int k = static_cast<int>(lane); k < n_real; k += 32) {
+                    double s1 = macc[2 * k], s2 = macc[2 * k + 1];
+                    moments_round(stage_real + k * kStageRealStride, wst, s1, s2);
+                    macc[2 * k] = s1;
+                    macc[2 * k + 1] = s2;
+                }
+                for (int k = static_cast<int>(lane); k < n_int; k += 32) {
+                    hist_round_dispatch(bins, stage_int + k * kStageIntStride, wst, hacc + k * bins);
+                }
+                __syncwarp();
+            }
+        }
+
+        // the unit's partial row: base columns by the xor tree over lanes (the warp stage of block_reduce) ...
+        double v[kBaseCols];
+        v[col::max_lw] = max_lw;
+        v[col::s0] = s0;
+        v[col::s00] = s00;
+        v[col::n_neginf] = static_cast<double>(n_neginf);
+        const bool any_int = imin <= imax;
+        v[col::neg_imin] = any_int ? -static_cast<double>(imin) : dm::neg_inf();
+        v[col::imax] = any_int ? static_cast<double>(imax) : dm::neg_inf();
+        v[col::int_oor] = (any_int && (imin < lo || static_cast<long long>(imax) >= static_cast<long long>(lo) + bins)) ? 1.0 : 0.0;
+        v[col::n_nan] = static_cast<double>(n_nan);
+        double mine = 0.0;
+#pragma unroll
+        for (int j = 0; j < kBaseCols; ++j) {
+            double x = v[j];
+            const bool is_max = (kMaxColsMask >> j) & 1ull;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double y = __shfl_xor_sync(0xffffffffu, x, off);
+                x = is_max ? fmax(x, y) : x + y;
+            }
+            if (static_cast<int>(lane) == j) mine = x;
+        }
+        double * const out = a.warp_partials + static_cast<size_t>(unit) * n_cols;
+        if (static_cast<int>(lane) < kBaseCols) out[lane] = mine;
+        // ... and the row sums straight from the accumulators (already complete per row: no reduction over lanes)
+        for (int k = static_cast<int>(lane); k < 2 * n_real; k += 32) out[kBaseCols + k] = macc[k];
+        for (int k = static_cast<int>(lane); k < n_int * bins; k += 32) out[kBaseCols + 2 * n_real + k] = hacc[k];
+        __syncwarp();
+    }
+}
+
+}  // namespace engine
+}  // namespace cpprob
+#endif  // CPPROB_B200_STAGED_KERNELS_CUH

@@ -24,6 +24,7 @@
 #include <cstdint>
 #include <initializer_list>
 #include <limits>
+#include <stdexcept>
 
 #include "cpprob/hd.hpp"
 #include "cpprob/math/dmath.hpp"
@@ -260,6 +261,10 @@ public:
         return static_cast<IntType>(out);
     }
 
+    // the integer thresholds operator() compares against (thresholds()[i] = t_i, i < size - 1); what a
+    // table_discrete_distribution is built from
+    CPPROB_HD const std::uint32_t * thresholds() const { return thr_; }
+
 private:
     template<class Iter>
     CPPROB_HD void init(Iter first, Iter last)
@@ -270,12 +275,24 @@ private:
             probs_.p[n] = *first;
             sum += probs_.p[n];
         }
+        if (first != last) too_many_weights();     // Boost's discrete_distribution has no such limit: never truncate silently
         probs_.n = n;
         for (int i = n; i < MaxK; ++i) probs_.p[i] = WeightType(0);
         if (sum != WeightType(1)) {          // x / 1 == x exactly: skip the divisions when already normalised
             for (int i = 0; i < n; ++i) probs_.p[i] /= sum;
         }
         set_thresholds();
+    }
+
+    // more weights than the inline capacity: a device trap / host exception, not a different distribution
+    CPPROB_HD static void too_many_weights()
+    {
+#if CPPROB_ON_DEVICE
+        __trap();
+#else
+        throw std::length_error("cpprob::discrete_distribution: more weights than its capacity MaxK; name a larger MaxK "
+                                "(discrete_distribution<IntType, WeightType, MaxK>)");
+#endif
     }
 
     CPPROB_HD void set_thresholds()
@@ -316,6 +333,66 @@ struct logpdf<discrete_distribution<IntType, WeightType, MaxK>> {
         }
         return dm::log(p);
     }
+};
+
+// -------------------------------------------------------------------------------------------------
+// table_discrete: the sampler of a discrete_distribution whose K - 1 integer thresholds sit in a table (e.g. one
+// row per state of a transition matrix, filled once per launch by Model::fill_scratch).  Draws exactly what the
+// discrete_distribution the thresholds came from draws — the smallest i with r < t_i — with K - 1 compares and no
+// per-particle set-up.  Sampling only: it carries no probabilities, so it has no logpdf.
+// -------------------------------------------------------------------------------------------------
+template<class IntType, int K>
+class table_discrete_distribution {
+public:
+    using result_type = IntType;
+    using input_type = double;
+
+    CPPROB_HD explicit table_discrete_distribution(const std::uint32_t * thresholds) : thr_(thresholds) {}
+    CPPROB_HD IntType min() const { return 0; }
+    CPPROB_HD IntType max() const { return static_cast<IntType>(K - 1); }
+
+    template<class Rng>
+    CPPROB_HD result_type operator()(Rng & rng) const
+    {
+        const std::uint32_t r = rng.next_u32();
+        int out = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int i = 0; i < K - 1; ++i) out += r >= thr_[i] ? 1 : 0;       // thresholds are non-decreasing
+        return static_cast<IntType>(out);
+    }
+
+private:
+    const std::uint32_t * thr_;
+};
+
+// The same draw from a word taken earlier (philox_stream::next_u32x4 hands out four at a time): the stream is not
+// touched.
+template<class IntType, int K>
+class table_discrete_of_word {
+public:
+    using result_type = IntType;
+    using input_type = double;
+
+    CPPROB_HD table_discrete_of_word(const std::uint32_t * thresholds, std::uint32_t word) : thr_(thresholds), r_(word) {}
+    CPPROB_HD IntType min() const { return 0; }
+    CPPROB_HD IntType max() const { return static_cast<IntType>(K - 1); }
+
+    template<class Rng>
+    CPPROB_HD result_type operator()(Rng &) const
+    {
+        int out = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int i = 0; i < K - 1; ++i) out += r_ >= thr_[i] ? 1 : 0;
+        return static_cast<IntType>(out);
+    }
+
+private:
+    const std::uint32_t * thr_;
+    std::uint32_t r_;
 };
 
 // -------------------------------------------------------------------------------------------------

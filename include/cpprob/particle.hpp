@@ -130,8 +130,9 @@ class particle {
 public:
     // `rng` is the stream this particle draws from; the two particles of a stream pair are run one
     // after the other on the same stream object (random/philox.hpp, "particle -> stream map").
-    CPPROB_HD particle(philox_stream & rng, Policy & policy)
-        : rng_(rng), log_w_(0.0), policy_(policy), default_address_("[model]"), observed_(false) {}
+    // `scratch`: the model's per-launch table (Model::fill_scratch, see invoke_model below), or nullptr
+    CPPROB_HD particle(philox_stream & rng, Policy & policy, const double * scratch = nullptr)
+        : rng_(rng), log_w_(0.0), policy_(policy), default_address_("[model]"), scratch_(scratch), observed_(false) {}
 
     // cpprob::sample(distr, control) — cpprob.hpp:68-76.  `control` is accepted and, as in the
     // reference's SIS branch (:72), has no effect.
@@ -166,6 +167,14 @@ public:
         // first observe stores instead of adding: in a straight-line model `observed_` is resolved at compile time and
         // an FP64 instruction per particle is saved (the fused kernel).  Where observes sit in a loop the flag is a
         // run-time select on every trip, so the default is the reference's plain `+=`.
+        increment_log_prob(lp);
+    }
+
+    // StateInfer::increment_log_prob (state.cpp:212-223): what `observe` does with the log-density.  Public so that a
+    // model with a per-launch table of log-densities (Model::fill_scratch: entries computed by the very same
+    // logpdf<D>()(distr, x) calls) can add an entry instead of re-evaluating it for every particle.
+    CPPROB_HD void increment_log_prob(const double lp)
+    {
         if (detail::first_observe_stores<Policy>::value) {
             log_w_ = observed_ ? log_w_ + lp : lp;
             observed_ = true;
@@ -173,6 +182,9 @@ public:
             log_w_ += lp;
         }
     }
+
+    // the model's per-launch table, or nullptr when the kernel has none (host probe, tables that do not fit)
+    CPPROB_HD const double * scratch() const { return scratch_; }
 
     // cpprob::predict(x, addr) — cpprob.hpp:92-98 -> StateInfer::add_predict, state.hpp:312-326.
 #if defined(__CUDACC__)
@@ -182,7 +194,7 @@ public:
              typename std::enable_if<std::is_integral<T>::value, int>::type = 0>
     CPPROB_HD void predict(T x, const String & addr)
     {
-        policy_.predict_int(static_cast<long long>(x), addr);
+        policy_.predict_int(x, addr);          // with its own width: 32-bit values keep 32-bit bookkeeping on the device
     }
 
 #if defined(__CUDACC__)
@@ -232,6 +244,7 @@ private:
     double log_w_;
     Policy & policy_;
     const char * default_address_;
+    const double * scratch_;
     bool observed_;
 };
 
@@ -274,6 +287,29 @@ template<class Model, class P>
 CPPROB_HD void set_address(P &, long) {}
 }  // namespace detail
 
+// -------------------------------------------------------------------------------------------------
+// Per-launch model tables.  A model may declare
+//     static CPPROB_HD int scratch_doubles(int n_obs);                         // size of its table
+//     static CPPROB_HD void fill_scratch(double * t, const double * obs, int n_obs, int first, int stride);
+// (entries first, first + stride, ... are filled by the caller: the kernels fill it cooperatively into shared
+// memory once per CTA) and read it back through particle::scratch().  Everything particle-invariant that the
+// reference recomputes for every trace — log-densities of the observations under each discrete state, sampler
+// thresholds — belongs there.  scratch() may be nullptr (host probe, tables beyond the shared-memory budget): the
+// model must then compute the same values inline.
+// -------------------------------------------------------------------------------------------------
+template<class Model, class = void>
+struct model_scratch {
+    static constexpr bool present = false;
+    CPPROB_HD static int doubles(int) { return 0; }
+    CPPROB_HD static void fill(double *, const double *, int, int, int) {}
+};
+template<class Model>
+struct model_scratch<Model, decltype(void(Model::scratch_doubles(0)))> {
+    static constexpr bool present = true;
+    CPPROB_HD static int doubles(int n_obs) { return Model::scratch_doubles(n_obs); }
+    CPPROB_HD static void fill(double * t, const double * obs, int n_obs, int first, int stride) { Model::fill_scratch(t, obs, n_obs, first, stride); }
+};
+
 template<class Model, class P>
 CPPROB_HD void invoke_model(const Model & m, P & p, const double * obs, int n_obs)
 {
@@ -312,7 +348,7 @@ public:
         ++out_.n_samples;
         return d(rng);
     }
-    template<class S> void predict_int(long long, const S & addr) { add(true, std::string(addr)); }
+    template<class T, class S> void predict_int(T, const S & addr) { add(true, std::string(addr)); }
     template<class S> void predict_real(double, const S & addr)
     {
         if (vector_left_ > 0) {          // component of a vector predict: one more row of the open slot

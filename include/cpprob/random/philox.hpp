@@ -23,6 +23,7 @@
 //
 // Word consumption rules (identical on host and device, they are part of the stream definition):
 //   * next_u32()      takes one 32-bit word from the current block (4 per block);
+//   * next_u32x4()    drops what is left of the current block and takes the whole next one;
 //   * next_uniform()  takes an aligned pair of words (52 random mantissa bits, result in (0,1));
 //   * next_std_normal() takes an aligned pair of words (a, b) and runs one ziggurat trial on them
 //     (8192 layers, tools/gen_ziggurat.py): layer = bits 3..15 of a, sign = bit 0 of a, u = (b : a >> 12)
@@ -116,6 +117,13 @@ CPPROB_HD double u52_to_open01(std::uint32_t hi_word, std::uint32_t lo_word)
     std::memcpy(&d, &bits, sizeof d);
 #endif
     return d - 0.99999999999999988897769753748434595763683319091796875;   // 1 - 2^-53 (exact)
+}
+// two 32-bit words stored in the bytes of one double slot of a model table (lo word first)
+CPPROB_HD void pack_u32_pair(double * slot, std::uint32_t lo, std::uint32_t hi)
+{
+    std::uint32_t * w = reinterpret_cast<std::uint32_t *>(slot);
+    w[0] = lo;
+    w[1] = hi;
 }
 }  // namespace detail
 
@@ -287,6 +295,16 @@ public:
         w0_ = w1_; w1_ = w2_; w2_ = w3_;
         ++pos_;
         return r;
+    }
+
+    // A whole block at once: the unread words of the current block are dropped and the four words of the next block
+    // are handed out together (the caller uses them in order).  For loops that draw one word per trip: taking them four
+    // at a time keeps the pool bookkeeping (position counter, refill test, shifts) out of the trip.
+    CPPROB_HD void next_u32x4(std::uint32_t (&w)[4])
+    {
+        philox4x32::block(s_lo_, s_hi_, blk_, tag_, keys_, w[0], w[1], w[2], w[3]);
+        ++blk_;
+        pos_ = 4;
     }
 
     // Uniform double in the open interval (0,1) with 52 random bits.

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define CPPROB_SIS_ABI_VERSION 1
+#define CPPROB_SIS_ABI_VERSION 2
 
 enum {
     CPPROB_SIS_OK = 0,
@@ -111,7 +111,14 @@ typedef struct cpprob_sis_stats {
     double device_ms;            /* CUDA-event time of the particle + reduction kernels of this call */
     uint64_t kernel_launches;    /* kernels launched by this call */
     int passes;                  /* 1, or 2 if m_ref had to be re-based */
+    int path;                    /* CPPROB_SIS_PATH_*: where the traces lived while the estimators were formed */
 } cpprob_sis_stats;
+
+enum {
+    CPPROB_SIS_PATH_FUSED = 0,   /* registers (k_sis_fused): <= 4 real predicts, no int predicts, nothing emitted */
+    CPPROB_SIS_PATH_STAGED = 1,  /* per-warp shared-memory staging areas (k_sis_staged): longer traces, nothing emitted */
+    CPPROB_SIS_PATH_ROWS = 2     /* SoA rows in HBM (k_sis_rows + k_rows_moments / k_rows_hist): emitting runs, very long traces */
+};
 
 enum {
     CPPROB_SIS_EMIT_NONE = 0,    /* estimators only: no trace leaves the GPU */

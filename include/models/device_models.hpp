@@ -104,23 +104,88 @@ struct hmm_model {
     static constexpr bool replayable = true;
     static constexpr bool draws_normals = false;   // uniform_smallint + discrete only: no ziggurat table needed
     static constexpr const char * name() { return "hmm"; }
+    static constexpr int k = 3;
+
+    using transition_t = ::cpprob::discrete_distribution<int, double, k>;
+    CPPROB_HD static ::cpprob::reg_table<double, k> state_means() { return ::cpprob::reg_table<double, k>{{-1, 0, 1}}; }
+    CPPROB_HD static transition_t transition_of(int s)
+    {
+        const ::cpprob::reg_table<::cpprob::reg_table<double, k>, k> T{{{{0.1, 0.5, 0.4}},
+                                                                      {{0.2, 0.2, 0.6}},
+                                                                      {{0.15, 0.15, 0.7}}}};
+        return transition_t{T[s]};
+    }
+
+    // Per-launch table (particle.hpp, "Per-launch model tables").  Everything the reference recomputes for every
+    // trace although it does not depend on the particle:
+    //   t[2 s], s < 3   : the two sampler thresholds of transition row s, as a pair of 32-bit words
+    //   t[8 + 4 i + s]  : logpdf<normal>()(normal(state_mean[s], 1), observed_states[i]) — the same call observe() makes,
+    //                     so the same bits (utils_normal_distribution.hpp:38-41 operation order)
+    // A step of a trace is then one table-row draw, one 8-byte load and one add.
+    static constexpr int kLpdfBase = 8, kLpdfStride = 4;
+    CPPROB_HD static int scratch_doubles(int n_obs) { return kLpdfBase + kLpdfStride * n_obs; }
+    CPPROB_HD static void fill_scratch(double * t, const double * obs, int n_obs, int first, int stride)
+    {
+        const ::cpprob::reg_table<double, k> state_mean = state_means();
+        for (int e = first; e < kLpdfBase + kLpdfStride * n_obs; e += stride) {
+            if (e < kLpdfBase) {
+                const transition_t tr = transition_of(e < k ? e : 0);
+                ::cpprob::detail::pack_u32_pair(t + e, e < k ? tr.thresholds()[0] : 0u, e < k ? tr.thresholds()[1] : 0u);
+                continue;
+            }
+            const int i = (e - kLpdfBase) / kLpdfStride, s = (e - kLpdfBase) % kLpdfStride;
+            double v = 0.0;
+            if (s < k) {
+                const ::cpprob::normal_distribution<> likelihood{state_mean[s], 1};
+                v = ::cpprob::logpdf<::cpprob::normal_distribution<>>()(likelihood, obs[i]);
+            }
+            t[e] = v;
+        }
+    }
 
     template<class P>
     CPPROB_HD void operator()(P & cpprob, const ::cpprob::obs_span<double> observed_states) const
     {
-        constexpr int k = 3;
-        const ::cpprob::reg_table<double, k> state_mean{{-1, 0, 1}};
-        const ::cpprob::reg_table<::cpprob::reg_table<double, k>, k> T{{{{0.1, 0.5, 0.4}},
-                                                                      {{0.2, 0.2, 0.6}},
-                                                                      {{0.15, 0.15, 0.7}}}};
+        const ::cpprob::uniform_smallint<int> prior{0, 2};
+        const double * const tab = cpprob.scratch();
+        if (tab != nullptr) {
+            // models.hpp:114-141 with the particle-invariant parts read from the table
+            const std::uint32_t * const thr = reinterpret_cast<const std::uint32_t *>(tab);
+            const double * lp = tab + kLpdfBase;
+            auto state = cpprob.sample(prior, true);
+            cpprob.predict(state, "State");
+            cpprob.increment_log_prob(lp[state]);
+            const int n = observed_states.size();
+            int i = 1;
+            // four steps per Philox block (philox_stream::next_u32x4), then the tail one word at a time
+            for (; i + 4 <= n; i += 4) {
+                std::uint32_t r[4];
+                cpprob.rng().next_u32x4(r);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+                for (int j = 0; j < 4; ++j) {
+                    lp += kLpdfStride;
+                    state = cpprob.sample(::cpprob::table_discrete_of_word<int, k>(thr + 2 * state, r[j]), true);
+                    cpprob.predict(state, "State");
+                    cpprob.increment_log_prob(lp[state]);
+                }
+            }
+            for (; i < n; ++i) {
+                lp += kLpdfStride;
+                state = cpprob.sample(::cpprob::table_discrete_distribution<int, k>(thr + 2 * state), true);
+                cpprob.predict(state, "State");
+                cpprob.increment_log_prob(lp[state]);
+            }
+            return;
+        }
+        const ::cpprob::reg_table<double, k> state_mean = state_means();
         // one transition distribution per row, built once per trace; the reference builds
         // `discrete_distribution{T[state].begin(), T[state].end()}` anew at every step (models.hpp:135), which
         // yields the same three objects
         // (the state is an `int` here, std::size_t in the reference: same values, same records, but 32-bit
         // compares on the device)
-        using transition_t = ::cpprob::discrete_distribution<int, double, k>;
-        const ::cpprob::reg_table<transition_t, k> transition{{transition_t{T[0]}, transition_t{T[1]}, transition_t{T[2]}}};
-        const ::cpprob::uniform_smallint<int> prior{0, 2};
+        const ::cpprob::reg_table<transition_t, k> transition{{transition_of(0), transition_of(1), transition_of(2)}};
         auto state = cpprob.sample(prior, true);
         cpprob.predict(state, "State");
         auto obs_it = observed_states.begin();

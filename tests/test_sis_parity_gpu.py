@@ -422,7 +422,7 @@ def test_c5_prefix_vs_forward_backward(engine):
     st = engine.run("hmm", obs, n)
     post, le = analytic.hmm_forward_backward(obs)
     tol = ess_tolerance(st, 1.0)
-    assert tol < 0.02
+    assert tol < 0.03
     np.testing.assert_allclose(st["int_prob"], post, atol=tol)
     assert abs(st["log_evidence"] - le) < 3 * tol
 
