@@ -78,24 +78,26 @@ __global__ void __launch_bounds__(kBlock) k_rows_moments(const double * __restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4b k_rows_hist<V>: weighted histogram sum_i w_i [x_i == lo + b], b < V, for 32 int rows of one sub-chunk, canonical
-// order as above (hist_round of staged_kernels.cuh).  1-D grid of n_sub_chunks * ceil(n_int / 32) CTAs.  V <= 8 bins live
-// in registers; wider windows are covered by several launches with shifted `lo` (bin_offset selects the output
-// columns).  States are staged as bytes relative to `lo`; anything outside [0, 255) is staged as 255 and matches no bin.
+// K4b k_rows_hist: weighted histogram sum_i w_i [x_i == lo + b], b < bins_here <= kRowsHistBins, for 32 int rows of one
+// sub-chunk, canonical order as above (hist_round of staged_kernels.cuh).  1-D grid of n_sub_chunks * ceil(n_int / 32)
+// CTAs.  Wider windows are covered by several launches with shifted `lo` (bin_offset selects the output columns).
+// States are staged as bytes relative to `lo`; anything outside [0, 255) is staged as 255 and matches no bin.
 // Output: partials[sub_chunk][hist_col0 + row*hist_bins + bin_offset + b].
 // ------------------------------------------------------------------------------------------------
-template<int V>
+constexpr int kRowsHistBins = 16;
+
 __global__ void __launch_bounds__(kBlock) k_rows_hist(const int * __restrict__ int_rows, const double * __restrict__ w,
                                                       unsigned long long stride, unsigned long long n_particles, int n_int,
-                                                      long long lo, int bin_offset, int hist_bins, int hist_col0,
+                                                      long long lo, int bin_offset, int bins_here, int hist_bins, int hist_col0,
                                                       double * __restrict__ partials, int n_cols)
 {
     __shared__ __align__(16) unsigned char stage_all[kWarps][32 * kStageIntStride];
     __shared__ __align__(16) double wst_all[kWarps][32];
-    __shared__ double slot_sums[kWarps][32][V];
+    __shared__ double acc_all[kWarps][32][kRowsHistBins + 1];
     const unsigned lane = threadIdx.x & 31u, slot = threadIdx.x >> 5;
     unsigned char * const stage = stage_all[slot];
     double * const wst = wst_all[slot];
+    double * const acc = acc_all[slot][lane];
     const unsigned n_groups = static_cast<unsigned>((n_int + 31) / 32);
     const unsigned c = blockIdx.x / n_groups;
     const int row0 = static_cast<int>(blockIdx.x % n_groups) * 32;
@@ -105,9 +107,7 @@ __global__ void __launch_bounds__(kBlock) k_rows_hist(const int * __restrict__ i
     const int rows_here = min(32, n_int - row0);
     const unsigned lo32 = static_cast<unsigned>(static_cast<int>(lo));
 
-    double h[V];
-#pragma unroll
-    for (int b = 0; b < V; ++b) h[b] = 0.0;
+    for (int b = 0; b <= bins_here; ++b) acc[b] = 0.0;
     for (unsigned round = 0; round < kSubChunk / kBlock; ++round) {
         const unsigned i0 = round * kBlock + slot * 32u;
         if (i0 >= n_here) break;
@@ -129,18 +129,16 @@ __global__ void __launch_bounds__(kBlock) k_rows_hist(const int * __restrict__ i
             }
         }
         __syncwarp();
-        hist_round<V>(stage + lane * kStageIntStride, wst, 0u, h);       // `lo` already is the first bin of this launch
+        hist_round(stage + lane * kStageIntStride, wst, static_cast<unsigned>(bins_here), acc);   // `lo` already is the first bin of this launch
         __syncwarp();
     }
-#pragma unroll
-    for (int b = 0; b < V; ++b) slot_sums[slot][lane][b] = h[b];
     __syncthreads();
-    for (unsigned t = threadIdx.x; t < 32u * V; t += kBlock) {
-        const unsigned q = t / V, b = t % V;
+    for (unsigned t = threadIdx.x; t < 32u * static_cast<unsigned>(bins_here); t += kBlock) {
+        const unsigned q = t / static_cast<unsigned>(bins_here), b = t % static_cast<unsigned>(bins_here);
         if (static_cast<int>(q) < rows_here && bin_offset + static_cast<int>(b) < hist_bins) {
-            double r = slot_sums[0][q][b];
+            double r = acc_all[0][q][b];
 #pragma unroll
-            for (unsigned sl = 1; sl < kWarps; ++sl) r = __dadd_rn(r, slot_sums[sl][q][b]);
+            for (unsigned sl = 1; sl < kWarps; ++sl) r = __dadd_rn(r, acc_all[sl][q][b]);       // slots in slot order
             partials[static_cast<size_t>(c) * n_cols + hist_col0 + (row0 + static_cast<int>(q)) * hist_bins + bin_offset + static_cast<int>(b)] = r;
         }
     }

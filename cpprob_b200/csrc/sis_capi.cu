@@ -235,14 +235,6 @@ struct hist_window {
     int bins = 0;
 };
 
-template<int V>
-cudaError_t launch_hist(cudaStream_t s, unsigned grid, int n_int, const int * rows, const double * w, unsigned long long stride,
-                        unsigned long long n, long long lo, int off, int bins, int col0, double * partials, int n_cols)
-{
-    k_rows_hist<V><<<grid, kBlock, 0, s>>>(rows, w, stride, n, n_int, lo, off, bins, col0, partials, n_cols);
-    return cudaGetLastError();
-}
-
 cudaError_t launch_rows_moments(cudaStream_t s, unsigned n_sub_chunks, const double * rows, const double * w, unsigned long long stride,
                                 unsigned long long n, int n_real, double * partials, int n_cols)
 {
@@ -253,27 +245,16 @@ cudaError_t launch_rows_moments(cudaStream_t s, unsigned n_sub_chunks, const dou
     return cudaGetLastError();
 }
 
-// all histogram passes for one batch; returns number of launches through *launches
+// all histogram passes for one batch (kRowsHistBins bins per launch); counts the launches in *launches
 cudaError_t launch_hist_all(cudaStream_t s, unsigned n_chunks, int n_int, const int * rows, const double * w,
                             unsigned long long stride, unsigned long long n, hist_window hw, int col0,
                             double * partials, int n_cols, uint64_t * launches)
 {
     const unsigned grid = n_chunks * static_cast<unsigned>((n_int + 31) / 32);        // one CTA per (sub-chunk, group of 32 rows)
-    for (int off = 0; off < hw.bins; off += 8) {
-        const int left = hw.bins - off;
-        cudaError_t err;
-        const long long lo = hw.lo + off;
-        switch (left >= 8 ? 8 : left) {
-        case 1: err = launch_hist<1>(s, grid, n_int, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        case 2: err = launch_hist<2>(s, grid, n_int, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        case 3: err = launch_hist<3>(s, grid, n_int, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        case 4: err = launch_hist<4>(s, grid, n_int, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        case 5: err = launch_hist<5>(s, grid, n_int, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        case 6: err = launch_hist<6>(s, grid, n_int, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        case 7: err = launch_hist<7>(s, grid, n_int, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        default: err = launch_hist<8>(s, grid, n_int, rows, w, stride, n, lo, off, hw.bins, col0, partials, n_cols); break;
-        }
-        if (err != cudaSuccess) return err;
+    for (int off = 0; off < hw.bins; off += kRowsHistBins) {
+        const int here = std::min(kRowsHistBins, hw.bins - off);
+        k_rows_hist<<<grid, kBlock, 0, s>>>(rows, w, stride, n, n_int, hw.lo + off, off, here, hw.bins, col0, partials, n_cols);
+        if (cudaError_t err = cudaGetLastError()) return err;
         ++*launches;
     }
     return cudaSuccess;

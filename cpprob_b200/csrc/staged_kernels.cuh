@@ -32,7 +32,7 @@ namespace engine {
 
 constexpr int kStageRealStride = 34;        // doubles per staged real row: 32 lanes + 2, so lane k's 128-bit reads of row k are conflict-free
 constexpr int kStageIntStride = 32;         // bytes per staged int row: one state byte per lane
-constexpr int kStagedMaxBins = 8;           // histogram bins the staged kernel keeps in registers
+constexpr int kStagedMaxBins = 64;          // widest histogram window the staged kernel takes (accumulators live in shared memory)
 // CTA size the staged kernel is compiled for (it is launched with as many warps as the staging areas allow, at most
 // this).  A model that draws normals carries the 64 KB ziggurat table, which leaves room for about 16 staging areas of a
 // 32-predict trace: 512 threads, and the 128 registers that go with them keep the normal sampler's state out of local
@@ -40,6 +40,10 @@ constexpr int kStagedMaxBins = 8;           // histogram bins the staged kernel 
 template<class Model>
 constexpr int staged_threads() { return model_draws_normals<Model>::value ? 512 : 1024; }
 constexpr unsigned kSmemBudget = 227u * 1024u;
+
+// doubles per row of histogram accumulators: the bins, a scratch slot for unmatched states, rounded up to an odd count
+// (see hist_round)
+__host__ __device__ constexpr unsigned hist_acc_stride(unsigned bins) { return (bins + 1u) | 1u; }
 
 // One warp's staging area.  All offsets are multiples of 16 bytes.
 struct stage_layout {
@@ -54,7 +58,7 @@ __host__ __device__ inline stage_layout make_stage_layout(int n_real, int n_int,
     o = (o + 15u) & ~15u;
     L.w_off = o;     o += 32u * 8u;
     L.macc_off = o;  o += static_cast<unsigned>(n_real) * 16u;
-    L.hacc_off = o;  o += static_cast<unsigned>(n_int) * static_cast<unsigned>(bins > 0 ? bins : 0) * 8u;
+    L.hacc_off = o;  o += static_cast<unsigned>(n_int) * (bins > 0 ? hist_acc_stride(static_cast<unsigned>(bins)) : 0u) * 8u;
     L.bytes = (o + 15u) & ~15u;
     return L;
 }
@@ -80,10 +84,16 @@ __device__ __forceinline__ void moments_round(const double * __restrict__ row, c
     }
 }
 
-// states are staged as bytes (value - window start); a byte that matches no bin (outside the window, or the 255 of a
-// lane beyond the end) adds nothing
-template<int V>
-__device__ __forceinline__ void hist_round(const unsigned char * __restrict__ row, const double * __restrict__ wst, unsigned first_bin, double (&h)[V])
+// States are staged as bytes (value - window start).  Lane k owns the accumulators of row k in shared memory and adds
+// each particle's weight to the one its state selects: one indexed load / add / store per (particle, row), whatever the
+// number of bins, and no data-dependent control flow.  (Accumulators in registers were tried first: `if (s == v) h[v] += w`
+// compiles to a branch around every add, on which the lanes of a warp — different rows — diverge; a predicated add
+// becomes an unconditional DADD plus two selects per (particle, bin), 15 issue slots per particle for 3 bins against 8
+// here.  profiles/r02_notes.md.)  A byte at or beyond `bins` (outside the window, or the 255 of a lane beyond the end) is
+// redirected to a scratch slot behind the row's accumulators.  acc: the hist_acc_stride(bins) doubles of this row; the
+// stride is odd, so the 32 lanes' accumulators of one bin fall into different banks.
+
+__device__ __forceinline__ void hist_round(const unsigned char * __restrict__ row, const double * __restrict__ wst, unsigned bins, double * __restrict__ acc)
 {
     const uint4 a = *reinterpret_cast<const uint4 *>(row), b = *reinterpret_cast<const uint4 *>(row + 16);
     const unsigned words[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -93,37 +103,32 @@ __device__ __forceinline__ void hist_round(const unsigned char * __restrict__ ro
         const double w[4] = {w01.x, w01.y, w23.x, w23.y};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const unsigned s = ((words[q] >> (8 * e)) & 0xffu) - first_bin;
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                if (s == static_cast<unsigned>(v)) h[v] = __dadd_rn(h[v], w[e]);   // empirical_distribution.hpp:30-40
-            }
+            const unsigned s = min((words[q] >> (8 * e)) & 0xffu, bins);
+            acc[s] = __dadd_rn(acc[s], w[e]);                    // empirical_distribution.hpp:30-40: sum of w over x == v
         }
     }
 }
 
-template<int V>
-__device__ __forceinline__ void hist_round_acc(const unsigned char * __restrict__ row, const double * __restrict__ wst, double * __restrict__ acc)
+// two rows of the same lane interleaved: their accumulator chains (load -> add -> store) are independent
+__device__ __forceinline__ void hist_round2(const unsigned char * __restrict__ row0, const unsigned char * __restrict__ row1,
+                                            const double * __restrict__ wst, unsigned bins, double * __restrict__ acc0, double * __restrict__ acc1)
 {
-    double h[V];
+    const uint4 a0 = *reinterpret_cast<const uint4 *>(row0), b0 = *reinterpret_cast<const uint4 *>(row0 + 16);
+    const uint4 a1 = *reinterpret_cast<const uint4 *>(row1), b1 = *reinterpret_cast<const uint4 *>(row1 + 16);
+    const unsigned w0[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
+    const unsigned w1[8] = {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-    for (int v = 0; v < V; ++v) h[v] = acc[v];
-    hist_round<V>(row, wst, 0u, h);
+    for (int q = 0; q < 8; ++q) {
+        const double2 w01 = *reinterpret_cast<const double2 *>(wst + 4 * q), w23 = *reinterpret_cast<const double2 *>(wst + 4 * q + 2);
+        const double w[4] = {w01.x, w01.y, w23.x, w23.y};
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = h[v];
-}
-
-__device__ __forceinline__ void hist_round_dispatch(int bins, const unsigned char * __restrict__ row, const double * __restrict__ wst, double * __restrict__ acc)
-{
-    switch (bins) {            // warp-uniform
-    case 1: hist_round_acc<1>(row, wst, acc); break;
-    case 2: hist_round_acc<2>(row, wst, acc); break;
-    case 3: hist_round_acc<3>(row, wst, acc); break;
-    case 4: hist_round_acc<4>(row, wst, acc); break;
-    case 5: hist_round_acc<5>(row, wst, acc); break;
-    case 6: hist_round_acc<6>(row, wst, acc); break;
-    case 7: hist_round_acc<7>(row, wst, acc); break;
-    default: hist_round_acc<8>(row, wst, acc); break;
+        for (int e = 0; e < 4; ++e) {
+            const unsigned s0 = min((w0[q] >> (8 * e)) & 0xffu, bins);
+            const unsigned s1 = min((w1[q] >> (8 * e)) & 0xffu, bins);
+            const double t0 = acc0[s0], t1 = acc1[s1];
+            acc0[s0] = __dadd_rn(t0, w[e]);
+            acc1[s1] = __dadd_rn(t1, w[e]);
+        }
     }
 }
 
@@ -196,7 +201,8 @@ __global__ void __launch_bounds__(staged_threads<Model>(), 1) k_sis_staged(const
         const unsigned n_here = left < kSubChunk ? static_cast<unsigned>(left) : kSubChunk;
 
         for (int k = static_cast<int>(lane); k < 2 * n_real; k += 32) macc[k] = 0.0;
-        for (int k = static_cast<int>(lane); k < n_int * bins; k += 32) hacc[k] = 0.0;
+        const int hstride = static_cast<int>(hist_acc_stride(static_cast<unsigned>(bins)));
+        for (int k = static_cast<int>(lane); k < n_int * hstride; k += 32) hacc[k] = 0.0;
         double max_lw = dm::neg_inf(), s0 = 0.0, s00 = 0.0;
         unsigned n_neginf = 0, n_nan = 0;
         int imin = 0x7fffffff, imax = static_cast<int>(0x80000000u);
@@ -238,8 +244,13 @@ __global__ void __launch_bounds__(staged_threads<Model>(), 1) k_sis_staged(const
                     macc[2 * k] = s1;
                     macc[2 * k + 1] = s2;
                 }
-                for (int k = static_cast<int>(lane); k < n_int; k += 32) {
-                    hist_round_dispatch(bins, stage_int + k * kStageIntStride, wst, hacc + k * bins);
+                {
+                    int k = static_cast<int>(lane);
+                    for (; k + 32 < n_int; k += 64) {
+                        hist_round2(stage_int + k * kStageIntStride, stage_int + (k + 32) * kStageIntStride, wst, static_cast<unsigned>(bins),
+                                    hacc + k * hstride, hacc + (k + 32) * hstride);
+                    }
+                    if (k < n_int) hist_round(stage_int + k * kStageIntStride, wst, static_cast<unsigned>(bins), hacc + k * hstride);
                 }
                 __syncwarp();
             }
@@ -272,7 +283,7 @@ __global__ void __launch_bounds__(staged_threads<Model>(), 1) k_sis_staged(const
         if (static_cast<int>(lane) < kBaseCols) out[lane] = mine;
         // ... and the row sums straight from the accumulators (already complete per row: no reduction over lanes)
         for (int k = static_cast<int>(lane); k < 2 * n_real; k += 32) out[kBaseCols + k] = macc[k];
-        for (int k = static_cast<int>(lane); k < n_int * bins; k += 32) out[kBaseCols + 2 * n_real + k] = hacc[k];
+        for (int k = static_cast<int>(lane); k < n_int * bins; k += 32) out[kBaseCols + 2 * n_real + k] = hacc[(k / bins) * hstride + k % bins];
         __syncwarp();
     }
 }

@@ -285,7 +285,14 @@ public:
     CPPROB_HD philox_stream(const philox_keys & keys, std::uint64_t stream, unsigned zig_base = 0, std::uint32_t stream_tag = 0)
         : keys_(keys), s_lo_(static_cast<std::uint32_t>(stream)), s_hi_(static_cast<std::uint32_t>(stream >> 32)),
           tag_(stream_tag), blk_(0), pos_(4), w0_(0), w1_(0), w2_(0), w3_(0), zig_base_(zig_base),
-          spare_(0.0), has_spare_(false) {}
+          spare_(0.0), has_spare_(false)
+    {
+#if CPPROB_ON_DEVICE
+        // keep the stream id in two registers: without this the compiler re-derives it from the kernel parameters
+        // (a dozen integer instructions) in front of every refill, i.e. every one or two draws of a long trace
+        asm volatile("" : "+r"(s_lo_), "+r"(s_hi_));
+#endif
+    }
 
     CPPROB_HD std::uint32_t next_u32()
     {
