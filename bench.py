@@ -179,7 +179,6 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from cpprob_b200 import Engine
-    from cpprob_b200.dist import gather_padded
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -200,39 +199,22 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    gathered_buf = {}
+    if world > 1:
+        # The library's own communicator (cpprob_sis_comm_init): rank 0 draws the NCCL id, torch.distributed is only the
+        # out-of-band transport for its 128 bytes.  From here on the data path is one library call per inference
+        # (cpprob_sis_run_dist): shard kernels, ONE ncclAllGather on the engine's stream, in-place merge, one host sync.
+        from cpprob_b200 import capi
+        id_t = torch.zeros(capi.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            id_t.copy_(torch.frombuffer(bytearray(capi.comm_get_id()), dtype=torch.uint8))
+        dist.broadcast(id_t, 0)
+        engine.comm_init(bytes(id_t.cpu().numpy().tobytes()), rank, world)
 
-    def step():
-        """One inference pass of `total` particles over `world` GPUs.  Returns (stats, kernel_ms, launches)."""
-        if world == 1:
-            # cpprob_sis_run: pilot, particle kernel, folds and merge queued back to back, one synchronisation
-            st = engine.run(MODEL, OBS, total)
-            return st, st["device_ms"], st["kernel_launches"]
-        m_ref = None
-        for _attempt in range(3):
-            p = engine.run_shard(MODEL, OBS, total, rank, world, m_ref=m_ref)
-            kernel_ms, launches = p.device_ms, p.kernel_launches
-            if world == 1:
-                ptr, n_chunks = p.device_ptr, p.n_chunks_total
-            else:
-                # the one collective of the path: all-gather of the per-(super-)chunk partial rows in rank order (NCCL over
-                # NVLink), straight from the engine's buffer; the engine compacts and merges the gathered segments
-                g, rows_per_rank = gather_padded(p, total, world, gathered_buf)
-                torch.cuda.synchronize()
-                st, rebase = engine.merge_padded(MODEL, OBS, g.data_ptr(), world, rows_per_rank, p.rows_per_chunk, p.n_cols, p.m_ref, total)
-                kernel_ms += st["device_ms"]
-                launches += st["kernel_launches"]
-                if not rebase:
-                    return st, kernel_ms, launches
-                m_ref = st["max_log_w"]
-                continue
-            st, rebase = engine.merge(MODEL, OBS, ptr, n_chunks, p.n_cols, p.m_ref, total)
-            kernel_ms += st["device_ms"]
-            launches += st["kernel_launches"]
-            if not rebase:
-                return st, kernel_ms, launches
-            m_ref = st["max_log_w"]
-        raise RuntimeError("weights could not be re-based")
+    def step(n_total=None):
+        """One inference pass of `n_total` particles over `world` GPUs.  Returns (stats, kernel_ms, launches)."""
+        n_total = total if n_total is None else n_total
+        st = engine.run(MODEL, OBS, n_total) if world == 1 else engine.run_dist(MODEL, OBS, n_total)
+        return st, st["device_ms"], st["kernel_launches"]
 
     for _ in range(args.warmup):
         step()
@@ -267,16 +249,37 @@ def run_ours(args):
     e2e_steps = max(3, min(args.steps, 10))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        if world == 1:
-            st_e2e = engine.run(MODEL, OBS, total)
-        else:
-            st_e2e, _, _ = step()
+        st_e2e, _, _ = step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = te.item()
+
+    # Strong scaling (BASELINE.json configs[1] reads "1e9 particles on 1/2/4/8 B200"): the SAME 1e9 particles split over
+    # the N GPUs, device-timed like the main figure; and a fingerprint of the merged sums of a fixed 2^30-particle run,
+    # which must be the same string for every N (results are bit-identical for any GPU count).
+    import hashlib
+    strong_n = args.strong_particles
+    for _ in range(3):
+        step(strong_n)
+    barrier()
+    s_ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    s_ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        torch.cuda.synchronize()
+        s_ev0[i].record()
+        step(strong_n)
+        s_ev1[i].record()
+    barrier()
+    ts = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(s_ev0, s_ev1))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+    strong_ms = ts.item() / args.steps
+    fp_st, _, _ = step(1 << 30)
+    sums_sha = hashlib.sha256(fp_st["sums"].tobytes()).hexdigest()[:16]
 
     if rank == 0:
         value = total * args.steps / (step_ms * 1e-3)
@@ -296,6 +299,11 @@ def run_ours(args):
                           "ess": last["ess"], "analytic_mean": 2.323529411764706, "analytic_variance": 1.0588235294117647,
                           "mean_err_in_mc_se": abs(float(last["real_mean"][0]) - 2.323529411764706) / (1.2973 / math.sqrt(total))},
             "kernel_ms_per_step": kernel_ms_total / args.steps,
+            "strong_scaling": {"total_particles": strong_n, "ms_per_step": strong_ms, "value": strong_n / (strong_ms * 1e-3), "unit": "particles/s",
+                               "note": "the same total split over the N GPUs (fixed total work); the main `value` is weak scaling"},
+            "sums_sha": {"particles": 1 << 30, "sha256_16": sums_sha,
+                         "note": "SHA-256 (first 16 hex digits) of the merged estimator sums of a 2^30-particle run: identical for every --gpus N"},
+            "collective": "none (1 GPU)" if world == 1 else "one ncclAllGather per inference inside libcpprob_sis.so (cpprob_sis_run_dist)",
         }
         if world == 1:
             peak_tflops, est_mhz = engine.dfma_peak()
@@ -396,7 +404,9 @@ def secondary_configs(engine, args):
     def files(label, model, obs, n, note):
         d = scratch_dir()
         with tempfile.TemporaryDirectory(dir=d) as tmp:
-            engine.infer_to_files(model, obs, max(n // 8, 1), os.path.join(tmp, "warm"))      # pinned buffers, page cache
+            engine.infer_to_files(model, obs, n, os.path.join(tmp, "warm"))      # same size: pinned / text buffers reach their final size
+            for f in os.listdir(tmp):
+                os.remove(os.path.join(tmp, f))
             prefix = os.path.join(tmp, "post")
             t0 = time.perf_counter()
             st = engine.infer_to_files(model, obs, n, prefix)
@@ -464,6 +474,7 @@ def main():
     ap.add_argument("--particles", type=int, default=1_000_000_000, help="particles per GPU per step")
     ap.add_argument("--cpu-particles", type=int, default=1_000_000, help="particles of the cpu_baseline sample")
     ap.add_argument("--ref-particles", type=int, default=50_000, help="particles per process per step of --impl reference")
+    ap.add_argument("--strong-particles", type=int, default=1_000_000_000, help="total particles of the strong-scaling extra")
     ap.add_argument("--no-configs", action="store_true", help="skip the C3/C4/C5/file-emission block")
     ap.add_argument("--c3-particles", type=int, default=100_000_000)
     ap.add_argument("--c4-particles", type=int, default=100_000_000)

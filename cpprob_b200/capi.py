@@ -28,7 +28,9 @@ SYMBOLS = [
     "cpprob_sis_sample", "cpprob_sis_philox", "cpprob_sis_dmath", "cpprob_sis_measure_dfma_peak",
     "cpprob_sis_measure_store_peak", "cpprob_sis_plan_shard", "cpprob_sis_probe_issue", "cpprob_sis_probe_dfma_chains", "cpprob_sis_run_multi", "cpprob_sis_write_summary",
     "cpprob_sis_text_stage_stats", "cpprob_sis_plan_rows", "cpprob_sis_merge_padded",
+    "cpprob_sis_comm_get_id", "cpprob_sis_comm_init", "cpprob_sis_comm_init_local", "cpprob_sis_comm_destroy", "cpprob_sis_run_dist",
 ]
+COMM_ID_BYTES = 128
 
 
 class Config(C.Structure):
@@ -116,6 +118,11 @@ def lib():
         L.cpprob_sis_measure_store_peak.argtypes = [C.c_void_p, dp]
         L.cpprob_sis_write_summary.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(Stats)]
         L.cpprob_sis_run_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, dp, C.c_size_t, u64, C.POINTER(Stats)]
+        L.cpprob_sis_comm_get_id.argtypes = [C.c_void_p]
+        L.cpprob_sis_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.cpprob_sis_comm_init_local.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.cpprob_sis_comm_destroy.argtypes = [C.c_void_p]
+        L.cpprob_sis_run_dist.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t, u64, C.POINTER(Stats)]
         L.cpprob_sis_text_stage_stats.argtypes = [C.c_void_p, dp, dp, dp, C.POINTER(u64), C.POINTER(u64)]
         L.cpprob_sis_probe_issue.argtypes = [C.c_void_p, C.c_int, dp]
         L.cpprob_sis_probe_dfma_chains.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, dp]
@@ -172,6 +179,19 @@ def stats_to_dict(st, structure=None):
     d["int_map"] = np.array([st.int_map[i] for i in range(st.n_int)], dtype=np.int64)
     d["sums"] = np.array([st.sums[i] for i in range(st.n_cols)])
     return d
+
+
+def comm_get_id():
+    """cpprob_sis_comm_get_id: the 128 bytes rank 0 hands to every rank of a new communicator."""
+    buf = (C.c_ubyte * COMM_ID_BYTES)()
+    _check(lib().cpprob_sis_comm_get_id(buf))
+    return bytes(buf)
+
+
+def comm_init_local(engines):
+    """cpprob_sis_comm_init_local: one process, one engine per GPU, rank r = engines[r]."""
+    arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    _check(lib().cpprob_sis_comm_init_local(arr, len(engines)))
 
 
 def run_multi(engines, model, obs, n):
@@ -265,6 +285,18 @@ class Engine:
         b, f = C.c_uint64(), C.c_uint64()
         _check(self._L.cpprob_sis_text_stage_stats(self._h, C.byref(k), C.byref(c), C.byref(w), C.byref(b), C.byref(f)))
         return {"kernel_ms": k.value, "copy_ms": c.value, "write_s": w.value, "bytes": b.value, "fixups": f.value}
+
+    def comm_init(self, comm_id, rank, world):
+        """cpprob_sis_comm_init (collective over the ranks of the new communicator)."""
+        buf = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(bytes(comm_id))
+        _check(self._L.cpprob_sis_comm_init(self._h, buf, rank, world))
+
+    def run_dist(self, model, obs, n_total):
+        """cpprob_sis_run_dist (collective): this rank's shard, one NCCL all-gather, the merge; bit-identical everywhere."""
+        obs = _f64(obs)
+        st = Stats()
+        _check(self._L.cpprob_sis_run_dist(self._h, self.model_id(model), _dptr(obs), obs.size, int(n_total), C.byref(st)))
+        return stats_to_dict(st)
 
     def run_shard(self, model, obs, n_total, rank, world, m_ref=None):
         obs = _f64(obs)

@@ -202,6 +202,37 @@ __global__ void __launch_bounds__(kBlock) k_merge_columns(const double * __restr
     if (threadIdx.x == 0) out[c] = res;
 }
 
+// The same merge straight from the output of an all-gather: `world` segments of rows_per_rank rows each, segment r
+// holding the first[r+1] - first[r] rows of rank r (the rest of a segment is padding that is never read).  Logical
+// row i lives at segment r = the rank that owns it, position i - first[r]; every thread walks its rows in the same
+// order as k_merge_columns, so the result has the same bits — no compaction copy in between.
+constexpr int kMaxMergeRanks = 64;
+struct gather_layout {
+    unsigned first[kMaxMergeRanks + 1];      // first[r] = index of rank r's first logical row; first[world] = total rows
+    unsigned world;
+    unsigned rows_per_rank;
+};
+
+__global__ void __launch_bounds__(kBlock) k_merge_columns_gathered(const double * __restrict__ gathered, const __grid_constant__ gather_layout lay,
+                                                                   int n_cols, unsigned long long max_mask, double * __restrict__ out)
+{
+    __shared__ double smem[kWarps];
+    const int c = blockIdx.x;
+    const bool is_max = c < 64 && ((max_mask >> c) & 1ull);
+    const unsigned n_rows = lay.first[lay.world];
+    double v[1];
+    v[0] = is_max ? dm::neg_inf() : 0.0;
+    unsigned rank = 0;
+    for (unsigned r = threadIdx.x; r < n_rows; r += kBlock) {
+        while (r >= lay.first[rank + 1]) ++rank;                  // rows only grow: the owner is found by walking on
+        const size_t phys = static_cast<size_t>(rank) * lay.rows_per_rank + (r - lay.first[rank]);
+        const double x = gathered[phys * n_cols + c];
+        v[0] = is_max ? fmax(v[0], x) : v[0] + x;
+    }
+    const double res = block_reduce<1>(v, is_max ? 1ull : 0ull, smem);
+    if (threadIdx.x == 0) out[c] = res;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K3 k_row_base: weights w = exp(log_w - m_ref) and the base sums of one sub-chunk from its log_w
 // column (16 B of HBM traffic per particle).  Used after k_sis_rows and for externally supplied

@@ -18,6 +18,8 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>            // types only: the library is opened at run time (nccl_api below), never linked
 
 #include "cpprob_sis.h"
 #include "dist_kernels.cuh"
@@ -108,6 +110,66 @@ struct pinned_buffer {
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// NCCL, opened at run time.  libcpprob_sis.so does not link against it: a single-GPU user needs no NCCL at all, and
+// a process that already has one loaded (torch.distributed ships its own libnccl.so.2) must share that one.
+// ------------------------------------------------------------------------------------------------
+struct nccl_api {
+    void * handle = nullptr;
+    ncclResult_t (*GetVersion)(int *) = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char * (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string why;         // set when loading failed
+};
+
+const nccl_api & nccl()
+{
+    static const nccl_api api = [] {
+        nccl_api a;
+        const char * names[] = {std::getenv("CPPROB_SIS_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char * n : names) {
+            if (!n || !*n) continue;
+            a.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (a.handle) break;
+        }
+        if (!a.handle) {
+            a.why = std::string("NCCL could not be opened (libnccl.so.2): ") + (dlerror() ? dlerror() : "not found");
+            return a;
+        }
+        bool ok = true;
+        auto sym = [&](const char * name) { void * p = dlsym(a.handle, name); ok = ok && p != nullptr; return p; };
+        a.GetVersion = reinterpret_cast<decltype(a.GetVersion)>(sym("ncclGetVersion"));
+        a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(sym("ncclGetUniqueId"));
+        a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(sym("ncclCommInitRank"));
+        a.CommInitAll = reinterpret_cast<decltype(a.CommInitAll)>(sym("ncclCommInitAll"));
+        a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
+        a.AllGather = reinterpret_cast<decltype(a.AllGather)>(sym("ncclAllGather"));
+        a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(sym("ncclGroupStart"));
+        a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
+        a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
+        if (!ok) {
+            a.why = "the NCCL library that was found lacks an entry point this engine needs";
+            a.handle = nullptr;
+        }
+        return a;
+    }();
+    return api;
+}
+
+#define NCCL_TRY(expr)                                                                                         \
+    do {                                                                                                       \
+        const ncclResult_t nccl_try_res = (expr);                                                              \
+        if (nccl_try_res != ncclSuccess) {                                                                     \
+            return fail(CPPROB_SIS_ENCCL, std::string(#expr) + ": " + nccl().GetErrorString(nccl_try_res));    \
+        }                                                                                                      \
+    } while (0)
+
 }  // namespace
 
 struct cpprob_sis_engine {
@@ -140,6 +202,10 @@ struct cpprob_sis_engine {
     uint64_t text_bytes = 0, text_fixups = 0;
     pinned_buffer<double> h_real[2], h_logw[2], h_merged, h_pilot;
     pinned_buffer<int> h_int[2];
+
+    // communicator of a multi-GPU run (cpprob_sis_comm_init / _init_local); rank 0 of 1 without one
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
 
     // results kept alive for the caller
     model_structure structure;
@@ -790,13 +856,17 @@ constexpr double kRebaseLimit = 300.0;
 // device time are collected here, after the one synchronisation of the inference.
 int merge_impl(cpprob_sis_engine * e, const double * gathered, uint32_t n_chunks, int n_cols, int n_real, int n_int,
                hist_window hw, double m_ref, uint64_t n_total, cpprob_sis_stats * out, uint64_t * launches, double * ms_out,
-               shard_result * pending = nullptr)
+               shard_result * pending = nullptr, const gather_layout * layout = nullptr)
 {
     if (n_cols != kBaseCols + 2 * n_real + n_int * hw.bins) return fail(CPPROB_SIS_EINVAL, "n_cols does not match the model structure");
     CU_TRY(e->d_merged.reserve(static_cast<size_t>(n_cols)));
     CU_TRY(e->h_merged.reserve(static_cast<size_t>(n_cols)));
     CU_TRY(cudaEventRecord(e->ev_merge_begin, e->compute));
-    k_merge_columns<<<n_cols, kBlock, 0, e->compute>>>(gathered, n_chunks, n_cols, kMaxColsMask, e->d_merged.ptr);
+    if (layout) {        // the raw output of an all-gather: read in place (k_merge_columns_gathered)
+        k_merge_columns_gathered<<<n_cols, kBlock, 0, e->compute>>>(gathered, *layout, n_cols, kMaxColsMask, e->d_merged.ptr);
+    } else {
+        k_merge_columns<<<n_cols, kBlock, 0, e->compute>>>(gathered, n_chunks, n_cols, kMaxColsMask, e->d_merged.ptr);
+    }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(e->ev_merge_end, e->compute));
     ++*launches;
@@ -936,6 +1006,9 @@ int run_full(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, const do
 // ================================================================================================
 extern "C" {
 
+static int merge_gathered(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs, const double * gathered,
+                          const gather_layout * lay, int n_cols, double m_ref, uint64_t n_particles_total, cpprob_sis_stats * out);
+
 int cpprob_sis_abi_version(void) { return CPPROB_SIS_ABI_VERSION; }
 
 const char * cpprob_sis_last_error(void) { return g_last_error.c_str(); }
@@ -1058,6 +1131,7 @@ int cpprob_sis_create(const cpprob_sis_config * cfg, cpprob_sis_engine ** out)
 void cpprob_sis_destroy(cpprob_sis_engine * e)
 {
     if (!e) return;
+    cpprob_sis_comm_destroy(e);
     cudaSetDevice(e->device);
     if (e->compute) cudaStreamSynchronize(e->compute);
     if (e->copy) cudaStreamSynchronize(e->copy);
@@ -1161,68 +1235,130 @@ int cpprob_sis_write_summary(cpprob_sis_engine * e, const char * prefix, const c
     return 0;
 }
 
-int cpprob_sis_run_multi(cpprob_sis_engine * const * engines, int n_engines, int model_id, const double * obs, size_t n_obs,
-                         uint64_t n_particles, cpprob_sis_stats * out)
+// ---- multi-GPU inside the library ------------------------------------------------------------------------------------
+namespace {
+
+// the rows every rank owns (host arithmetic, identical on every rank) as the layout of the gathered buffer
+int make_gather_layout(uint64_t n_total, int world, int rows_per_chunk, gather_layout * lay)
 {
-    if (!engines || n_engines <= 0 || !obs || !out) return fail(CPPROB_SIS_EINVAL, "bad argument");
-    for (int r = 0; r < n_engines; ++r) {
-        if (!engines[r]) return fail(CPPROB_SIS_EINVAL, "null engine");
-        if (engines[r]->seed != engines[0]->seed) return fail(CPPROB_SIS_EINVAL, "all engines of a multi-GPU run must share one seed");
+    if (world > kMaxMergeRanks) return fail(CPPROB_SIS_EINVAL, "more than 64 ranks");
+    uint32_t seen = 0, most = 0, total = 0;
+    for (int r = 0; r < world; ++r) {
+        uint32_t first = 0, n_local = 0;
+        if (int rc = cpprob_sis_plan_rows(n_total, r, world, rows_per_chunk, &first, &n_local, &total)) return rc;
+        if (first != seen) return fail(CPPROB_SIS_EINVAL, "inconsistent row plan");
+        lay->first[r] = first;
+        seen += n_local;
+        most = std::max(most, n_local);
     }
-    const cpprob_sis_model_vtable * vt = model_of(model_id);
-    if (!vt) return fail(CPPROB_SIS_ENOMODEL, "unknown model id");
-    cpprob_sis_engine * primary = engines[0];
+    lay->first[world] = seen;
+    lay->world = static_cast<unsigned>(world);
+    lay->rows_per_rank = std::max<uint32_t>(most, 1u);
+    return 0;
+}
+
+// One inference over the ranks of a communicator.  `local`: the engines of THIS process (one per GPU; one in the usual
+// process-per-GPU set-up), each carrying its rank of the same communicator.  Every rank queues its shard, the ONE
+// collective of the path — an all-gather of the per-(super-)chunk partial rows, straight from the buffer the shard
+// kernels wrote — and the merge on its own stream; the host synchronises once, on local[0], whose engine owns the results.
+// Re-basing / a wider histogram window repeat the pass on every rank alike (the decision is a function of the merged
+// sums, which are bit-identical everywhere).
+int run_dist_impl(cpprob_sis_engine * const * local, int n_local, const cpprob_sis_model_vtable * vt, const double * obs, size_t n_obs,
+                  uint64_t n_total, cpprob_sis_stats * out)
+{
+    const nccl_api & nc = nccl();
+    const int world = local[0]->comm_world;
+    if (world > 1 && !nc.handle) return fail(CPPROB_SIS_ENCCL, nc.why);
+    for (int i = 0; i < n_local; ++i) {
+        if (world > 1 && !local[i]->comm) return fail(CPPROB_SIS_EINVAL, "engine has no communicator (cpprob_sis_comm_init)");
+        if (local[i]->comm_world != world) return fail(CPPROB_SIS_EINVAL, "engines belong to different communicators");
+        if (local[i]->seed != local[0]->seed) return fail(CPPROB_SIS_EINVAL, "all engines of a multi-GPU run must share one seed");
+    }
+    cpprob_sis_engine * primary = local[0];
     double m_ref_override = 0.0;
     const double * mo = nullptr;
+    hist_window hw_override;
+    const hist_window * ho = nullptr;
     double total_ms = 0.0;
     uint64_t launches = 0;
+    std::vector<shard_result> res(static_cast<size_t>(n_local));
     for (int pass = 1;; ++pass) {
-        // one host thread per GPU; every shard leaves its partial rows in its own engine
-        std::vector<shard_result> res(static_cast<size_t>(n_engines));
-        std::vector<int> rc(static_cast<size_t>(n_engines), 0);
-        std::vector<std::string> msg(static_cast<size_t>(n_engines));
-        std::vector<std::thread> pool;
-        for (int r = 0; r < n_engines; ++r) {
-            pool.emplace_back([&, r] {
-                shard_options so;
-                rc[static_cast<size_t>(r)] = run_shard_impl(engines[r], vt, obs, n_obs, n_particles, r, n_engines, mo, nullptr, so, &res[static_cast<size_t>(r)]);
-                if (rc[static_cast<size_t>(r)] != 0) msg[static_cast<size_t>(r)] = g_last_error;   // thread-local: carry it out
-            });
+        shard_options so;
+        so.no_wait = true;
+        for (int i = 0; i < n_local; ++i) {
+            res[static_cast<size_t>(i)] = shard_result();
+            if (int rc = run_shard_impl(local[i], vt, obs, n_obs, n_total, local[i]->comm_rank, world, mo, ho, so, &res[static_cast<size_t>(i)])) return rc;
+            launches += res[static_cast<size_t>(i)].launches;
         }
-        for (auto & t : pool) t.join();
-        for (int r = 0; r < n_engines; ++r) {
-            if (rc[static_cast<size_t>(r)] != 0) return fail(rc[static_cast<size_t>(r)], "device " + std::to_string(engines[r]->device) + ": " + msg[static_cast<size_t>(r)]);
+        const shard_result & r0 = res[0];
+        const int n_cols = r0.n_cols;
+        gather_layout lay;
+        if (int rc = make_gather_layout(n_total, world, static_cast<int>(r0.rows_per_chunk), &lay)) return rc;
+        const size_t count = static_cast<size_t>(lay.rows_per_rank) * n_cols;
+        const double * merged_from = nullptr;
+        if (world > 1) {
+            if (n_local > 1) NCCL_TRY(nc.GroupStart());
+            for (int i = 0; i < n_local; ++i) {
+                cpprob_sis_engine * e = local[i];
+                if (int rc = use_device(e)) return rc;
+                CU_TRY(e->d_gather.reserve(count * static_cast<size_t>(world)));
+                const double * send = res[static_cast<size_t>(i)].rows;
+                if (!send) {                       // a rank without particles still takes part; its segment is never read
+                    CU_TRY(e->d_partials.reserve(count + static_cast<size_t>(n_cols)));
+                    send = e->d_partials.ptr;
+                }
+                NCCL_TRY(nc.AllGather(send, e->d_gather.ptr, count, ncclDouble, e->comm, e->compute));
+            }
+            if (n_local > 1) NCCL_TRY(nc.GroupEnd());
+            merged_from = primary->d_gather.ptr;
         }
-        // gather in rank order on the primary GPU (peer copies over NVLink), then the usual merge
-        if (int rc0 = use_device(primary)) return rc0;
-        const int n_cols = res[0].n_cols;
-        const uint32_t rows_total = res[0].n_rows_total;
-        CU_TRY(primary->d_gather.reserve(static_cast<size_t>(rows_total) * n_cols));
-        double shard_ms = 0.0;
-        for (int r = 0; r < n_engines; ++r) {
-            const shard_result & sr = res[static_cast<size_t>(r)];
-            shard_ms = std::max(shard_ms, sr.device_ms);
-            launches += sr.launches;
-            if (sr.n_rows_local == 0) continue;
-            CU_TRY(cudaMemcpyPeerAsync(primary->d_gather.ptr + static_cast<size_t>(sr.row_first) * n_cols, primary->device,
-                                       sr.rows, engines[r]->device,
-                                       static_cast<size_t>(sr.n_rows_local) * n_cols * sizeof(double), primary->compute));
-        }
+        if (int rc = use_device(primary)) return rc;
         double merge_ms = 0.0;
-        const int mrc = merge_impl(primary, primary->d_gather.ptr, rows_total, n_cols, static_cast<int>(primary->structure.n_real),
-                                   static_cast<int>(primary->structure.n_int), res[0].hw, res[0].m_ref, n_particles, out, &launches, &merge_ms);
-        if (mrc < 0) return mrc;
-        total_ms += shard_ms + merge_ms;
-        if (primary->structure.n_int > 0 && out->sums[col::int_oor] != 0.0) {
-            return fail(CPPROB_SIS_ERANGE, "int predicts fell outside the pilot's histogram window");
+        int mrc;
+        if (world > 1) {
+            mrc = merge_impl(primary, merged_from, lay.first[world], n_cols, static_cast<int>(primary->structure.n_real),
+                             static_cast<int>(primary->structure.n_int), r0.hw, r0.m_ref, n_total, out, &launches, &merge_ms, &res[0], &lay);
+        } else {
+            mrc = merge_impl(primary, r0.rows, r0.n_rows_total, n_cols, static_cast<int>(primary->structure.n_real),
+                             static_cast<int>(primary->structure.n_int), r0.hw, r0.m_ref, n_total, out, &launches, &merge_ms, &res[0]);
         }
+        if (mrc < 0) return mrc;
+        // the other local engines only have to finish (their device time is taken after the fact; max over ranks)
+        double shard_ms = res[0].device_ms;
+        for (int i = 1; i < n_local; ++i) {
+            cpprob_sis_engine * e = local[i];
+            if (int rc = use_device(e)) return rc;
+            CU_TRY(cudaStreamSynchronize(e->compute));
+            if (res[static_cast<size_t>(i)].waiting) {
+                float ms = 0.f;
+                CU_TRY(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));
+                res[static_cast<size_t>(i)].device_ms = ms;
+                res[static_cast<size_t>(i)].waiting = false;
+            }
+            shard_ms = std::max(shard_ms, res[static_cast<size_t>(i)].device_ms);
+        }
+        total_ms += shard_ms + merge_ms;
+        bool again = false;
         if (mrc == 1 && pass < 3) {
             m_ref_override = out->max_log_w;
             mo = &m_ref_override;
-            continue;
+            again = true;
         }
-        out->passes = pass;
-        break;
+        hist_window hw = r0.hw;
+        if (pass < 3 && widen_window(*out, static_cast<int>(primary->structure.n_int), &hw)) {
+            if (hw.bins > 4096) return fail(CPPROB_SIS_ERANGE, "int predicts span more than 4096 values");
+            hw_override = hw;
+            ho = &hw_override;
+            again = true;
+        }
+        if (!again) {
+            if (primary->structure.n_int > 0 && out->sums[col::int_oor] != 0.0) {
+                return fail(CPPROB_SIS_ERANGE, "int predicts fell outside the histogram window");
+            }
+            out->passes = pass;
+            out->path = r0.path;
+            break;
+        }
     }
     out->device_ms = total_ms;
     out->kernel_launches = launches;
@@ -1230,31 +1366,126 @@ int cpprob_sis_run_multi(cpprob_sis_engine * const * engines, int n_engines, int
     return 0;
 }
 
+}  // namespace
+
+int cpprob_sis_comm_get_id(void * id_out)
+{
+    if (!id_out) return fail(CPPROB_SIS_EINVAL, "null argument");
+    const nccl_api & nc = nccl();
+    if (!nc.handle) return fail(CPPROB_SIS_ENCCL, nc.why);
+    static_assert(sizeof(ncclUniqueId) == CPPROB_SIS_COMM_ID_BYTES, "cpprob_sis.h states the size of an NCCL unique id");
+    ncclUniqueId id;
+    NCCL_TRY(nc.GetUniqueId(&id));
+    std::memcpy(id_out, &id, sizeof id);
+    return 0;
+}
+
+int cpprob_sis_comm_init(cpprob_sis_engine * e, const void * id_in, int rank, int world)
+{
+    if (!e || !id_in || world <= 0 || rank < 0 || rank >= world) return fail(CPPROB_SIS_EINVAL, "bad argument");
+    if (world > kMaxMergeRanks) return fail(CPPROB_SIS_EINVAL, "more than 64 ranks");
+    const nccl_api & nc = nccl();
+    if (!nc.handle) return fail(CPPROB_SIS_ENCCL, nc.why);
+    if (int rc = cpprob_sis_comm_destroy(e)) return rc;
+    if (int rc = use_device(e)) return rc;
+    ncclUniqueId id;
+    std::memcpy(&id, id_in, sizeof id);
+    NCCL_TRY(nc.CommInitRank(&e->comm, world, id, rank));
+    e->comm_rank = rank;
+    e->comm_world = world;
+    return 0;
+}
+
+int cpprob_sis_comm_init_local(cpprob_sis_engine * const * engines, int n_engines)
+{
+    if (!engines || n_engines <= 0 || n_engines > kMaxMergeRanks) return fail(CPPROB_SIS_EINVAL, "bad argument");
+    std::vector<int> devs;
+    for (int r = 0; r < n_engines; ++r) {
+        if (!engines[r]) return fail(CPPROB_SIS_EINVAL, "null engine");
+        for (int d : devs) if (d == engines[r]->device) return fail(CPPROB_SIS_EINVAL, "two engines on one device cannot share a local communicator");
+        devs.push_back(engines[r]->device);
+        if (int rc = cpprob_sis_comm_destroy(engines[r])) return rc;
+    }
+    if (n_engines == 1) return 0;                       // rank 0 of 1 needs no communicator
+    const nccl_api & nc = nccl();
+    if (!nc.handle) return fail(CPPROB_SIS_ENCCL, nc.why);
+    std::vector<ncclComm_t> comms(static_cast<size_t>(n_engines));
+    NCCL_TRY(nc.CommInitAll(comms.data(), n_engines, devs.data()));
+    for (int r = 0; r < n_engines; ++r) {
+        engines[r]->comm = comms[static_cast<size_t>(r)];
+        engines[r]->comm_rank = r;
+        engines[r]->comm_world = n_engines;
+    }
+    return 0;
+}
+
+int cpprob_sis_comm_destroy(cpprob_sis_engine * e)
+{
+    if (!e) return fail(CPPROB_SIS_EINVAL, "null engine");
+    if (e->comm) {
+        cudaSetDevice(e->device);
+        if (e->compute) cudaStreamSynchronize(e->compute);
+        nccl().CommDestroy(e->comm);
+        e->comm = nullptr;
+    }
+    e->comm_rank = 0;
+    e->comm_world = 1;
+    return 0;
+}
+
+int cpprob_sis_run_dist(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs, uint64_t n_particles_total, cpprob_sis_stats * out)
+{
+    if (!e || !obs || !out) return fail(CPPROB_SIS_EINVAL, "null argument");
+    const cpprob_sis_model_vtable * vt = model_of(model_id);
+    if (!vt) return fail(CPPROB_SIS_ENOMODEL, "unknown model id");
+    return run_dist_impl(&e, 1, vt, obs, n_obs, n_particles_total, out);
+}
+
+int cpprob_sis_run_multi(cpprob_sis_engine * const * engines, int n_engines, int model_id, const double * obs, size_t n_obs,
+                         uint64_t n_particles, cpprob_sis_stats * out)
+{
+    if (!engines || n_engines <= 0 || !obs || !out) return fail(CPPROB_SIS_EINVAL, "bad argument");
+    for (int r = 0; r < n_engines; ++r) if (!engines[r]) return fail(CPPROB_SIS_EINVAL, "null engine");
+    const cpprob_sis_model_vtable * vt = model_of(model_id);
+    if (!vt) return fail(CPPROB_SIS_ENOMODEL, "unknown model id");
+    // the engines need one communicator among themselves, rank r = position in the list; made on first use and kept
+    bool ready = true;
+    for (int r = 0; r < n_engines; ++r) ready = ready && engines[r]->comm_world == n_engines && engines[r]->comm_rank == r && (n_engines == 1 || engines[r]->comm);
+    if (!ready) {
+        if (int rc = cpprob_sis_comm_init_local(engines, n_engines)) return rc;
+    }
+    return run_dist_impl(engines, n_engines, vt, obs, n_obs, n_particles, out);
+}
+
 int cpprob_sis_merge_padded(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs, const double * gathered,
                             int world, uint32_t rows_per_rank, int rows_per_chunk, int n_cols, double m_ref,
                             uint64_t n_particles_total, cpprob_sis_stats * out)
 {
-    if (!e || !gathered || world <= 0 || n_cols <= 0) return fail(CPPROB_SIS_EINVAL, "bad argument");
-    if (int rc = use_device(e)) return rc;
-    // rank r's rows sit at gathered[r * rows_per_rank ...]; its count is host arithmetic (cpprob_sis_plan_rows)
-    uint32_t n_total_rows = 0, seen = 0;
+    if (!e || !gathered || !obs || !out || world <= 0 || n_cols <= 0) return fail(CPPROB_SIS_EINVAL, "bad argument");
+    gather_layout lay;
+    if (int rc = make_gather_layout(n_particles_total, world, rows_per_chunk, &lay)) return rc;
     for (int r = 0; r < world; ++r) {
-        uint32_t first = 0, n_local = 0;
-        if (int rc = cpprob_sis_plan_rows(n_particles_total, r, world, rows_per_chunk, &first, &n_local, &n_total_rows)) return rc;
-        if (n_local > rows_per_rank || first != seen) return fail(CPPROB_SIS_EINVAL, "rows_per_rank is smaller than a rank's row count");
-        if (r == 0) CU_TRY(e->d_gather.reserve(static_cast<size_t>(n_total_rows) * n_cols));
-        if (n_local) {
-            CU_TRY(cudaMemcpyAsync(e->d_gather.ptr + static_cast<size_t>(first) * n_cols, gathered + static_cast<size_t>(r) * rows_per_rank * n_cols,
-                                   static_cast<size_t>(n_local) * n_cols * sizeof(double), cudaMemcpyDeviceToDevice, e->compute));
-        }
-        seen += n_local;
+        if (lay.first[r + 1] - lay.first[r] > rows_per_rank) return fail(CPPROB_SIS_EINVAL, "rows_per_rank is smaller than a rank's row count");
     }
-    return cpprob_sis_merge(e, model_id, obs, n_obs, e->d_gather.ptr, n_total_rows, n_cols, m_ref, n_particles_total, out);
+    lay.rows_per_rank = rows_per_rank;
+    return merge_gathered(e, model_id, obs, n_obs, gathered, &lay, n_cols, m_ref, n_particles_total, out);
 }
 
 int cpprob_sis_merge(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs, const double * gathered,
                      uint32_t n_chunks_total, int n_cols, double m_ref, uint64_t n_particles_total, cpprob_sis_stats * out)
 {
+    gather_layout lay;                       // one segment holding every row
+    lay.world = 1;
+    lay.first[0] = 0;
+    lay.first[1] = n_chunks_total;
+    lay.rows_per_rank = n_chunks_total;
+    return merge_gathered(e, model_id, obs, n_obs, gathered, &lay, n_cols, m_ref, n_particles_total, out);
+}
+
+static int merge_gathered(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs, const double * gathered,
+                          const gather_layout * lay, int n_cols, double m_ref, uint64_t n_particles_total, cpprob_sis_stats * out)
+{
+    const uint32_t n_chunks_total = lay->first[lay->world];
     if (!e || !out || !obs || !gathered) return fail(CPPROB_SIS_EINVAL, "null argument");
     const cpprob_sis_model_vtable * vt = model_of(model_id);
     if (!vt) return fail(CPPROB_SIS_ENOMODEL, "unknown model id");
@@ -1277,7 +1508,8 @@ int cpprob_sis_merge(cpprob_sis_engine * e, int model_id, const double * obs, si
     }
     uint64_t launches = 0;
     double ms = 0.0;
-    const int rc = merge_impl(e, gathered, n_chunks_total, n_cols, n_real, n_int, hw, m_ref, n_particles_total, out, &launches, &ms);
+    const int rc = merge_impl(e, gathered, n_chunks_total, n_cols, n_real, n_int, hw, m_ref, n_particles_total, out, &launches, &ms, nullptr,
+                              lay->world > 1 ? lay : nullptr);
     if (rc < 0) return rc;
     if (n_int > 0 && out->sums[col::int_oor] != 0.0) {
         return fail(CPPROB_SIS_ERANGE, "int predicts fell outside the pilot's histogram window");

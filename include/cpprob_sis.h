@@ -29,7 +29,8 @@ enum {
     CPPROB_SIS_ENOMODEL = -3,  /* unknown model id / name */
     CPPROB_SIS_EIO = -4,       /* posterior file could not be written */
     CPPROB_SIS_ERANGE = -5,    /* int predict window too wide for the on-device histogram */
-    CPPROB_SIS_ENOMEM = -6
+    CPPROB_SIS_ENOMEM = -6,
+    CPPROB_SIS_ENCCL = -7      /* NCCL missing or an NCCL call failed (multi-GPU entry points only) */
 };
 
 typedef struct cpprob_sis_engine cpprob_sis_engine;
@@ -209,10 +210,30 @@ int cpprob_sis_run_shard(cpprob_sis_engine * e, int model_id, const double * obs
                          const double * m_ref_override /* NULL: pilot */,
                          cpprob_sis_partials * out);
 
-/* Single-process form of the same scheme: engines[r] (one per GPU, created by the caller with ONE seed) runs shard r
- * on its own host thread; the partial rows are copied peer-to-peer to engines[0]'s GPU in rank order and merged
- * there.  Estimators only (no trace emission).  Results are owned by engines[0] and are bit-identical to a
- * single-GPU run of the same seed. */
+/* ---- multi-GPU inside the library: one NCCL all-gather per inference -------------------------------------------------
+ * north_star: "each rank reduces locally, and one small NCCL [collective] over NVLink combines the global max
+ * log-weight, the sum of exp-weights and the weighted moment sums".  The collective is an all-gather of the per-
+ * (super-)chunk partial rows (<= 4096 rows of n_cols doubles in all) on the engine's own stream, right behind the
+ * kernels that wrote them; every rank then merges the gathered rows in place (k_merge_columns_gathered), which gives the
+ * same bits on every rank and for every rank count.  The host synchronises once per inference.
+ * NCCL is opened at run time (libnccl.so.2; CPPROB_SIS_NCCL_LIB overrides): nothing here is needed on one GPU.
+ *
+ * Process per GPU: rank 0 calls cpprob_sis_comm_get_id and hands the 128 bytes to the others by any means (MPI,
+ * torch.distributed, a file); every rank calls cpprob_sis_comm_init on its engine (collective), then
+ * cpprob_sis_run_dist with the same arguments (collective).  All engines must be created with ONE seed. */
+#define CPPROB_SIS_COMM_ID_BYTES 128
+int cpprob_sis_comm_get_id(void * id_out /* [CPPROB_SIS_COMM_ID_BYTES] */);
+int cpprob_sis_comm_init(cpprob_sis_engine * e, const void * id, int rank, int world);
+int cpprob_sis_comm_destroy(cpprob_sis_engine * e);
+int cpprob_sis_run_dist(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs, uint64_t n_particles_total,
+                        cpprob_sis_stats * out);
+/* One process driving several GPUs: a communicator among engines[0..n) (rank r = engines[r]; ncclCommInitAll). */
+int cpprob_sis_comm_init_local(cpprob_sis_engine * const * engines, int n_engines);
+
+/* Single-process form of the same scheme: engines[r] (one per GPU, created by the caller with ONE seed) is rank r; the
+ * calling thread queues every shard, the grouped all-gather and the merge, and waits once.  The local communicator is
+ * made on first use (cpprob_sis_comm_init_local) and kept.  Estimators only (no trace emission).  Results are owned by
+ * engines[0] and are bit-identical to a single-GPU run of the same seed. */
 int cpprob_sis_run_multi(cpprob_sis_engine * const * engines, int n_engines, int model_id, const double * obs,
                          size_t n_obs, uint64_t n_particles, cpprob_sis_stats * out);
 

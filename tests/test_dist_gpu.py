@@ -1,0 +1,72 @@
+"""Multi-GPU inside the library (cpprob_sis_comm_* / cpprob_sis_run_dist / cpprob_sis_run_multi): one NCCL all-gather of
+the partial rows per inference, merged in place, bit-identical to a single-GPU run.  The multi-device tests need >= 2 GPUs
+(gpurun --gpus 2); the single-rank forms run anywhere."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import analytic
+from cpprob_b200 import capi
+
+pytestmark = pytest.mark.gpu
+G = analytic.golden()
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+CASES = [("gaussian_unknown_mean", [3.0, 4.0], 37 * capi.CHUNK + 4321), ("linear_gaussian_1d", G["obs_linear_gaussian_32"][:7], 5 * capi.CHUNK + 3),
+         ("hmm", G["obs_hmm_64"][:9], 5 * capi.CHUNK + 3)]
+
+
+@pytest.mark.parametrize("model,obs,n", CASES, ids=[c[0] for c in CASES])
+def test_run_dist_on_one_rank_is_run(engine, model, obs, n):
+    a = engine.run(model, obs, n)
+    b = engine.run_dist(model, obs, n)                   # rank 0 of 1: no communicator, no NCCL needed
+    assert (a["sums"] == b["sums"]).all() and a["path"] == b["path"]
+
+
+def test_communicator_of_one_rank(engine):
+    """The whole NCCL path (unique id, ncclCommInitRank, ncclAllGather is skipped for world 1) opens and closes."""
+    from cpprob_b200 import Engine
+    with Engine(seed=0x5EED) as e:
+        e.comm_init(capi.comm_get_id(), 0, 1)
+        a = e.run_dist("gaussian_unknown_mean", [3.0, 4.0], 100_000)
+    b = engine.run("gaussian_unknown_mean", [3.0, 4.0], 100_000)
+    assert (a["sums"] == b["sums"]).all()
+
+
+@pytest.mark.skipif(n_gpus() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.parametrize("model,obs,n", CASES + [("gaussian_unknown_mean", [3.0, 4.0], 5000 * capi.CHUNK + 777)],
+                         ids=[c[0] for c in CASES] + ["super_chunks"])
+def test_run_multi_equals_single_gpu(engine, model, obs, n):
+    from cpprob_b200 import Engine
+    k = min(n_gpus(), 4)
+    engines = [Engine(device=d, seed=0x5EED) for d in range(k)]
+    try:
+        multi = capi.run_multi(engines, model, obs, n)
+        again = capi.run_multi(engines, model, obs, n)     # the communicator is kept
+    finally:
+        for e in engines:
+            e.close()
+    solo = engine.run(model, obs, n)
+    assert (multi["sums"] == solo["sums"]).all() and (again["sums"] == solo["sums"]).all()
+    assert np.array_equal(multi["real_mean"], solo["real_mean"]) and np.array_equal(multi["int_prob"], solo["int_prob"])
+
+
+@pytest.mark.skipif(n_gpus() < 2, reason="needs at least 2 GPUs")
+def test_process_per_gpu_run_dist_equals_single_gpu():
+    k = min(n_gpus(), 8)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={k}", "--master-addr", "127.0.0.1",
+                        "--master-port", "29531", os.path.join(ROOT, "tools", "dist_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["ok"] and line["world"] == k
+    assert all(c["equals_single_gpu"] and c["same_on_every_rank"] for c in line["cases"])
