@@ -93,11 +93,11 @@ __global__ void __launch_bounds__(kBlock) k_rows_hist(const int * __restrict__ i
 {
     __shared__ __align__(16) unsigned char stage_all[kWarps][32 * kStageIntStride];
     __shared__ __align__(16) double wst_all[kWarps][32];
-    __shared__ double acc_all[kWarps][32][kRowsHistBins + 1];
+    __shared__ double acc_all[kWarps][kRowsHistBins + 1][32];          // bin-major: see hist_acc_stride
     const unsigned lane = threadIdx.x & 31u, slot = threadIdx.x >> 5;
     unsigned char * const stage = stage_all[slot];
     double * const wst = wst_all[slot];
-    double * const acc = acc_all[slot][lane];
+    double * const acc = &acc_all[slot][0][lane];
     const unsigned n_groups = static_cast<unsigned>((n_int + 31) / 32);
     const unsigned c = blockIdx.x / n_groups;
     const int row0 = static_cast<int>(blockIdx.x % n_groups) * 32;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kBlock) k_rows_hist(const int * __restrict__ i
     const int rows_here = min(32, n_int - row0);
     const unsigned lo32 = static_cast<unsigned>(static_cast<int>(lo));
 
-    for (int b = 0; b <= bins_here; ++b) acc[b] = 0.0;
+    for (int b = 0; b <= bins_here; ++b) acc[b * 32] = 0.0;
     for (unsigned round = 0; round < kSubChunk / kBlock; ++round) {
         const unsigned i0 = round * kBlock + slot * 32u;
         if (i0 >= n_here) break;
@@ -136,9 +136,9 @@ __global__ void __launch_bounds__(kBlock) k_rows_hist(const int * __restrict__ i
     for (unsigned t = threadIdx.x; t < 32u * static_cast<unsigned>(bins_here); t += kBlock) {
         const unsigned q = t / static_cast<unsigned>(bins_here), b = t % static_cast<unsigned>(bins_here);
         if (static_cast<int>(q) < rows_here && bin_offset + static_cast<int>(b) < hist_bins) {
-            double r = acc_all[0][q][b];
+            double r = acc_all[0][b][q];
 #pragma unroll
-            for (unsigned sl = 1; sl < kWarps; ++sl) r = __dadd_rn(r, acc_all[sl][q][b]);       // slots in slot order
+            for (unsigned sl = 1; sl < kWarps; ++sl) r = __dadd_rn(r, acc_all[sl][b][q]);       // slots in slot order
             partials[static_cast<size_t>(c) * n_cols + hist_col0 + (row0 + static_cast<int>(q)) * hist_bins + bin_offset + static_cast<int>(b)] = r;
         }
     }

@@ -41,9 +41,10 @@ template<class Model>
 constexpr int staged_threads() { return model_draws_normals<Model>::value ? 512 : 1024; }
 constexpr unsigned kSmemBudget = 227u * 1024u;
 
-// doubles per row of histogram accumulators: the bins, a scratch slot for unmatched states, rounded up to an odd count
-// (see hist_round)
-__host__ __device__ constexpr unsigned hist_acc_stride(unsigned bins) { return (bins + 1u) | 1u; }
+// Histogram accumulators of one group of 32 int rows: [bins + 1][32 lanes] doubles, bin-major — the accumulator of
+// (bin s, lane k) sits at s * 32 + k, so the 32 lanes always hit 32 different 8-byte bank pairs whatever their states
+// are.  Slot `bins` takes the states that match no bin.  hist_acc_stride = doubles per group.
+__host__ __device__ constexpr unsigned hist_acc_stride(unsigned bins) { return (bins + 1u) * 32u; }
 
 // One warp's staging area.  All offsets are multiples of 16 bytes.
 struct stage_layout {
@@ -58,7 +59,7 @@ __host__ __device__ inline stage_layout make_stage_layout(int n_real, int n_int,
     o = (o + 15u) & ~15u;
     L.w_off = o;     o += 32u * 8u;
     L.macc_off = o;  o += static_cast<unsigned>(n_real) * 16u;
-    L.hacc_off = o;  o += static_cast<unsigned>(n_int) * (bins > 0 ? hist_acc_stride(static_cast<unsigned>(bins)) : 0u) * 8u;
+    L.hacc_off = o;  o += static_cast<unsigned>((n_int + 31) / 32) * (bins > 0 ? hist_acc_stride(static_cast<unsigned>(bins)) : 0u) * 8u;
     L.bytes = (o + 15u) & ~15u;
     return L;
 }
@@ -90,9 +91,7 @@ __device__ __forceinline__ void moments_round(const double * __restrict__ row, c
 // compiles to a branch around every add, on which the lanes of a warp — different rows — diverge; a predicated add
 // becomes an unconditional DADD plus two selects per (particle, bin), 15 issue slots per particle for 3 bins against 8
 // here.  profiles/r02_notes.md.)  A byte at or beyond `bins` (outside the window, or the 255 of a lane beyond the end) is
-// redirected to a scratch slot behind the row's accumulators.  acc: the hist_acc_stride(bins) doubles of this row; the
-// stride is odd, so the 32 lanes' accumulators of one bin fall into different banks.
-
+// redirected to the scratch slot.  acc: this lane's column of its group's accumulators, i.e. acc[s * 32] is bin s.
 __device__ __forceinline__ void hist_round(const unsigned char * __restrict__ row, const double * __restrict__ wst, unsigned bins, double * __restrict__ acc)
 {
     const uint4 a = *reinterpret_cast<const uint4 *>(row), b = *reinterpret_cast<const uint4 *>(row + 16);
@@ -103,7 +102,7 @@ __device__ __forceinline__ void hist_round(const unsigned char * __restrict__ ro
         const double w[4] = {w01.x, w01.y, w23.x, w23.y};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const unsigned s = min((words[q] >> (8 * e)) & 0xffu, bins);
+            const unsigned s = min((words[q] >> (8 * e)) & 0xffu, bins) * 32u;
             acc[s] = __dadd_rn(acc[s], w[e]);                    // empirical_distribution.hpp:30-40: sum of w over x == v
         }
     }
@@ -123,8 +122,8 @@ __device__ __forceinline__ void hist_round2(const unsigned char * __restrict__ r
         const double w[4] = {w01.x, w01.y, w23.x, w23.y};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const unsigned s0 = min((w0[q] >> (8 * e)) & 0xffu, bins);
-            const unsigned s1 = min((w1[q] >> (8 * e)) & 0xffu, bins);
+            const unsigned s0 = min((w0[q] >> (8 * e)) & 0xffu, bins) * 32u;
+            const unsigned s1 = min((w1[q] >> (8 * e)) & 0xffu, bins) * 32u;
             const double t0 = acc0[s0], t1 = acc1[s1];
             acc0[s0] = __dadd_rn(t0, w[e]);
             acc1[s1] = __dadd_rn(t1, w[e]);
@@ -201,8 +200,8 @@ __global__ void __launch_bounds__(staged_threads<Model>(), 1) k_sis_staged(const
         const unsigned n_here = left < kSubChunk ? static_cast<unsigned>(left) : kSubChunk;
 
         for (int k = static_cast<int>(lane); k < 2 * n_real; k += 32) macc[k] = 0.0;
-        const int hstride = static_cast<int>(hist_acc_stride(static_cast<unsigned>(bins)));
-        for (int k = static_cast<int>(lane); k < n_int * hstride; k += 32) hacc[k] = 0.0;
+        const int hstride = static_cast<int>(hist_acc_stride(static_cast<unsigned>(bins)));       // doubles per group of 32 rows
+        for (int k = static_cast<int>(lane); k < ((n_int + 31) / 32) * hstride; k += 32) hacc[k] = 0.0;
         double max_lw = dm::neg_inf(), s0 = 0.0, s00 = 0.0;
         unsigned n_neginf = 0, n_nan = 0;
         int imin = 0x7fffffff, imax = static_cast<int>(0x80000000u);
@@ -245,12 +244,12 @@ __global__ void __launch_bounds__(staged_threads<Model>(), 1) k_sis_staged(const
                     macc[2 * k + 1] = s2;
                 }
                 {
-                    int k = static_cast<int>(lane);
-                    for (; k + 32 < n_int; k += 64) {
+                    int k = static_cast<int>(lane), grp = 0;           // row k = 32 grp + lane: column `lane` of group grp
+                    for (; k + 32 < n_int; k += 64, grp += 2) {
                         hist_round2(stage_int + k * kStageIntStride, stage_int + (k + 32) * kStageIntStride, wst, static_cast<unsigned>(bins),
-                                    hacc + k * hstride, hacc + (k + 32) * hstride);
+                                    hacc + grp * hstride + lane, hacc + (grp + 1) * hstride + lane);
                     }
-                    if (k < n_int) hist_round(stage_int + k * kStageIntStride, wst, static_cast<unsigned>(bins), hacc + k * hstride);
+                    if (k < n_int) hist_round(stage_int + k * kStageIntStride, wst, static_cast<unsigned>(bins), hacc + grp * hstride + lane);
                 }
                 __syncwarp();
             }
@@ -283,7 +282,10 @@ __global__ void __launch_bounds__(staged_threads<Model>(), 1) k_sis_staged(const
         if (static_cast<int>(lane) < kBaseCols) out[lane] = mine;
         // ... and the row sums straight from the accumulators (already complete per row: no reduction over lanes)
         for (int k = static_cast<int>(lane); k < 2 * n_real; k += 32) out[kBaseCols + k] = macc[k];
-        for (int k = static_cast<int>(lane); k < n_int * bins; k += 32) out[kBaseCols + 2 * n_real + k] = hacc[(k / bins) * hstride + k % bins];
+        for (int k = static_cast<int>(lane); k < n_int * bins; k += 32) {
+            const int row = k / bins, bin = k % bins;
+            out[kBaseCols + 2 * n_real + k] = hacc[(row / 32) * hstride + bin * 32 + (row % 32)];
+        }
         __syncwarp();
     }
 }

@@ -395,6 +395,41 @@ private:
     std::uint32_t r_;
 };
 
+// Thresholds of all K rows held in registers: thr[i][state] is threshold i of row `state` (reg_table::operator[] is a
+// select chain).  For inner loops that are bound by shared-memory traffic rather than by issue slots: K - 1 selects
+// per threshold instead of a table load on the state -> next state dependency chain.
+template<class IntType, int K>
+class reg_discrete_of_word {
+public:
+    using result_type = IntType;
+    using input_type = double;
+
+    CPPROB_HD reg_discrete_of_word(const reg_table<std::uint32_t, K> (&thr)[K - 1], IntType state, std::uint32_t word) : r_(word)
+    {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int i = 0; i < K - 1; ++i) t_[i] = thr[i][state];
+    }
+    CPPROB_HD IntType min() const { return 0; }
+    CPPROB_HD IntType max() const { return static_cast<IntType>(K - 1); }
+
+    template<class Rng>
+    CPPROB_HD result_type operator()(Rng &) const
+    {
+        int out = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int i = 0; i < K - 1; ++i) out += r_ >= t_[i] ? 1 : 0;
+        return static_cast<IntType>(out);
+    }
+
+private:
+    std::uint32_t t_[K - 1];
+    std::uint32_t r_;
+};
+
 // -------------------------------------------------------------------------------------------------
 // categorical: non-owning view of K probabilities (e.g. one row of a transition matrix).  Not in the
 // reference; north_star lists it next to `discrete`.  Probabilities are used as given (no

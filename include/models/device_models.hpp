@@ -157,6 +157,15 @@ struct hmm_model {
             cpprob.increment_log_prob(lp[state]);
             const int n = observed_states.size();
             int i = 1;
+            // the six thresholds, read once per trace: rthr[j][s] = threshold j of transition row s
+            ::cpprob::reg_table<std::uint32_t, k> rthr[k - 1];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+            for (int s = 0; s < k; ++s) {
+                rthr[0].v[s] = thr[2 * s];
+                rthr[1].v[s] = thr[2 * s + 1];
+            }
             // four steps per Philox block (philox_stream::next_u32x4), then the tail one word at a time
             for (; i + 4 <= n; i += 4) {
                 std::uint32_t r[4];
@@ -166,7 +175,7 @@ struct hmm_model {
 #endif
                 for (int j = 0; j < 4; ++j) {
                     lp += kLpdfStride;
-                    state = cpprob.sample(::cpprob::table_discrete_of_word<int, k>(thr + 2 * state, r[j]), true);
+                    state = cpprob.sample(::cpprob::reg_discrete_of_word<int, k>(rthr, state, r[j]), true);
                     cpprob.predict(state, "State");
                     cpprob.increment_log_prob(lp[state]);
                 }
