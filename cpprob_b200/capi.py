@@ -28,7 +28,7 @@ SYMBOLS = [
     "cpprob_sis_sample", "cpprob_sis_philox", "cpprob_sis_dmath", "cpprob_sis_measure_dfma_peak",
     "cpprob_sis_measure_store_peak", "cpprob_sis_plan_shard", "cpprob_sis_probe_issue", "cpprob_sis_probe_dfma_chains", "cpprob_sis_run_multi", "cpprob_sis_write_summary",
     "cpprob_sis_text_stage_stats", "cpprob_sis_plan_rows", "cpprob_sis_merge_padded",
-    "cpprob_sis_comm_get_id", "cpprob_sis_comm_init", "cpprob_sis_comm_init_local", "cpprob_sis_comm_destroy", "cpprob_sis_run_dist",
+    "cpprob_sis_set_seed", "cpprob_sis_comm_get_id", "cpprob_sis_comm_init", "cpprob_sis_comm_init_local", "cpprob_sis_comm_destroy", "cpprob_sis_run_dist",
 ]
 COMM_ID_BYTES = 128
 
@@ -118,6 +118,7 @@ def lib():
         L.cpprob_sis_measure_store_peak.argtypes = [C.c_void_p, dp]
         L.cpprob_sis_write_summary.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(Stats)]
         L.cpprob_sis_run_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, dp, C.c_size_t, u64, C.POINTER(Stats)]
+        L.cpprob_sis_set_seed.argtypes = [C.c_void_p, C.c_uint64]
         L.cpprob_sis_comm_get_id.argtypes = [C.c_void_p]
         L.cpprob_sis_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.cpprob_sis_comm_init_local.argtypes = [C.POINTER(C.c_void_p), C.c_int]
@@ -216,6 +217,9 @@ class Engine:
         if self._h:
             self._L.cpprob_sis_destroy(self._h)
             self._h = C.c_void_p()
+
+    def set_seed(self, seed):
+        _check(self._L.cpprob_sis_set_seed(self._h, int(seed)))
 
     def __del__(self):
         try:

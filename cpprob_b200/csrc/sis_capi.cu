@@ -1128,6 +1128,13 @@ int cpprob_sis_create(const cpprob_sis_config * cfg, cpprob_sis_engine ** out)
     return 0;
 }
 
+int cpprob_sis_set_seed(cpprob_sis_engine * e, uint64_t seed)
+{
+    if (!e) return fail(CPPROB_SIS_EINVAL, "null engine");
+    e->seed = seed;
+    return 0;
+}
+
 void cpprob_sis_destroy(cpprob_sis_engine * e)
 {
     if (!e) return;

@@ -154,16 +154,20 @@ void inference(
     const std::vector<int> devices = sis::device_list();
     if (emit == CPPROB_SIS_EMIT_NONE && devices.size() > 1) {
         // estimators only, particles sharded over the listed GPUs of this box (one host thread per GPU)
+        // (engines, and the NCCL communicator among them, are kept for the next call: sis::cached_engine)
         const std::uint64_t seed = sis::default_seed();
-        std::vector<std::unique_ptr<sis::engine>> engines;
-        for (int d : devices) engines.emplace_back(new sis::engine(d, seed));
-        std::vector<sis::engine *> others;
-        for (std::size_t i = 1; i < engines.size(); ++i) others.push_back(engines[i].get());
+        std::vector<sis::engine *> engines;
+        for (int d : devices) {
+            engines.push_back(&sis::cached_engine(d));
+            engines.back()->set_seed(seed);
+        }
+        const std::vector<sis::engine *> others(engines.begin() + 1, engines.end());
         const int model = engines[0]->model_id(who.name);
         last.stats = engines[0]->run_multi(others, model, who.obs, n);
         sis::check(cpprob_sis_write_summary(engines[0]->handle(), file_name.c_str(), &last.stats), "cpprob_sis_write_summary");
     } else {
-        sis::engine engine;
+        sis::engine & engine = sis::cached_engine(devices.size() == 1 ? devices[0] : sis::default_device());
+        engine.set_seed(sis::default_seed());
         const int model = engine.model_id(who.name);
         last.stats = engine.infer_to_files(model, who.obs, n, file_name, emit);
     }

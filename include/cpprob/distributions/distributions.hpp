@@ -60,6 +60,25 @@ private:
     RealType mean_, sigma_;
 };
 
+// A normal whose standard-normal variate was drawn earlier (philox_stream::next_std_normal_x4 hands out four at a
+// time): sampling returns z * sigma + mean, the expression normal_distribution uses, without touching the stream.
+template<class RealType = double>
+class normal_of_std {
+public:
+    using result_type = RealType;
+    using input_type = RealType;
+
+    CPPROB_HD normal_of_std(RealType mean, RealType sigma, RealType z) : mean_(mean), sigma_(sigma), z_(z) {}
+    CPPROB_HD RealType mean() const { return mean_; }
+    CPPROB_HD RealType sigma() const { return sigma_; }
+
+    template<class Rng>
+    CPPROB_HD result_type operator()(Rng &) const { return static_cast<RealType>(z_ * sigma_ + mean_); }
+
+private:
+    RealType mean_, sigma_, z_;
+};
+
 template<class RealType>
 struct logpdf<normal_distribution<RealType>> {
     // Operation order of utils_normal_distribution.hpp:26-43 (needed for the 1e-12 replay gate).

@@ -6,6 +6,9 @@
 
 #include <cstdint>
 #include <cstdlib>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <random>
 #include <stdexcept>
 #include <string>
@@ -74,6 +77,8 @@ public:
 
     cpprob_sis_engine * handle() const { return h_; }
 
+    void set_seed(std::uint64_t seed) { check(cpprob_sis_set_seed(h_, seed), "cpprob_sis_set_seed"); }
+
     int model_id(const std::string & name) const
     {
         const int id = cpprob_sis_find_model(name.c_str());
@@ -116,6 +121,20 @@ public:
 private:
     cpprob_sis_engine * h_ = nullptr;
 };
+
+// One engine per GPU for the whole process, re-seeded per call: what cpprob::inference uses.  The reference's
+// inference() has no per-call set-up to speak of (cpprob.hpp:184-192 resets a few statics); creating a CUDA context,
+// streams, events and device tables on every call would put milliseconds in front of a 10,000-particle run whose
+// kernels take microseconds.  Engines are released when the process ends.
+inline engine & cached_engine(int device)
+{
+    static std::mutex m;
+    static std::map<int, std::unique_ptr<engine>> cache;
+    std::lock_guard<std::mutex> lock(m);
+    std::unique_ptr<engine> & slot = cache[device];
+    if (!slot) slot.reset(new engine(device, 0));
+    return *slot;
+}
 
 }  // namespace sis
 }  // namespace cpprob

@@ -219,7 +219,7 @@ private:
         }
         if (n == 0 || cols.empty()) return true;
 
-        sis::engine engine(sis::default_device(), 0);
+        sis::engine & engine = sis::cached_engine(sis::default_device());      // shared with cpprob::inference
         if (!ragged) {
             reduce_dense(engine, is_int, keys, cols, log_w, n);
         } else {

@@ -24,6 +24,7 @@
 // Word consumption rules (identical on host and device, they are part of the stream definition):
 //   * next_u32()      takes one 32-bit word from the current block (4 per block);
 //   * next_u32x4()    drops what is left of the current block and takes the whole next one;
+//   * next_std_normal_x4() drops what is left of the current block and runs the four pair trials of the next two;
 //   * next_uniform()  takes an aligned pair of words (52 random mantissa bits, result in (0,1));
 //   * next_std_normal() takes an aligned pair of words (a, b) and runs one ziggurat trial on them
 //     (8192 layers, tools/gen_ziggurat.py): layer = bits 3..15 of a, sign = bit 0 of a, u = (b : a >> 12)
@@ -362,6 +363,39 @@ public:
         const double x = zig::trial_abs(a, b, xi);
         if (CPPROB_UNLIKELY(zig::high_word(x) >= zig::high_word(xn))) return zig::slow_path(keys_.k[0], keys_.k[1], s_lo_, s_hi_, where, tag_, a, b, x, xn);
         return zig::with_sign(x, a);
+    }
+#endif
+
+#if !defined(CPPROB_NORMAL_BOX_MULLER)
+    // Four standard normals at once: the unread words of the current block are dropped, the next TWO blocks are
+    // generated side by side (two independent multiply chains for the scheduler to interleave) and each of their four
+    // aligned word pairs runs one ziggurat trial — the same trial next_std_normal() runs on that pair.  For loops that
+    // draw one normal per trip: the pool bookkeeping leaves the trip and four draws overlap.
+    CPPROB_HD void next_std_normal_x4(double (&z)[4])
+    {
+        std::uint32_t w[8];
+        philox4x32::block(s_lo_, s_hi_, blk_, tag_, keys_, w[0], w[1], w[2], w[3]);
+        philox4x32::block(s_lo_, s_hi_, blk_ + 1u, tag_, keys_, w[4], w[5], w[6], w[7]);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 4; ++j) {
+            const std::uint32_t a = w[2 * j], b = w[2 * j + 1];
+            const std::uint32_t where = ((blk_ + static_cast<std::uint32_t>(j >> 1)) << 2) | static_cast<std::uint32_t>((j & 1) << 1);
+#if CPPROB_ON_DEVICE
+            double xi, xn;
+            const unsigned addr = zig_base_ + (a & 0xfff8u);
+            asm("ld.shared.f64 %0, [%1];" : "=d"(xi) : "r"(addr));
+            asm("ld.shared.f64 %0, [%1+8];" : "=d"(xn) : "r"(addr));
+#else
+            const double xi = zig::x_of(zig::layer_of(a)), xn = zig::x_of(zig::layer_of(a) + 1);
+#endif
+            const double x = zig::trial_abs(a, b, xi);
+            if (CPPROB_UNLIKELY(zig::high_word(x) >= zig::high_word(xn))) z[j] = zig::slow_path(keys_.k[0], keys_.k[1], s_lo_, s_hi_, where, tag_, a, b, x, xn);
+            else z[j] = zig::with_sign(x, a);
+        }
+        blk_ += 2u;
+        pos_ = 4;
     }
 #endif
 

@@ -48,6 +48,10 @@ int cpprob_sis_abi_version(void);
 const char * cpprob_sis_last_error(void);
 int cpprob_sis_create(const cpprob_sis_config * cfg, cpprob_sis_engine ** out);
 void cpprob_sis_destroy(cpprob_sis_engine * e);
+/* A new Philox key for the runs that follow.  An engine keeps its streams, buffers and tables between calls: a host API
+ * that serves many inference() calls (include/cpprob/cpprob.hpp) keeps ONE engine per GPU and re-seeds it, instead of
+ * paying the context / allocation / table-upload cost on every call. */
+int cpprob_sis_set_seed(cpprob_sis_engine * e, uint64_t seed);
 
 /* ---- model registry --------------------------------------------------------------------------
  * A model is a device functor (include/models/models.hpp) compiled into a set of kernel

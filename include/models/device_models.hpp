@@ -86,11 +86,31 @@ struct linear_gaussian_1d_model {
     CPPROB_HD void operator()(P & cpprob, const ::cpprob::obs_span<double> observations) const
     {
         double state = 0;
-        for (const auto obs : observations) {
+        const int n = observations.size();
+        int i = 0;
+#if !defined(CPPROB_NORMAL_BOX_MULLER)
+        // the reference's loop body, four trips at a time: their four standard normals come from one call
+        // (philox_stream::next_std_normal_x4 — two Philox blocks and four ziggurat trials side by side)
+        for (; i + 4 <= n; i += 4) {
+            double z[4];
+            cpprob.rng().next_std_normal_x4(z);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+            for (int j = 0; j < 4; ++j) {
+                const ::cpprob::normal_of_std<> transition_distr{state, 1, z[j]};
+                state = cpprob.sample(transition_distr, true);
+                const ::cpprob::normal_distribution<> likelihood{state, 1};
+                cpprob.observe(likelihood, observations[i + j]);
+                cpprob.predict(state, "State");
+            }
+        }
+#endif
+        for (; i < n; ++i) {                       // models.hpp:70-78 as written
             const ::cpprob::normal_distribution<> transition_distr{state, 1};
             state = cpprob.sample(transition_distr, true);
             const ::cpprob::normal_distribution<> likelihood{state, 1};
-            cpprob.observe(likelihood, obs);
+            cpprob.observe(likelihood, observations[i]);
             cpprob.predict(state, "State");
         }
     }
