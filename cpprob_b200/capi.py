@@ -28,7 +28,7 @@ SYMBOLS = [
     "cpprob_sis_sample", "cpprob_sis_philox", "cpprob_sis_dmath", "cpprob_sis_measure_dfma_peak",
     "cpprob_sis_measure_store_peak", "cpprob_sis_plan_shard", "cpprob_sis_probe_issue", "cpprob_sis_probe_dfma_chains", "cpprob_sis_run_multi", "cpprob_sis_write_summary",
     "cpprob_sis_text_stage_stats", "cpprob_sis_plan_rows", "cpprob_sis_merge_padded",
-    "cpprob_sis_set_seed", "cpprob_sis_comm_get_id", "cpprob_sis_comm_init", "cpprob_sis_comm_init_local", "cpprob_sis_comm_destroy", "cpprob_sis_run_dist",
+    "cpprob_sis_set_seed", "cpprob_sis_infer_to_files_multi", "cpprob_sis_comm_get_id", "cpprob_sis_comm_init", "cpprob_sis_comm_init_local", "cpprob_sis_comm_destroy", "cpprob_sis_run_dist",
 ]
 COMM_ID_BYTES = 128
 
@@ -119,6 +119,7 @@ def lib():
         L.cpprob_sis_write_summary.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(Stats)]
         L.cpprob_sis_run_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, dp, C.c_size_t, u64, C.POINTER(Stats)]
         L.cpprob_sis_set_seed.argtypes = [C.c_void_p, C.c_uint64]
+        L.cpprob_sis_infer_to_files_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, dp, C.c_size_t, u64, C.c_char_p, C.POINTER(Stats)]
         L.cpprob_sis_comm_get_id.argtypes = [C.c_void_p]
         L.cpprob_sis_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.cpprob_sis_comm_init_local.argtypes = [C.POINTER(C.c_void_p), C.c_int]
@@ -193,6 +194,16 @@ def comm_init_local(engines):
     """cpprob_sis_comm_init_local: one process, one engine per GPU, rank r = engines[r]."""
     arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
     _check(lib().cpprob_sis_comm_init_local(arr, len(engines)))
+
+
+def infer_to_files_multi(engines, model, obs, n, prefix):
+    """cpprob_sis_infer_to_files_multi: the posterior files of one inference written by several GPUs, rank r = engines[r]."""
+    obs = _f64(obs)
+    arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    st = Stats()
+    _check(lib().cpprob_sis_infer_to_files_multi(arr, len(engines), engines[0].model_id(model), _dptr(obs), obs.size, int(n),
+                                                 prefix.encode(), C.byref(st)))
+    return stats_to_dict(st)
 
 
 def run_multi(engines, model, obs, n):

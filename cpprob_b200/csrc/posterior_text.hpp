@@ -108,6 +108,38 @@ public:
         return true;
     }
 
+    // A writer that owns one byte range of files somebody else has already extended to their final size (multi-GPU
+    // emission: rank r's records start where rank r-1's end).  Nothing here changes the file size.
+    bool open_at(off_t real_offset, off_t int_offset)
+    {
+        presized_ = true;
+        if (!real_ids_.empty()) {
+            f_real_ = ::open((prefix_ + ".real").c_str(), O_RDWR | O_CREAT, 0666);
+            if (f_real_ < 0) return false;
+            off_real_ = real_offset;
+        }
+        if (!int_ids_.empty()) {
+            f_int_ = ::open((prefix_ + ".int").c_str(), O_RDWR | O_CREAT, 0666);
+            if (f_int_ < 0) return false;
+            off_int_ = int_offset;
+        }
+        return true;
+    }
+
+    // Appends `bytes` of room to <prefix>.<kind> and returns the old end (-1 on error): the offset of the first new byte.
+    static off_t extend_file(const std::string & path, unsigned long long bytes)
+    {
+        const int fd = ::open(path.c_str(), O_RDWR | O_CREAT, 0666);
+        if (fd < 0) return -1;
+        const off_t end = ::lseek(fd, 0, SEEK_END);
+        struct statvfs vfs;
+        const bool room = ::fstatvfs(fd, &vfs) != 0 || static_cast<unsigned long long>(vfs.f_bavail) * vfs.f_frsize > bytes + (64ull << 20);
+        const bool ok = end >= 0 && room && ::ftruncate(fd, end + static_cast<off_t>(bytes)) == 0;
+        if (end >= 0 && !room) errno = ENOSPC;
+        ::close(fd);
+        return ok ? end : static_cast<off_t>(-1);
+    }
+
     // One trace block -> text.  The block is cut into slices that are formatted concurrently (one buffer
     // per slice) and written in order, so the file content does not depend on the thread count.
     bool append(const cpprob_sis_block & blk)
@@ -144,7 +176,7 @@ public:
             const off_t page = static_cast<off_t>(::sysconf(_SC_PAGESIZE));
             const off_t map_off = file_off / page * page;
             lead = static_cast<size_t>(file_off - map_off);
-            if (::ftruncate(fd, file_off + static_cast<off_t>(n)) == 0) {
+            if (presized_ || ::ftruncate(fd, file_off + static_cast<off_t>(n)) == 0) {
                 void * m = ::mmap(nullptr, lead + n, PROT_READ | PROT_WRITE, MAP_SHARED, fd, map_off);
                 if (m != MAP_FAILED) map = static_cast<char *>(m);
             }
@@ -301,6 +333,7 @@ private:
     int f_real_ = -1, f_int_ = -1;
     std::vector<text_buffer> bufs_;
     off_t off_real_ = 0, off_int_ = 0;
+    bool presized_ = false;
 };
 
 // <prefix>.stats: the on-device estimators of the LAST run (the record files may hold older runs

@@ -4,6 +4,7 @@
 // (model_vtable.cuh).  One engine drives one GPU with a compute stream and a copy stream; device
 // and pinned buffers grow on demand and are kept between calls.
 #include <algorithm>
+#include <array>
 #include <cerrno>
 #include <chrono>
 #include <cmath>
@@ -11,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <mutex>
 #include <future>
 #include <string>
@@ -364,6 +366,7 @@ struct shard_options {
     void * user = nullptr;
     cpprob::text::posterior_writer * text_writer = nullptr;   // EMIT_ALL with the records formatted on the GPU
     bool no_wait = false;    // fused path only: return right after the launches; merge_impl(..., pending) collects m_ref and the time
+    bool count_text_only = false;   // with text_writer: only measure the text of this shard (shard_result::text_total), write nothing
 };
 
 constexpr int kMinStagedWarps = 4;          // fewer resident warps than this: the row path is the better choice
@@ -380,6 +383,7 @@ bool staged_enabled()
 
 struct shard_result {
     int path = CPPROB_SIS_PATH_ROWS;
+    unsigned long long text_total[2] = {0, 0};                     // count_text_only: bytes of this shard's .real / .int text
     shard_plan plan;
     uint32_t rows_per_chunk = 1;       // partial rows per kChunk particles: 1 (fused) or kChunk / kSubChunk (row path)
     uint32_t n_rows_local = 0, n_rows_total = 0, row_first = 0;   // the rows handed on (super-chunk rows, see plan_shard)
@@ -734,11 +738,11 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         k_row_base<<<subs_here, kBlock, 0, e->compute>>>(a.logw, n_here, kSubChunk, e->d_pilot.ptr, a.w, a.int_extras, hw.lo, hw.bins, a.partials, n_cols);
         CU_TRY(cudaGetLastError());
         ++res->launches;
-        if (n_real > 0) {
+        if (n_real > 0 && !opt.count_text_only) {
             CU_TRY(launch_rows_moments(e->compute, subs_here, a.real_rows, a.w, cap, n_here, n_real, a.partials, n_cols));
             ++res->launches;
         }
-        if (n_int > 0) {
+        if (n_int > 0 && !opt.count_text_only) {
             CU_TRY(launch_hist_all(e->compute, subs_here, n_int, a.int_rows, a.w, cap, n_here, hw, kBaseCols + 2 * n_real,
                                    a.partials, n_cols, &res->launches));
         }
@@ -768,6 +772,10 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
             }
             CU_TRY(cudaMemcpyAsync(e->h_text_meta[buf].ptr, e->d_text_meta.ptr, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->compute));
             CU_TRY(cudaStreamSynchronize(e->compute));
+            if (opt.count_text_only) {           // multi-GPU emission, first pass: the size of this rank's text is all that is wanted
+                for (int kind = 0; kind < 2; ++kind) if (n_text_slots[kind]) res->text_total[kind] += e->h_text_meta[buf].ptr[2 * kind];
+                continue;
+            }
             // the text buffers are sized from the measured totals (grow-only, 1/16 head room), not from a worst case:
             // an hmm<1000> line is 6 KB, its worst case 28 KB
             for (int kind = 0; kind < 2; ++kind) {
@@ -1874,6 +1882,139 @@ int cpprob_sis_infer_to_files(cpprob_sis_engine * e, int model_id, const double 
     if (rc != 0) return rc;
     if (!writer.finish(e->structure.ids)) return fail(CPPROB_SIS_EIO, std::string("cannot write ") + prefix + ".ids");
     if (!cpprob::text::write_stats_sidecar(prefix, *out, e->slots, e->structure.ids)) {
+        return fail(CPPROB_SIS_EIO, std::string("cannot write ") + prefix + ".stats");
+    }
+    return 0;
+}
+
+// Multi-GPU emission.  Rank r (= engines[r]) owns a contiguous range of global particle indices, so the posterior file of
+// the run is the ranks' texts one after the other.  Pass A measures every rank's text (particle kernel + the length
+// kernels, nothing copied or written); the files are extended ONCE to their final size; pass B runs the ranks
+// concurrently, each formatting its own records on its own GPU and copying them into its own byte range of the shared
+// mapping.  The estimators come from the ranks' partial rows, gathered on engines[0]'s GPU and merged as always.  Every
+// byte of every file equals what one GPU writes for the same seed.
+int cpprob_sis_infer_to_files_multi(cpprob_sis_engine * const * engines, int n_engines, int model_id, const double * obs, size_t n_obs,
+                                    uint64_t n_particles, const char * prefix, cpprob_sis_stats * out)
+{
+    if (!engines || n_engines <= 0 || !obs || !prefix || !out) return fail(CPPROB_SIS_EINVAL, "bad argument");
+    for (int r = 0; r < n_engines; ++r) {
+        if (!engines[r]) return fail(CPPROB_SIS_EINVAL, "null engine");
+        if (engines[r]->seed != engines[0]->seed) return fail(CPPROB_SIS_EINVAL, "all engines of a multi-GPU run must share one seed");
+    }
+    const cpprob_sis_model_vtable * vt = model_of(model_id);
+    if (!vt) return fail(CPPROB_SIS_ENOMODEL, "unknown model id");
+    cpprob_sis_engine * primary = engines[0];
+    if (int rc = probe_structure(primary, vt, obs, n_obs)) return rc;
+    const size_t R = static_cast<size_t>(n_engines);
+    const int n_real = static_cast<int>(primary->structure.n_real), n_int = static_cast<int>(primary->structure.n_int);
+
+    std::vector<std::unique_ptr<cpprob::text::posterior_writer>> writers;
+    for (size_t r = 0; r < R; ++r) writers.emplace_back(new cpprob::text::posterior_writer(prefix, primary->slots));
+    std::vector<shard_result> res(R);
+    // one host thread per rank: a shard that emits waits for its own copies and writes its own file range
+    auto run_all = [&](const shard_options & proto, const double * mo, const hist_window * ho) -> int {
+        std::vector<int> rc(R, 0);
+        std::vector<std::string> msg(R);
+        std::vector<std::thread> pool;
+        for (size_t r = 0; r < R; ++r) {
+            pool.emplace_back([&, r] {
+                shard_options so = proto;
+                if (so.text_writer) so.text_writer = writers[r].get();
+                res[r] = shard_result();
+                rc[r] = run_shard_impl(engines[r], vt, obs, n_obs, n_particles, static_cast<int>(r), n_engines, mo, ho, so, &res[r]);
+                if (rc[r] != 0) msg[r] = g_last_error;                 // thread-local: carry it out
+            });
+        }
+        for (auto & t : pool) t.join();
+        for (size_t r = 0; r < R; ++r) {
+            if (rc[r] != 0) return fail(rc[r], "device " + std::to_string(engines[r]->device) + ": " + msg[r]);
+        }
+        return 0;
+    };
+    // the ranks' partial rows -> engines[0]'s GPU in rank order -> merge
+    uint64_t launches = 0;
+    double total_ms = 0.0;
+    auto gather_merge = [&]() -> int {
+        if (int rc = use_device(primary)) return rc;
+        const int n_cols = res[0].n_cols;
+        const uint32_t rows_total = res[0].n_rows_total;
+        CU_TRY(primary->d_gather.reserve(static_cast<size_t>(rows_total) * n_cols));
+        double shard_ms = 0.0;
+        for (size_t r = 0; r < R; ++r) {
+            shard_ms = std::max(shard_ms, res[r].device_ms);
+            launches += res[r].launches;
+            if (res[r].n_rows_local == 0) continue;
+            CU_TRY(cudaMemcpyPeerAsync(primary->d_gather.ptr + static_cast<size_t>(res[r].row_first) * n_cols, primary->device, res[r].rows,
+                                       engines[r]->device, static_cast<size_t>(res[r].n_rows_local) * n_cols * sizeof(double), primary->compute));
+        }
+        double merge_ms = 0.0;
+        const int mrc = merge_impl(primary, primary->d_gather.ptr, rows_total, n_cols, n_real, n_int, res[0].hw, res[0].m_ref, n_particles, out,
+                                   &launches, &merge_ms);
+        total_ms += shard_ms + merge_ms;
+        return mrc;
+    };
+
+    // pass A: sizes
+    shard_options so;
+    so.emit = CPPROB_SIS_EMIT_ALL;
+    so.text_writer = writers[0].get();
+    so.count_text_only = true;
+    if (int rc = run_all(so, nullptr, nullptr)) return rc;
+    std::vector<std::array<unsigned long long, 2>> sizes(R);
+    unsigned long long total[2] = {0, 0};
+    for (size_t r = 0; r < R; ++r) {
+        for (int k = 0; k < 2; ++k) { sizes[r][static_cast<size_t>(k)] = res[r].text_total[k]; total[k] += res[r].text_total[k]; }
+    }
+    // the files grow once; every rank learns where its records start
+    off_t begin[2] = {0, 0};
+    if (n_real > 0) {
+        begin[0] = cpprob::text::posterior_writer::extend_file(std::string(prefix) + ".real", total[0]);
+        if (begin[0] < 0) return fail(CPPROB_SIS_EIO, std::string("cannot extend ") + prefix + ".real: " + std::strerror(errno));
+    }
+    if (n_int > 0) {
+        begin[1] = cpprob::text::posterior_writer::extend_file(std::string(prefix) + ".int", total[1]);
+        if (begin[1] < 0) return fail(CPPROB_SIS_EIO, std::string("cannot extend ") + prefix + ".int: " + std::strerror(errno));
+    }
+    off_t at[2] = {begin[0], begin[1]};
+    for (size_t r = 0; r < R; ++r) {
+        if (!writers[r]->open_at(at[0], at[1])) return fail(CPPROB_SIS_EIO, std::string("cannot open posterior files for ") + prefix + ": " + std::strerror(errno));
+        at[0] += static_cast<off_t>(sizes[r][0]);
+        at[1] += static_cast<off_t>(sizes[r][1]);
+    }
+    // pass B: records and partial sums
+    so.count_text_only = false;
+    if (int rc = run_all(so, nullptr, nullptr)) return rc;
+    int mrc = gather_merge();
+    if (mrc < 0) return mrc;
+    // re-basing / a wider histogram window only redo the sums (the records are written), as on one GPU
+    double m_ref_override = 0.0;
+    hist_window hw_override;
+    int passes = 1;
+    for (; passes < 3; ++passes) {
+        const double * mo = nullptr;
+        const hist_window * ho = nullptr;
+        if (mrc == 1) { m_ref_override = out->max_log_w; mo = &m_ref_override; }
+        hist_window hw = res[0].hw;
+        if (widen_window(*out, n_int, &hw)) {
+            if (hw.bins > 4096) return fail(CPPROB_SIS_ERANGE, "int predicts span more than 4096 values");
+            hw_override = hw;
+            ho = &hw_override;
+        }
+        if (!mo && !ho) break;
+        shard_options again;
+        again.force_rows = 1;
+        if (int rc = run_all(again, mo, ho)) return rc;
+        mrc = gather_merge();
+        if (mrc < 0) return mrc;
+    }
+    out->device_ms = total_ms;
+    out->kernel_launches = launches;
+    out->passes = passes;
+    out->path = CPPROB_SIS_PATH_ROWS;
+    primary->launches += launches;
+    for (size_t r = 1; r < R; ++r) writers[r].reset();                 // closes their descriptors
+    if (!writers[0]->finish(primary->structure.ids)) return fail(CPPROB_SIS_EIO, std::string("cannot write ") + prefix + ".ids");
+    if (!cpprob::text::write_stats_sidecar(prefix, *out, primary->slots, primary->structure.ids)) {
         return fail(CPPROB_SIS_EIO, std::string("cannot write ") + prefix + ".stats");
     }
     return 0;

@@ -19,7 +19,7 @@
 //     would be 10^7 lines.
 // Environment knobs (additions, all optional): CPPROB_SIS_SEED, CPPROB_SIS_DEVICE,
 // CPPROB_SIS_EMIT=all|none (none: estimators + .ids + .stats only, no per-particle records),
-// CPPROB_SIS_DEVICES=0,1,... (with EMIT=none: shard the particles over these GPUs).
+// CPPROB_SIS_DEVICES=0,1,... (shard the particles over these GPUs of the box, with or without record files).
 #ifndef INCLUDE_CPPROB_HPP
 #define INCLUDE_CPPROB_HPP
 
@@ -152,8 +152,9 @@ void inference(
     detail::last_run_t & last = detail::last_run();
     last.valid = false;
     const std::vector<int> devices = sis::device_list();
-    if (emit == CPPROB_SIS_EMIT_NONE && devices.size() > 1) {
-        // estimators only, particles sharded over the listed GPUs of this box (one host thread per GPU)
+    if (devices.size() > 1) {
+        // particles sharded over the listed GPUs of this box: estimators only (one NCCL all-gather), or with every rank
+        // writing its own particle range of the posterior files
         // (engines, and the NCCL communicator among them, are kept for the next call: sis::cached_engine)
         const std::uint64_t seed = sis::default_seed();
         std::vector<sis::engine *> engines;
@@ -163,8 +164,12 @@ void inference(
         }
         const std::vector<sis::engine *> others(engines.begin() + 1, engines.end());
         const int model = engines[0]->model_id(who.name);
-        last.stats = engines[0]->run_multi(others, model, who.obs, n);
-        sis::check(cpprob_sis_write_summary(engines[0]->handle(), file_name.c_str(), &last.stats), "cpprob_sis_write_summary");
+        if (emit == CPPROB_SIS_EMIT_NONE) {
+            last.stats = engines[0]->run_multi(others, model, who.obs, n);
+            sis::check(cpprob_sis_write_summary(engines[0]->handle(), file_name.c_str(), &last.stats), "cpprob_sis_write_summary");
+        } else {
+            last.stats = engines[0]->infer_to_files_multi(others, model, who.obs, n, file_name);
+        }
     } else {
         sis::engine & engine = sis::cached_engine(devices.size() == 1 ? devices[0] : sis::default_device());
         engine.set_seed(sis::default_seed());

@@ -103,6 +103,18 @@ public:
         return st;
     }
 
+    // posterior files written by several engines (this one is rank 0 and owns the results)
+    cpprob_sis_stats infer_to_files_multi(const std::vector<engine *> & others, int model, const std::vector<double> & obs, std::uint64_t n,
+                                          const std::string & prefix)
+    {
+        std::vector<cpprob_sis_engine *> hs(1, h_);
+        for (engine * e : others) hs.push_back(e->handle());
+        cpprob_sis_stats st;
+        check(cpprob_sis_infer_to_files_multi(hs.data(), static_cast<int>(hs.size()), model, obs.data(), obs.size(), n, prefix.c_str(), &st),
+              "cpprob_sis_infer_to_files_multi");
+        return st;
+    }
+
     cpprob_sis_stats run(int model, const std::vector<double> & obs, std::uint64_t n)
     {
         cpprob_sis_stats st;

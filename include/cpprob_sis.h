@@ -167,6 +167,14 @@ int cpprob_sis_infer_to_files(cpprob_sis_engine * e, int model_id, const double 
                               uint64_t n_particles, const char * prefix, int emit /* CPPROB_SIS_EMIT_* */,
                               cpprob_sis_stats * out);
 
+/* The same with the particles sharded over several GPUs of this process (engines[r] = rank r, one seed): every rank
+ * formats its own particle range on its own GPU and writes it into its own byte range of <prefix>.real / .int (the
+ * files are extended once, after a first pass that only measures each rank's text), so the files are byte for byte what
+ * one GPU writes ("each rank streams its own particle range; the host writer concatenates in rank order").  .ids and
+ * .stats are written once; the estimators are merged from the ranks' partial rows on engines[0]'s GPU. */
+int cpprob_sis_infer_to_files_multi(cpprob_sis_engine * const * engines, int n_engines, int model_id, const double * obs, size_t n_obs,
+                                    uint64_t n_particles, const char * prefix, cpprob_sis_stats * out);
+
 /* Stage times of the last cpprob_sis_infer_to_files(..., EMIT_ALL) on this engine: the lines are formatted on
  * the GPU (`%.15e` exactly as the reference's ostream, cpprob_b200/csrc/text_format.cuh), only text crosses
  * PCIe, and the host appends it with concurrent pwrites.  kernel_ms: text kernels (CUDA events); copy_ms:

@@ -146,3 +146,37 @@ def test_gpu_text_ambiguous_records_are_fixed_on_the_host(tmp_path, monkeypatch)
     assert _files(tmp_path, "gpu") == _files(tmp_path, "host")
     assert _files(tmp_path, "gpui") == _files(tmp_path, "hosti")
     assert b"#" not in _files(tmp_path, "gpu")[".real"]
+
+
+# ---- multi-GPU emission: every rank writes its own particle range of the same files -------------------------------
+@pytest.mark.parametrize("model,obs_key,n_obs,n", [
+    ("gaussian_unknown_mean", None, 2, 7 * capi.CHUNK + 99),
+    ("linear_gaussian_1d", "obs_linear_gaussian_32", 32, 3 * capi.CHUNK + 5),
+    ("hmm", "obs_hmm_64", 64, 4 * capi.CHUNK + 1),
+    ("all_distr", None, 2, 2 * capi.CHUNK + 7),          # .real and .int in one run
+    ("gaussian_unknown_mean", None, 2, 1000),             # fewer chunks than ranks: some ranks own nothing
+])
+def test_multi_engine_files_equal_single_engine_files(model, obs_key, n_obs, n, tmp_path):
+    """cpprob_sis_infer_to_files_multi with 3 ranks (on distinct GPUs when the box has them, else three engines on one
+    GPU): <prefix>.real / .int / .ids are byte for byte what one engine writes, the estimators are the same bits, and a
+    second run appends after the first."""
+    import torch
+    from cpprob_b200 import Engine
+    obs = G[obs_key][:n_obs] if obs_key else [3.0, 4.0]
+    n_dev = torch.cuda.device_count()
+    engines = [Engine(device=r % n_dev, seed=0xF11E, max_batch=capi.CHUNK) for r in range(3)]
+    try:
+        multi = capi.infer_to_files_multi(engines, model, obs, n, str(tmp_path / "multi"))
+        capi.infer_to_files_multi(engines, model, obs, n, str(tmp_path / "multi"))       # appended (ios::app, state.cpp:264)
+    finally:
+        for e in engines:
+            e.close()
+    with Engine(seed=0xF11E, max_batch=capi.CHUNK) as e:
+        single = e.infer_to_files(model, obs, n, str(tmp_path / "single"))
+    a, b = _files(tmp_path, "multi"), _files(tmp_path, "single")
+    assert a.keys() == b.keys() and len(a) >= 2
+    for ext in a:
+        assert a[ext] == (b[ext] if ext == ".ids" else b[ext] + b[ext]), f"{model}{ext}"
+    assert (multi["sums"] == single["sums"]).all()
+    assert np.array_equal(multi["real_mean"], single["real_mean"]) and np.array_equal(multi["int_prob"], single["int_prob"])
+    assert os.path.exists(tmp_path / "multi.stats")
