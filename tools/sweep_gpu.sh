@@ -3,8 +3,8 @@
 mkdir -p gpurun_out/sweep
 for so in cpprob_b200/lib/variants/*.so; do
   n=$(basename $so .so)
-  CPPROB_SIS_LIB=$PWD/$so python bench.py --steps 10 --warmup 3 --cpu-particles 1000 > gpurun_out/sweep/$n.json 2> gpurun_out/sweep/$n.err
-  CPPROB_SIS_LIB=$PWD/$so ncu --metrics sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k regex:k_sis_fused -s 1 -c 1 --csv --log-file gpurun_out/sweep/$n.ncu.csv python bench.py --steps 1 --warmup 3 --particles 200000000 --cpu-particles 1000 > /dev/null 2>&1
+  CPPROB_SIS_LIB=$PWD/$so python bench.py --steps 10 --warmup 3 --cpu-particles 1000 --no-configs --strong-particles 1000000 > gpurun_out/sweep/$n.json 2> gpurun_out/sweep/$n.err
+  CPPROB_SIS_LIB=$PWD/$so ncu --metrics sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k regex:k_sis_fused -s 1 -c 1 --csv --log-file gpurun_out/sweep/$n.ncu.csv python bench.py --steps 1 --warmup 3 --particles 200000000 --cpu-particles 1000 --no-configs --strong-particles 1000000 > /dev/null 2>&1
   python - "$n" <<'PY'
 import json,sys,csv
 n=sys.argv[1]
