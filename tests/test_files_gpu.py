@@ -180,3 +180,14 @@ def test_multi_engine_files_equal_single_engine_files(model, obs_key, n_obs, n, 
     assert (multi["sums"] == single["sums"]).all()
     assert np.array_equal(multi["real_mean"], single["real_mean"]) and np.array_equal(multi["int_prob"], single["int_prob"])
     assert os.path.exists(tmp_path / "multi.stats")
+
+
+def test_estimator_only_run_removes_stale_record_files(engine, tmp_path):
+    """CPPROB_SIS_EMIT_NONE leaves .ids + .stats and no record file — not even an older run's, which StatsPrinter would
+    otherwise print against the new .ids (it reads the record files first, stats_printer.hpp:38-39)."""
+    prefix = str(tmp_path / "p")
+    engine.infer_to_files("gaussian_unknown_mean", [3.0, 4.0], 500, prefix)
+    assert os.path.exists(prefix + ".real")
+    engine.infer_to_files("hmm", G["obs_hmm_64"][:4], 500, prefix, emit=capi.EMIT_NONE)
+    assert sorted(os.listdir(tmp_path)) == ["p.ids", "p.stats"]
+    assert open(prefix + ".ids").read() == "State\n"

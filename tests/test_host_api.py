@@ -22,6 +22,12 @@ def test_host_twin_check(built):
     assert r.returncode == 0 and "host twin check: ok" in r.stdout, r.stdout + r.stderr
 
 
+def test_limits_fail_loudly(built):
+    """discrete_distribution with more weights than its inline capacity throws instead of sampling another distribution."""
+    r = subprocess.run([os.path.join(built, "limits_check")], capture_output=True, text=True)
+    assert r.returncode == 0 and "more weights than its capacity" in r.stdout, r.stdout + r.stderr
+
+
 def test_cli_argument_errors(built):
     main = os.path.join(built, "main")
     r = subprocess.run([main, "--help"], capture_output=True, text=True)
