@@ -37,6 +37,8 @@ struct cpprob_sis_model_vtable {
     // fit, use the row path), and the launch (one CTA of `warps` warps per grid entry; a->n_real/n_int/hist_* set)
     int (*staged_warps)(int n_obs, int n_real, int n_int, int bins);
     cudaError_t (*launch_staged)(cudaStream_t s, int grid, int warps, cpprob::engine::run_args * a);
+    // > 0: the model declares that its integral predicts lie in [0, int_states) (Model::int_predict_states)
+    int int_states;
 };
 }
 
@@ -115,7 +117,7 @@ struct model_launchers {
     {
         if (bins > kStagedMaxBins || (n_int > 0 && bins <= 0)) return 0;
         const unsigned fixed = model_smem<Model>(n_obs);
-        const unsigned per_warp = make_stage_layout(n_real, n_int, bins).bytes;
+        const unsigned per_warp = make_stage_layout(n_real, n_int, bins, staged_packed<Model>()).bytes;
         if (fixed + 4u * per_warp > kSmemBudget) return 0;
         const unsigned w = (kSmemBudget - fixed) / per_warp;
         constexpr unsigned max_warps = staged_threads<Model>() / 32u;
@@ -125,7 +127,7 @@ struct model_launchers {
     {
         a->scratch_doubles = model_scratch_doubles<Model>(a->n_obs);
         a->stage_base = model_smem<Model>(a->n_obs);
-        const unsigned smem = a->stage_base + static_cast<unsigned>(warps) * make_stage_layout(a->n_real, a->n_int, a->hist_bins).bytes;
+        const unsigned smem = a->stage_base + static_cast<unsigned>(warps) * make_stage_layout(a->n_real, a->n_int, a->hist_bins, staged_packed<Model>()).bytes;
         if (cudaError_t err = allow_smem(k_sis_staged<Model>, smem)) return err;
         k_sis_staged<Model><<<grid, warps * 32, smem, s>>>(*a);
         return cudaGetLastError();
@@ -159,7 +161,7 @@ struct model_launchers {
     {
         static const cpprob_sis_model_vtable vt = {
             CPPROB_SIS_ABI_VERSION, Model::name(), Model::n_scalar_obs, Model::replayable ? 1 : 0,
-            &probe, &pilot, &fused, &rows, &replay, &occupancy, &staged_warps, &staged};
+            &probe, &pilot, &fused, &rows, &replay, &occupancy, &staged_warps, &staged, model_int_states<Model>::value};
         return &vt;
     }
 };

@@ -434,7 +434,12 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     const bool est_only = !opt.force_rows && opt.emit == CPPROB_SIS_EMIT_NONE;
     const bool fused = est_only && n_int == 0 && n_real <= kMaxFusedReal;
     int staged_warps = 0;
-    if (est_only && !fused && n_int == 0 && staged_enabled()) staged_warps = vt->staged_warps(static_cast<int>(n_obs), n_real, 0, 0);
+    // a model that declares the range of its int predicts ([0, int_states)) needs no pilot for the histogram window
+    const int declared = (n_int > 0 && !hw_override) ? vt->int_states : 0;
+    if (est_only && !fused && staged_enabled()) {
+        if (n_int == 0) staged_warps = vt->staged_warps(static_cast<int>(n_obs), n_real, 0, 0);
+        else if (declared > 0) staged_warps = vt->staged_warps(static_cast<int>(n_obs), n_real, n_int, declared);
+    }
     const bool fused_early = fused || staged_warps >= kMinStagedWarps;
     if (fused_early) {
         const int n_pilot = static_cast<int>(std::min<uint64_t>(n_total, kPilot));
@@ -454,6 +459,9 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     if (n_int > 0) {
         if (hw_override) {
             hw = *hw_override;
+        } else if (declared > 0) {                 // the model says where its int predicts lie: same window on every path
+            hw.lo = 0;
+            hw.bins = declared;
         } else if (pilot[1] <= pilot[2]) {
             hw.lo = static_cast<long long>(pilot[1]);
             hw.bins = static_cast<int>(std::min<double>(pilot[2] - pilot[1] + 1.0, 1.0e9));
@@ -467,7 +475,11 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     res->m_ref = m_ref;
     const int n_cols = kBaseCols + 2 * n_real + n_int * hw.bins;
     res->n_cols = n_cols;
-    if (est_only && !fused && n_int > 0 && staged_enabled()) staged_warps = vt->staged_warps(static_cast<int>(n_obs), n_real, n_int, hw.bins);
+    // (a model compiled for four states per staged byte only fits the window it declared)
+    const bool packed_model = vt->int_states >= 1 && vt->int_states <= 4;
+    if (est_only && !fused && n_int > 0 && staged_enabled() && !fused_early && (!packed_model || (hw.lo == 0 && hw.bins == vt->int_states))) {
+        staged_warps = vt->staged_warps(static_cast<int>(n_obs), n_real, n_int, hw.bins);
+    }
     const bool staged = !fused && staged_warps >= kMinStagedWarps;
     res->path = fused ? CPPROB_SIS_PATH_FUSED : (staged ? CPPROB_SIS_PATH_STAGED : CPPROB_SIS_PATH_ROWS);
     // partial-sum rows: one per chunk on the fused path, one per sub-chunk on the row path (same on every rank)
@@ -986,6 +998,10 @@ int run_full(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, const do
             again = true;
         }
         hist_window hw = res.hw;
+        if (vt->int_states > 0 && e->structure.n_int > 0 && out->sums[col::int_oor] != 0.0) {
+            return fail(CPPROB_SIS_ERANGE, std::string("model ") + vt->name + " predicted an integral value outside [0, " + std::to_string(vt->int_states) +
+                                               "), the range it declares (int_predict_states)");
+        }
         if (passes < 3 && widen_window(*out, static_cast<int>(e->structure.n_int), &hw)) {
             if (hw.bins > 4096) return fail(CPPROB_SIS_ERANGE, "int predicts span more than 4096 values");
             hw_override = hw;
@@ -1360,6 +1376,10 @@ int run_dist_impl(cpprob_sis_engine * const * local, int n_local, const cpprob_s
             again = true;
         }
         hist_window hw = r0.hw;
+        if (vt->int_states > 0 && primary->structure.n_int > 0 && out->sums[col::int_oor] != 0.0) {
+            return fail(CPPROB_SIS_ERANGE, std::string("model ") + vt->name + " predicted an integral value outside [0, " + std::to_string(vt->int_states) +
+                                               "), the range it declares (int_predict_states)");
+        }
         if (pass < 3 && widen_window(*out, static_cast<int>(primary->structure.n_int), &hw)) {
             if (hw.bins > 4096) return fail(CPPROB_SIS_ERANGE, "int predicts span more than 4096 values");
             hw_override = hw;
@@ -1995,6 +2015,10 @@ int cpprob_sis_infer_to_files_multi(cpprob_sis_engine * const * engines, int n_e
         const hist_window * ho = nullptr;
         if (mrc == 1) { m_ref_override = out->max_log_w; mo = &m_ref_override; }
         hist_window hw = res[0].hw;
+        if (vt->int_states > 0 && n_int > 0 && out->sums[col::int_oor] != 0.0) {
+            return fail(CPPROB_SIS_ERANGE, std::string("model ") + vt->name + " predicted an integral value outside [0, " + std::to_string(vt->int_states) +
+                                               "), the range it declares (int_predict_states)");
+        }
         if (widen_window(*out, n_int, &hw)) {
             if (hw.bins > 4096) return fail(CPPROB_SIS_ERANGE, "int predicts span more than 4096 values");
             hw_override = hw;

@@ -46,20 +46,40 @@ constexpr unsigned kSmemBudget = 227u * 1024u;
 // are.  Slot `bins` takes the states that match no bin.  hist_acc_stride = doubles per group.
 __host__ __device__ constexpr unsigned hist_acc_stride(unsigned bins) { return (bins + 1u) * 32u; }
 
+// A model whose integral predicts all lie in [0, K) may say so: `static constexpr int int_predict_states = K;`.  The
+// engine then knows the histogram window without looking (no host round trip for the pilot's int range), and for K <= 4
+// the staged kernel keeps FOUR states per staged byte (2 bits each) — a 1000-step hmm trace is 8 KB per warp instead
+// of 32.  A predict outside the declared range ends the run with CPPROB_SIS_ERANGE.  Absent = 0 (unknown).
+template<class Model, class = void>
+struct model_int_states : std::integral_constant<int, 0> {};
+template<class Model>
+struct model_int_states<Model, decltype(void(Model::int_predict_states))> : std::integral_constant<int, Model::int_predict_states> {};
+template<class Model>
+constexpr bool staged_packed() { return model_int_states<Model>::value >= 1 && model_int_states<Model>::value <= 4; }
+
+// Histogram accumulators of a unit stay in the warp's staging area while they are small; for long traces (hmm<1000>: 24 KB
+// per unit) they live in the unit's own output row in global memory (L2) and every round reads / updates / writes them
+// back through a two-group scratch.  Same decision on host (launch size) and device (layout).
+__host__ __device__ inline bool staged_hacc_global(int n_int, int bins)
+{
+    return bins > 0 && static_cast<unsigned>((n_int + 31) / 32) * hist_acc_stride(static_cast<unsigned>(bins)) * 8u > 8192u;
+}
+
 // One warp's staging area.  All offsets are multiples of 16 bytes.
 struct stage_layout {
     unsigned real_off, int_off, w_off, macc_off, hacc_off, bytes;
 };
-__host__ __device__ inline stage_layout make_stage_layout(int n_real, int n_int, int bins)
+__host__ __device__ inline stage_layout make_stage_layout(int n_real, int n_int, int bins, bool packed)
 {
     stage_layout L;
     unsigned o = 0;
     L.real_off = o;  o += static_cast<unsigned>(n_real) * kStageRealStride * 8u;
-    L.int_off = o;   o += static_cast<unsigned>(n_int) * kStageIntStride;
+    L.int_off = o;   o += static_cast<unsigned>(packed ? (n_int + 3) / 4 : n_int) * kStageIntStride;
     o = (o + 15u) & ~15u;
     L.w_off = o;     o += 32u * 8u;
     L.macc_off = o;  o += static_cast<unsigned>(n_real) * 16u;
-    L.hacc_off = o;  o += static_cast<unsigned>((n_int + 31) / 32) * (bins > 0 ? hist_acc_stride(static_cast<unsigned>(bins)) : 0u) * 8u;
+    const unsigned groups = staged_hacc_global(n_int, bins) ? 2u : static_cast<unsigned>((n_int + 31) / 32);
+    L.hacc_off = o;  o += groups * (bins > 0 ? hist_acc_stride(static_cast<unsigned>(bins)) : 0u) * 8u;
     L.bytes = (o + 15u) & ~15u;
     return L;
 }
@@ -92,7 +112,10 @@ __device__ __forceinline__ void moments_round(const double * __restrict__ row, c
 // becomes an unconditional DADD plus two selects per (particle, bin), 15 issue slots per particle for 3 bins against 8
 // here.  profiles/r02_notes.md.)  A byte at or beyond `bins` (outside the window, or the 255 of a lane beyond the end) is
 // redirected to the scratch slot.  acc: this lane's column of its group's accumulators, i.e. acc[s * 32] is bin s.
-__device__ __forceinline__ void hist_round(const unsigned char * __restrict__ row, const double * __restrict__ wst, unsigned bins, double * __restrict__ acc)
+// `shift` / `mask`: where the row's state sits in each staged byte — (0, 0xff) for one state per byte, (2 (k & 3), 3) for
+// the packed form, whose byte row k / 4 holds rows 4 (k / 4) .. + 3.
+__device__ __forceinline__ void hist_round(const unsigned char * __restrict__ row, const double * __restrict__ wst, unsigned bins, double * __restrict__ acc,
+                                           unsigned shift = 0u, unsigned mask = 0xffu)
 {
     const uint4 a = *reinterpret_cast<const uint4 *>(row), b = *reinterpret_cast<const uint4 *>(row + 16);
     const unsigned words[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -100,9 +123,10 @@ __device__ __forceinline__ void hist_round(const unsigned char * __restrict__ ro
     for (int q = 0; q < 8; ++q) {
         const double2 w01 = *reinterpret_cast<const double2 *>(wst + 4 * q), w23 = *reinterpret_cast<const double2 *>(wst + 4 * q + 2);
         const double w[4] = {w01.x, w01.y, w23.x, w23.y};
+        const unsigned word = words[q] >> shift;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const unsigned s = min((words[q] >> (8 * e)) & 0xffu, bins) * 32u;
+            const unsigned s = min((word >> (8 * e)) & mask, bins) * 32u;
             acc[s] = __dadd_rn(acc[s], w[e]);                    // empirical_distribution.hpp:30-40: sum of w over x == v
         }
     }
@@ -110,7 +134,8 @@ __device__ __forceinline__ void hist_round(const unsigned char * __restrict__ ro
 
 // two rows of the same lane interleaved: their accumulator chains (load -> add -> store) are independent
 __device__ __forceinline__ void hist_round2(const unsigned char * __restrict__ row0, const unsigned char * __restrict__ row1,
-                                            const double * __restrict__ wst, unsigned bins, double * __restrict__ acc0, double * __restrict__ acc1)
+                                            const double * __restrict__ wst, unsigned bins, double * __restrict__ acc0, double * __restrict__ acc1,
+                                            unsigned shift = 0u, unsigned mask = 0xffu)
 {
     const uint4 a0 = *reinterpret_cast<const uint4 *>(row0), b0 = *reinterpret_cast<const uint4 *>(row0 + 16);
     const uint4 a1 = *reinterpret_cast<const uint4 *>(row1), b1 = *reinterpret_cast<const uint4 *>(row1 + 16);
@@ -120,10 +145,11 @@ __device__ __forceinline__ void hist_round2(const unsigned char * __restrict__ r
     for (int q = 0; q < 8; ++q) {
         const double2 w01 = *reinterpret_cast<const double2 *>(wst + 4 * q), w23 = *reinterpret_cast<const double2 *>(wst + 4 * q + 2);
         const double w[4] = {w01.x, w01.y, w23.x, w23.y};
+        const unsigned x0 = w0[q] >> shift, x1 = w1[q] >> shift;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const unsigned s0 = min((w0[q] >> (8 * e)) & 0xffu, bins) * 32u;
-            const unsigned s1 = min((w1[q] >> (8 * e)) & 0xffu, bins) * 32u;
+            const unsigned s0 = min((x0 >> (8 * e)) & mask, bins) * 32u;
+            const unsigned s1 = min((x1 >> (8 * e)) & mask, bins) * 32u;
             const double t0 = acc0[s0], t1 = acc1[s1];
             acc0[s0] = __dadd_rn(t0, w[e]);
             acc1[s1] = __dadd_rn(t1, w[e]);
@@ -134,23 +160,41 @@ __device__ __forceinline__ void hist_round2(const unsigned char * __restrict__ r
 // ------------------------------------------------------------------------------------------------
 // Policy: predicts go to this lane's column of the warp's staging area.
 // ------------------------------------------------------------------------------------------------
+template<bool Packed>
 struct staged_policy {
     double * real_col;             // &stage_real[k][lane], k = next real predict
-    unsigned char * int_col;       // &stage_int[k][lane]
+    unsigned char * int_col;       // &stage_int[k][lane] (one state per byte) or &stage_int[k / 4][lane] (Packed: four per byte)
     int lo;                        // start of the histogram window
     int imin, imax;                // range of the int predicts of this particle
+    unsigned acc, sh;              // Packed: the byte being filled and the position of the next state in it
     __device__ __forceinline__ staged_policy(double * rc, unsigned char * ic, int lo_)
-        : real_col(rc), int_col(ic), lo(lo_), imin(0x7fffffff), imax(static_cast<int>(0x80000000u)) {}
+        : real_col(rc), int_col(ic), lo(lo_), imin(0x7fffffff), imax(static_cast<int>(0x80000000u)), acc(0u), sh(0u) {}
     template<class D>
     __device__ __forceinline__ typename D::result_type sample(const D & d, philox_stream & rng) { return d(rng); }
     template<class T, class S> __device__ __forceinline__ void predict_int(T x, const S &)
     {
         const int xi = narrow_int(x, imin, imax);
-        // the low byte is enough: a value outside [lo, lo + bins) makes the run repeat with a wider window (run_full)
-        *int_col = static_cast<unsigned char>(xi - lo);
-        int_col += kStageIntStride;
+        // the low bits are enough: a value outside the window makes the run repeat with a wider one / fail (run_full)
+        if (Packed) {
+            acc |= (static_cast<unsigned>(xi - lo) & 3u) << sh;
+            sh += 2u;
+            if (sh == 8u) {
+                *int_col = static_cast<unsigned char>(acc);
+                int_col += kStageIntStride;
+                acc = 0u;
+                sh = 0u;
+            }
+        } else {
+            *int_col = static_cast<unsigned char>(xi - lo);
+            int_col += kStageIntStride;
+        }
         imin = min(imin, xi);
         imax = max(imax, xi);
+    }
+    // after the model body: the last, partly filled byte
+    __device__ __forceinline__ void finish()
+    {
+        if (Packed && sh != 0u) *int_col = static_cast<unsigned char>(acc);
     }
     template<class S> __device__ __forceinline__ void predict_real(double x, const S &)
     {
@@ -178,7 +222,10 @@ __global__ void __launch_bounds__(staged_threads<Model>(), 1) k_sis_staged(const
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int n_real = a.n_real, n_int = a.n_int, bins = a.hist_bins;
     const int lo = static_cast<int>(a.hist_lo);
-    const stage_layout L = make_stage_layout(n_real, n_int, bins);
+    constexpr bool kPacked = staged_packed<Model>();
+    const bool hacc_global = staged_hacc_global(n_int, bins);      // warp-uniform
+    const stage_layout L = make_stage_layout(n_real, n_int, bins, kPacked);
+    const int hist0 = kBaseCols + 2 * n_real;
     char * const area = reinterpret_cast<char *>(cpprob_zig_shared) + a.stage_base + static_cast<size_t>(warp) * L.bytes;
     double * const stage_real = reinterpret_cast<double *>(area + L.real_off);
     unsigned char * const stage_int = reinterpret_cast<unsigned char *>(area + L.int_off);
@@ -201,7 +248,12 @@ __global__ void __launch_bounds__(staged_threads<Model>(), 1) k_sis_staged(const
 
         for (int k = static_cast<int>(lane); k < 2 * n_real; k += 32) macc[k] = 0.0;
         const int hstride = static_cast<int>(hist_acc_stride(static_cast<unsigned>(bins)));       // doubles per group of 32 rows
-        for (int k = static_cast<int>(lane); k < ((n_int + 31) / 32) * hstride; k += 32) hacc[k] = 0.0;
+        double * const out = a.warp_partials + static_cast<size_t>(unit) * n_cols;
+        if (hacc_global) {
+            for (int k = static_cast<int>(lane); k < n_int * bins; k += 32) out[hist0 + k] = 0.0;
+        } else {
+            for (int k = static_cast<int>(lane); k < ((n_int + 31) / 32) * hstride; k += 32) hacc[k] = 0.0;
+        }
         double max_lw = dm::neg_inf(), s0 = 0.0, s00 = 0.0;
         unsigned n_neginf = 0, n_nan = 0;
         int imin = 0x7fffffff, imax = static_cast<int>(0x80000000u);
@@ -218,9 +270,10 @@ __global__ void __launch_bounds__(staged_threads<Model>(), 1) k_sis_staged(const
                 if (!__any_sync(0xffffffffu, valid)) break;          // the whole round lies beyond the end
                 double w = 0.0;
                 if (valid) {
-                    staged_policy pol(stage_real + lane, stage_int + lane, lo);
-                    particle<staged_policy> p(rng, pol, scratch);
+                    staged_policy<kPacked> pol(stage_real + lane, stage_int + lane, lo);
+                    particle<staged_policy<kPacked>> p(rng, pol, scratch);
                     invoke_model(model, p, oc.data(), a.n_obs);
+                    pol.finish();
                     const double lw = p.log_w();
                     w = dm::exp_weight(lw - m_ref);
                     // the base sums of k_row_base, same operations in the same order
@@ -233,7 +286,7 @@ __global__ void __launch_bounds__(staged_threads<Model>(), 1) k_sis_staged(const
                     imax = max(imax, pol.imax);
                 } else {
                     for (int k = 0; k < n_real; ++k) stage_real[k * kStageRealStride + lane] = 0.0;
-                    for (int k = 0; k < n_int; ++k) stage_int[k * kStageIntStride + lane] = 0xffu;
+                    for (int k = 0; k < (kPacked ? (n_int + 3) / 4 : n_int); ++k) stage_int[k * kStageIntStride + lane] = 0xffu;
                 }
                 wst[lane] = w;
                 __syncwarp();
@@ -244,12 +297,33 @@ __global__ void __launch_bounds__(staged_threads<Model>(), 1) k_sis_staged(const
                     macc[2 * k + 1] = s2;
                 }
                 {
-                    int k = static_cast<int>(lane), grp = 0;           // row k = 32 grp + lane: column `lane` of group grp
-                    for (; k + 32 < n_int; k += 64, grp += 2) {
-                        hist_round2(stage_int + k * kStageIntStride, stage_int + (k + 32) * kStageIntStride, wst, static_cast<unsigned>(bins),
-                                    hacc + grp * hstride + lane, hacc + (grp + 1) * hstride + lane);
+                    // row k = 32 grp + lane: column `lane` of group grp; two groups at a time (independent chains)
+                    const unsigned ubins = static_cast<unsigned>(bins);
+                    const unsigned shift = kPacked ? 2u * (lane & 3u) : 0u, mask = kPacked ? 3u : 0xffu;
+                    auto row_of = [&](int k) { return stage_int + (kPacked ? k >> 2 : k) * kStageIntStride; };
+                    int k = static_cast<int>(lane), grp = 0;
+                    if (!hacc_global) {
+                        for (; k + 32 < n_int; k += 64, grp += 2) {
+                            hist_round2(row_of(k), row_of(k + 32), wst, ubins, hacc + grp * hstride + lane, hacc + (grp + 1) * hstride + lane, shift, mask);
+                        }
+                        if (k < n_int) hist_round(row_of(k), wst, ubins, hacc + grp * hstride + lane, shift, mask);
+                    } else {
+                        // accumulators in the unit's output row (global, L2): read, update through the scratch, write back
+                        double * const sc0 = hacc + lane, * const sc1 = hacc + hstride + lane;
+                        for (; k < n_int; k += 64) {
+                            const bool two = k + 32 < n_int;                  // lanes of one warp agree except in the last group
+                            for (int b = 0; b < bins; ++b) {
+                                sc0[b * 32] = out[hist0 + k * bins + b];
+                                if (two) sc1[b * 32] = out[hist0 + (k + 32) * bins + b];
+                            }
+                            if (two) hist_round2(row_of(k), row_of(k + 32), wst, ubins, sc0, sc1, shift, mask);
+                            else hist_round(row_of(k), wst, ubins, sc0, shift, mask);
+                            for (int b = 0; b < bins; ++b) {
+                                out[hist0 + k * bins + b] = sc0[b * 32];
+                                if (two) out[hist0 + (k + 32) * bins + b] = sc1[b * 32];
+                            }
+                        }
                     }
-                    if (k < n_int) hist_round(stage_int + k * kStageIntStride, wst, static_cast<unsigned>(bins), hacc + grp * hstride + lane);
                 }
                 __syncwarp();
             }
@@ -278,13 +352,14 @@ __global__ void __launch_bounds__(staged_threads<Model>(), 1) k_sis_staged(const
             }
             if (static_cast<int>(lane) == j) mine = x;
         }
-        double * const out = a.warp_partials + static_cast<size_t>(unit) * n_cols;
         if (static_cast<int>(lane) < kBaseCols) out[lane] = mine;
         // ... and the row sums straight from the accumulators (already complete per row: no reduction over lanes)
         for (int k = static_cast<int>(lane); k < 2 * n_real; k += 32) out[kBaseCols + k] = macc[k];
-        for (int k = static_cast<int>(lane); k < n_int * bins; k += 32) {
-            const int row = k / bins, bin = k % bins;
-            out[kBaseCols + 2 * n_real + k] = hacc[(row / 32) * hstride + bin * 32 + (row % 32)];
+        if (!hacc_global) {
+            for (int k = static_cast<int>(lane); k < n_int * bins; k += 32) {
+                const int row = k / bins, bin = k % bins;
+                out[hist0 + k] = hacc[(row / 32) * hstride + bin * 32 + (row % 32)];
+            }
         }
         __syncwarp();
     }

@@ -125,6 +125,8 @@ struct hmm_model {
     static constexpr bool draws_normals = false;   // uniform_smallint + discrete only: no ziggurat table needed
     static constexpr const char * name() { return "hmm"; }
     static constexpr int k = 3;
+    static constexpr int int_predict_states = k;   // every predicted state lies in [0, 3): the engine needs no pilot for the
+                                                   // histogram window and stages four states per byte (staged_kernels.cuh)
 
     using transition_t = ::cpprob::discrete_distribution<int, double, k>;
     CPPROB_HD static ::cpprob::reg_table<double, k> state_means() { return ::cpprob::reg_table<double, k>{{-1, 0, 1}}; }
@@ -195,7 +197,11 @@ struct hmm_model {
 #endif
                 for (int j = 0; j < 4; ++j) {
                     lp += kLpdfStride;
+#if defined(CPPROB_HMM_REG_THRESHOLDS)
                     state = cpprob.sample(::cpprob::reg_discrete_of_word<int, k>(rthr, state, r[j]), true);
+#else
+                    state = cpprob.sample(::cpprob::table_discrete_of_word<int, k>(thr + 2 * state, r[j]), true);
+#endif
                     cpprob.predict(state, "State");
                     cpprob.increment_log_prob(lp[state]);
                 }

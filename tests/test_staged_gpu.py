@@ -15,7 +15,7 @@ from cpprob_b200 import capi
 pytestmark = pytest.mark.gpu
 G = analytic.golden()
 
-CASES = [("linear_gaussian_1d", G["obs_linear_gaussian_32"]), ("linear_gaussian_1d", G["obs_linear_gaussian_32"][:5]),
+CASES = [("hmm", G["obs_hmm_1000"]), ("hmm", G["obs_hmm_1000"][:130]), ("linear_gaussian_1d", G["obs_linear_gaussian_32"]), ("linear_gaussian_1d", G["obs_linear_gaussian_32"][:5]),
          ("hmm", G["obs_hmm_64"]), ("hmm", G["obs_hmm_64"][:7]), ("hmm", G["obs_hmm_64"][:1]),
          ("linear_gaussian_1d", (G["obs_linear_gaussian_32"] * 2)[:45])]         # 45 real rows: two row groups per lane
 
@@ -39,11 +39,12 @@ def test_path_selection(engine):
     assert engine.run("hmm", G["obs_hmm_64"], 1000)["path"] == "staged"
     assert engine.run("hmm", G["obs_hmm_64"], 1000, force_rows=True)["path"] == "rows"
     assert engine.run("hmm", G["obs_hmm_64"], 1000, collect=True)["path"] == "rows"           # emitting runs need the rows
-    # 1000 int predicts: 32 KB of staging per warp is still 6 warps; far longer traces fall back to rows
+    # 1000 int predicts of a model that declares 3 states: four states per staged byte, 8 KB per warp
     st = engine.run("hmm", G["obs_hmm_1000"], 2000)
-    assert st["path"] in ("staged", "rows") and st["n_int"] == 1000
-    long_obs = (G["obs_hmm_1000"] * 3)[:2500]
-    assert engine.run("hmm", long_obs, 600)["path"] == "rows"
+    assert st["path"] == "staged" and st["n_int"] == 1000 and st["int_lo"] == 0 and st["int_bins"] == 3
+    # far longer traces fall back to rows (neither the staging areas nor the model's table fit)
+    long_obs = (G["obs_hmm_1000"] * 30)[:30000]
+    assert engine.run("hmm", long_obs, 300)["path"] == "rows"
 
 
 def test_staged_matches_records(engine):
