@@ -478,7 +478,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the C3/C4/C5/file-emission block")
     ap.add_argument("--c3-particles", type=int, default=100_000_000)
     ap.add_argument("--c4-particles", type=int, default=100_000_000)
-    ap.add_argument("--c5-particles", type=int, default=4_000_000)
+    ap.add_argument("--c5-particles", type=int, default=16_000_000)
     ap.add_argument("--c5-file-particles", type=int, default=1_000_000)
     ap.add_argument("--file-particles", type=int, default=20_000_000)
     args = ap.parse_args()

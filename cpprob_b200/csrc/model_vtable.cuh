@@ -128,8 +128,13 @@ struct model_launchers {
         a->scratch_doubles = model_scratch_doubles<Model>(a->n_obs);
         a->stage_base = model_smem<Model>(a->n_obs);
         const unsigned smem = a->stage_base + static_cast<unsigned>(warps) * make_stage_layout(a->n_real, a->n_int, a->hist_bins, staged_packed<Model>()).bytes;
-        if (cudaError_t err = allow_smem(k_sis_staged<Model>, smem)) return err;
-        k_sis_staged<Model><<<grid, warps * 32, smem, s>>>(*a);
+        if (staged_threads<Model>() > kStagedFewThreads && warps * 32 <= kStagedFewThreads) {
+            if (cudaError_t err = allow_smem(k_sis_staged<Model, kStagedFewThreads>, smem)) return err;
+            k_sis_staged<Model, kStagedFewThreads><<<grid, warps * 32, smem, s>>>(*a);
+        } else {
+            if (cudaError_t err = allow_smem(k_sis_staged<Model, staged_threads<Model>()>, smem)) return err;
+            k_sis_staged<Model, staged_threads<Model>()><<<grid, warps * 32, smem, s>>>(*a);
+        }
         return cudaGetLastError();
     }
     static int occupancy(int which, int n_obs)

@@ -209,8 +209,13 @@ struct staged_policy {
 // [n_chunks * 8][n_cols]; a.stage_base = byte offset of the per-warp staging areas in dynamic shared memory.
 // Any warp takes any (sub-chunk, slot) unit from the atomic counter.
 // ------------------------------------------------------------------------------------------------
-template<class Model>
-__global__ void __launch_bounds__(staged_threads<Model>(), 1) k_sis_staged(const __grid_constant__ run_args a)
+// Threads: the CTA size the instantiation is compiled for (register budget 65536 / Threads).  Besides the model's
+// default (staged_threads) a 640-thread variant serves long traces, whose staging areas leave room for <= 20 warps
+// anyway: 100 registers instead of 64 keep the unit's bookkeeping out of local memory.
+constexpr int kStagedFewThreads = 640;
+
+template<class Model, int Threads>
+__global__ void __launch_bounds__(Threads, 1) k_sis_staged(const __grid_constant__ run_args a)
 {
     extern __shared__ double cpprob_zig_shared[];
     constexpr unsigned kTile = 2 * kPairStride;

@@ -141,10 +141,10 @@ struct hmm_model {
     // Per-launch table (particle.hpp, "Per-launch model tables").  Everything the reference recomputes for every
     // trace although it does not depend on the particle:
     //   t[2 s], s < 3   : the two sampler thresholds of transition row s, as a pair of 32-bit words
-    //   t[8 + 4 i + s]  : logpdf<normal>()(normal(state_mean[s], 1), observed_states[i]) — the same call observe() makes,
+    //   t[8 + 3 i + s]  : logpdf<normal>()(normal(state_mean[s], 1), observed_states[i]) — the same call observe() makes,
     //                     so the same bits (utils_normal_distribution.hpp:38-41 operation order)
     // A step of a trace is then one table-row draw, one 8-byte load and one add.
-    static constexpr int kLpdfBase = 8, kLpdfStride = 4;
+    static constexpr int kLpdfBase = 8, kLpdfStride = k;
     CPPROB_HD static int scratch_doubles(int n_obs) { return kLpdfBase + kLpdfStride * n_obs; }
     CPPROB_HD static void fill_scratch(double * t, const double * obs, int n_obs, int first, int stride)
     {

@@ -45,6 +45,7 @@ def main():
         run(e, "C3", "linear_gaussian_1d", g["obs_linear_gaussian_32"], int(1e8 * a.scale))
         run(e, "C4", "hmm", g["obs_hmm_64"], int(1e8 * a.scale))
         run(e, "C5 stats only", "hmm", g["obs_hmm_1000"], int(4e6 * a.scale))
+        run(e, "C5 stats only, 1.6e7", "hmm", g["obs_hmm_1000"], int(1.6e7 * a.scale))
         # C5 with full trace emission to host memory (pinned D2H on the side stream; records dropped on arrival)
         t0 = time.perf_counter()
         n = int(2e6 * a.scale)
