@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """One pass of each secondary configuration at a profiling-friendly size (run under ncu by tools/profile_r02.sh).
-usage: python tools/configs_once.py [c3|c4|c5|c5rows|all] [log2 particles]"""
+usage: python tools/configs_once.py [c3|c4|c5|c3rows|c4rows|c5rows|all] [log2 particles]"""
 import os
 import sys
 
@@ -22,5 +22,7 @@ with Engine(seed=0x5EED) as e:
         print("C5 est", e.run("hmm", g["obs_hmm_1000"], 1 << (lg - 4))["device_ms"])
     if which in ("c3rows", "all"):
         print("C3 rows", e.run("linear_gaussian_1d", g["obs_linear_gaussian_32"], 1 << lg, force_rows=True)["device_ms"])
+    if which in ("c5rows", "all"):
+        print("C5 rows", e.run("hmm", g["obs_hmm_1000"], 1 << (lg - 4), force_rows=True)["device_ms"])
     if which in ("c4rows", "all"):
         print("C4 rows", e.run("hmm", g["obs_hmm_64"], 1 << lg, force_rows=True)["device_ms"])

@@ -90,7 +90,7 @@ KEEP = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
-CAPTURES = {"fused_c2": ("C2", 200_000_000, 1), "staged_c3": ("C3", 1 << LG, 32), "staged_c4": ("C4", 1 << LG, 64), "rows_c5": ("C5_rows_kernel", 1 << (LG - 4), 1000)}
+CAPTURES = {"fused_c2": ("C2", 200_000_000, 1), "staged_c3": ("C3", 1 << LG, 32), "staged_c4": ("C4", 1 << LG, 64), "staged_c5": ("C5_estimators", 1 << (LG - 4), 1000), "rows_c5": ("C5_rows_kernel", 1 << (LG - 4), 1000)}
 costs = {}
 for name, (label, particles, steps) in CAPTURES.items():
     raw, src = f"{SRC}/{T}_{name}_raw.csv", f"{SRC}/{T}_{name}_source.csv"
@@ -128,22 +128,18 @@ for name, (label, particles, steps) in CAPTURES.items():
                     "fp64_pipe_pct": float(m["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"][0]),
                     "registers": int(float(m["launch__registers_per_thread"][0])), "source": f"profiles/{T}_{name}_ncu_full.csv"}
     print(label, json.dumps(costs[label]))
-# row path of C5 (estimators only): DRAM bytes of all its kernels per particle, from the per-kernel pass
-c5 = [(k, m) for k, m in by.items() if k[0] >= 0]
+# row path of C5 (emitting runs): DRAM bytes of all its kernels per particle, from the per-kernel pass ("C5 rows" of configs_once)
 rows_bytes, in_c5 = 0.0, False
 for (i, k, g, b), m in by.items():
-    if "k_pilot<models::hmm_model>" in k:
-        in_c5 = False
-    if "k_sis_rows<models::hmm_model>" in k and rows_bytes == 0.0:
+    if "k_sis_rows<models::hmm_model>" in k and not in_c5 and rows_bytes == 0.0:
         in_c5 = True
-    if in_c5 and not k.startswith("k_pilot"):
+    if in_c5:
         rows_bytes += nbytes(m, "dram__bytes_read.sum") + nbytes(m, "dram__bytes_write.sum")
-    if in_c5 and "k_merge_columns" in k:
-        break
+        if "k_merge_columns" in k:
+            break
 if rows_bytes:
-    costs["C5_estimators"] = {"dram_bytes_per_particle": rows_bytes / (1 << (LG - 4)), "particles": 1 << (LG - 4),
-                              "source": f"profiles/{T}_config_kernels_ncu.csv (k_sis_rows ... k_merge_columns of the hmm<1000> pass)"}
-    costs["C5"] = dict(costs["C5_estimators"])
+    costs["C5"] = {"dram_bytes_per_particle": rows_bytes / (1 << (LG - 4)), "particles": 1 << (LG - 4),
+                   "source": f"profiles/{T}_config_kernels_ncu.csv (k_sis_rows ... k_merge_columns of the forced-rows hmm<1000> pass)"}
 if costs:
     with open(f"{DST}/kernel_costs.json", "w") as f:
         json.dump({"tag": T, "how": "tools/profile_r02.sh + tools/summarise_r02.py: ncu --set full --clock-control none --import-source on, one launch each; "
