@@ -127,14 +127,26 @@ def scratch_dir():
     return "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
 
 
+REF_STATS_PRINTER = os.path.join(ROOT, "oracle", "_ref", "ref_stats_printer")
+
+
+def stats_printer_kind():
+    return ("reference's own StatsPrinter (oracle/_ref, compiled unmodified from the reference's headers)" if os.path.exists(REF_STATS_PRINTER)
+            else "restated StatsPrinter")
+
+
 def cpu_sis_step(n_procs, particles_each, flavour="faithful"):
     """One bounded sample: n_procs independent single-threaded runs (the reference is single-threaded,
-    SURVEY.md §5), each writing its own posterior files.  Returns wall seconds."""
+    SURVEY.md §5), each writing its own posterior files and post-processing them — with the reference's own StatsPrinter
+    where oracle/_ref was built.  Returns wall seconds."""
     exe = oracle_binary()
+    env = dict(os.environ)
+    if os.path.exists(REF_STATS_PRINTER):
+        env["ORACLE_STATS_PRINTER"] = REF_STATS_PRINTER
     with tempfile.TemporaryDirectory(dir=scratch_dir()) as d:
         t0 = time.perf_counter()
         procs = [subprocess.Popen([exe, MODEL, str(particles_each), os.path.join(d, f"p{i}"), flavour, "3", "4"],
-                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for i in range(n_procs)]
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env) for i in range(n_procs)]
         for p in procs:
             if p.wait() != 0:
                 raise RuntimeError("oracle_sis failed")
@@ -152,13 +164,14 @@ def run_reference(args):
     times = [cpu_sis_step(cores, each) for _ in range(args.steps)]
     total = sum(times)
     value = cores * each * args.steps / total
-    sample = f"{cores} processes x {each} particles per step, faithful flavour (3 file appends per trace + StatsPrinter), files on {scratch_dir()}"
+    sample = (f"{cores} processes x {each} particles per step, faithful flavour (restated cpprob::inference: 3 file appends per trace) + "
+              f"{stats_printer_kind()}, files on {scratch_dir()}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "particles/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "gaussian_unknown_mean x=(3,4), reference CPU SIS (oracle restatement of cpprob::inference + StatsPrinter; "
-                               "the reference itself needs Boost/ZeroMQ/FlatBuffers and cannot be built in this image)",
+        "config": {"workload": "gaussian_unknown_mean x=(3,4), reference CPU SIS: restated cpprob::inference (cpprob.hpp / state.cpp need "
+                               "Boost, ZeroMQ and FlatBuffers, absent from this image) + " + stats_printer_kind(),
                    "particles_per_step": cores * each},
         "cpu_baseline": {"value": value, "unit": "particles/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -441,7 +454,7 @@ def cpu_baseline(args):
     s = cpu_sis_step(1, n, "faithful")
     s_fast = cpu_sis_step(1, n, "fast")
     return {"value": n / s, "unit": "particles/s", "cores": 1, "kind": "port",
-            "sample": f"{n} particles of gaussian_unknown_mean x=(3,4): restated cpprob::inference (3 file appends per trace) + StatsPrinter, "
+            "sample": f"{n} particles of gaussian_unknown_mean x=(3,4): restated cpprob::inference (3 file appends per trace) + {stats_printer_kind()}, "
                       f"-O2, files on {scratch_dir()}",
             "fast_flavour_value": n / s_fast}
 

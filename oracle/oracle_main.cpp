@@ -27,9 +27,18 @@ int main(int argc, char ** argv)
         return 1;
     }
     const auto t0 = std::chrono::steady_clock::now();
-    const std::string text = oracle_stats_text(argv[3]);
+    // ORACLE_STATS_PRINTER=<path of oracle/_ref/ref_stats_printer>: post-process with the REFERENCE'S OWN StatsPrinter
+    // (compiled unmodified from /root/reference) instead of the restated one
+    if (const char * sp = std::getenv("ORACLE_STATS_PRINTER")) {
+        const std::string cmd = std::string(sp) + " '" + argv[3] + "'";
+        if (std::system(cmd.c_str()) != 0) {
+            std::cerr << "reference StatsPrinter failed\n";
+            return 1;
+        }
+    } else {
+        std::cout << oracle_stats_text(argv[3]);
+    }
     const double s2 = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    std::cout << text;
     std::cerr << "inference_s " << s << " stats_printer_s " << s2 << "\n";
     return 0;
 }
