@@ -1,4 +1,8 @@
-"""Multi-GPU plumbing: one process per GPU, particles sharded by whole chunks, and ONE small collective —
+"""Torch-side helpers for the shard / gather / merge entry points (cpprob_sis_run_shard, _merge, _merge_padded), kept for
+callers that bring their own transport and for the gloo tests of the host arithmetic.  The product's multi-GPU path no
+longer goes through here: cpprob_sis_run_dist issues the all-gather itself (NCCL inside libcpprob_sis.so).
+
+One process per GPU, particles sharded by whole chunks, and ONE small collective —
 an all-gather of the per-(super-)chunk partial sums in rank order (NCCL over NVLink on the GPU box, gloo in the CPU
 tests).  Merging the gathered rows in chunk order (cpprob_sis_merge) gives bit-identical results on every
 rank and for every world size; there is no data-path collective because particles are i.i.d.

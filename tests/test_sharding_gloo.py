@@ -1,5 +1,7 @@
-"""N>1 host-side logic on CPU: world_size-2 (and 3) gloo groups shard the chunks, all-gather their
-partial rows and must end up with the same, chunk-ordered matrix on every rank."""
+"""N>1 host-side logic on CPU: world_size-2 (3, 5) gloo groups shard the chunks, all-gather their partial rows and must end
+up with the same, chunk-ordered matrix on every rank — both through the torch-side helper (cpprob_b200/dist.py) and with the
+padded single all-gather + in-place row lookup that the library's own NCCL path uses (cpprob_sis_run_dist,
+k_merge_columns_gathered).  The NCCL path itself runs in tests/test_dist_gpu.py (-m gpu)."""
 import os
 import subprocess
 import sys
@@ -31,6 +33,25 @@ WORKER = textwrap.dedent("""
     s = g.sum().reshape(1).clone(); lo = s.clone(); hi = s.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     assert lo.item() == hi.item()
+    # The exchange the library performs (cpprob_sis_run_dist): every rank contributes rows_per_rank = the largest shard's
+    # row count, padding included, in ONE all-gather; the merge kernel then finds logical row i at segment r = its owner,
+    # position i - first[r], from cpprob_sis_plan_rows alone (k_merge_columns_gathered).  Same arithmetic, on the CPU:
+    for n_big, per_chunk in ((n_total, 1), (n_total, 8), (5000 * capi.CHUNK + 777, 1), (5000 * capi.CHUNK + 777, 8)):
+        plan = [capi.plan_rows(n_big, r, world, per_chunk) for r in range(world)]           # (first, n_local, n_total)
+        first = [p[0] for p in plan] + [plan[-1][2]]
+        assert first[0] == 0 and all(first[r] + plan[r][1] == first[r + 1] for r in range(world))
+        rows_per_rank = max(p[1] for p in plan)
+        mine = torch.full((rows_per_rank, 3), float("nan"), dtype=torch.float64)         # padding is never read
+        for i in range(plan[rank][1]):
+            mine[i] = float(first[rank] + i)                                                # row content = its logical index
+        gathered = torch.empty((world * rows_per_rank, 3), dtype=torch.float64)
+        dist.all_gather_into_tensor(gathered, mine)
+        r_own = 0
+        for i in range(first[-1]):
+            while i >= first[r_own + 1]:
+                r_own += 1
+            phys = r_own * rows_per_rank + (i - first[r_own])
+            assert gathered[phys, 0].item() == float(i), (rank, i, phys)
     dist.destroy_process_group()
     print("rank", rank, "ok")
 """) % ROOT
