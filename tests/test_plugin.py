@@ -51,3 +51,25 @@ def test_plugin_posterior_is_conjugate(engine):
     # the row path gives the same estimators
     rows = engine.run("coin", flips, n, force_rows=True)
     np.testing.assert_allclose(rows["real_mean"], st["real_mean"], rtol=1e-10)
+
+
+@pytest.mark.gpu
+def test_declared_int_range(engine):
+    """Model::int_predict_states: a true declaration selects the packed staged path (no pilot for the window) and agrees with
+    the row path bit for bit; a false one ends the run with CPPROB_SIS_ERANGE on every path instead of dropping values."""
+    load_plugin()
+    rolls = np.array([0.2, 2.9, 1.1, 3.3, 0.7, 2.2, 1.9])
+    n = 3 * capi.CHUNK + 77
+    a = engine.run("dice4", rolls, n)
+    b = engine.run("dice4", rolls, n, force_rows=True)
+    assert a["path"] == "staged" and b["path"] == "rows"
+    assert a["int_lo"] == 0 and a["int_bins"] == 4 and (a["sums"] == b["sums"]).all()
+    np.testing.assert_allclose(a["int_prob"].sum(1), 1.0, rtol=1e-12)
+    # exact posterior of each face: independent rolls, p(face | r) ~ exp(-(r - face)^2 / 2)
+    for k, r in enumerate(rolls):
+        p = np.exp(-0.5 * (r - np.arange(4)) ** 2)
+        np.testing.assert_allclose(a["int_prob"][k], p / p.sum(), atol=5.0 / math.sqrt(a["ess"]))
+    for kw in ({}, {"force_rows": True}):
+        with pytest.raises(capi.SisError) as ei:
+            engine.run("dice_lying", rolls, n, **kw)
+        assert ei.value.code == -5 and "declares" in str(ei.value)
