@@ -7,6 +7,8 @@
 //     include/cpprob/postprocess/empirical_distribution.hpp EmpiricalDistribution<T> (:16-147)
 //     include/cpprob/postprocess/stats_printer.hpp          StatsPrinter (:22-121)
 //     include/cpprob/utils.hpp, include/cpprob/traits.hpp   (helpers the above include)
+//     include/cpprob/distributions/utils_{discrete,uniform_smallint,poisson}.hpp   logpdf<> of the three distributions no
+//                                                           reference test pins (:17-27, :17-27, :17-36)
 // None of those files is copied or modified.  The third-party headers they name and this image lacks are
 // stood in for by oracle/ref_shim/ (Boost has_less, filesystem::path/exists, declarations of mpl::at_c and
 // function_types::*; and an empty cpprob/state.hpp, which stats_printer.hpp includes but does not use and
@@ -27,6 +29,14 @@
 #include <vector>
 
 #include "cpprob/postprocess/stats_printer.hpp"
+
+// The three log-pdf headers of the reference that no reference test pins and that need
+// nothing but a Boost.Random distribution type: compiled unmodified; Boost's classes are stood in for by accessor-only
+// shims (oracle/ref_shim/boost/random/), the FlatBuffers names their CSIS members mention by a declaration-only stub.
+namespace cpprob { template<class IntType, class RealType> class min_max_discrete_distribution; }   // named by proposal<uniform_smallint>
+#include "cpprob/distributions/utils_discrete.hpp"
+#include "cpprob/distributions/utils_uniform_smallint.hpp"
+#include "cpprob/distributions/utils_poisson.hpp"
 
 namespace {
 
@@ -64,7 +74,8 @@ extern "C" {
 const char * ref_describe(void)
 {
     return "reference code compiled from /root/reference/include: cpprob/serialization.hpp, cpprob/ndarray.hpp, "
-           "cpprob/postprocess/empirical_distribution.hpp, cpprob/postprocess/stats_printer.hpp";
+           "cpprob/postprocess/empirical_distribution.hpp, cpprob/postprocess/stats_printer.hpp, "
+           "cpprob/distributions/utils_discrete.hpp, utils_uniform_smallint.hpp, utils_poisson.hpp";
 }
 
 // ---- writer: serialization.hpp operator<< with dump_predicts' stream state --------------------------------------
@@ -164,6 +175,33 @@ int ref_empirical_int(const int * x, const double * log_w, unsigned long long n,
     *map_value = d.max_a_posteriori(distr);
     *num_points = d.num_points();
     return k;
+}
+
+// ---- logpdf<> of utils_uniform_smallint.hpp:17-27 (kind 2), utils_discrete.hpp:17-27 (3), utils_poisson.hpp:17-36 (4) ------
+// kind ids and parameter layout are those of include/cpprob_sis.h (CPPROB_SIS_DIST_*)
+int ref_logpdf(int kind, const double * q, int nq, const double * x, unsigned long long n, double * out)
+{
+    for (unsigned long long i = 0; i < n; ++i) {
+        switch (kind) {
+        case 2: {
+            const boost::random::uniform_smallint<long long> d(static_cast<long long>(q[0]), static_cast<long long>(q[1]));
+            out[i] = cpprob::logpdf<boost::random::uniform_smallint<long long>>()(d, static_cast<long long>(x[i]));
+            break;
+        }
+        case 3: {
+            const boost::random::discrete_distribution<long long, double> d(q, q + nq);
+            out[i] = cpprob::logpdf<boost::random::discrete_distribution<long long, double>>()(d, static_cast<long long>(x[i]));
+            break;
+        }
+        case 4: {
+            const boost::random::poisson_distribution<int, double> d(q[0]);
+            out[i] = cpprob::logpdf<boost::random::poisson_distribution<int, double>>()(d, static_cast<int>(x[i]));
+            break;
+        }
+        default: return -1;
+        }
+    }
+    return 0;
 }
 
 // ---- StatsPrinter: the console text of `std::cout << cpprob::StatsPrinter{prefix} << std::endl` (src/main.cpp:103-107)

@@ -1,6 +1,7 @@
 """ctypes wrapper of oracle/_ref/libcpprob_ref.so — TEST INFRASTRUCTURE.
 
-That library is the REFERENCE'S OWN serialization / NDArray / EmpiricalDistribution / StatsPrinter headers, compiled from
+That library is the REFERENCE'S OWN serialization / NDArray / EmpiricalDistribution / StatsPrinter headers and its
+uniform_smallint / discrete / poisson log-pdf headers, compiled from
 /root/reference by oracle/Makefile (target _ref) behind the C driver oracle/ref_driver.cpp.  It is built in the container
 that has /root/reference and travels to the GPU box as a built file; nothing here reads /root/reference at run time."""
 import ctypes as C
@@ -35,6 +36,7 @@ class Ref:
         L.ref_empirical_real.argtypes = [dp, dp, C.c_uint64, dp, dp]
         L.ref_empirical_int.argtypes = [ip, dp, C.c_uint64, C.c_int, ip, dp, ip, u64p]
         L.ref_stats_text.argtypes = [C.c_char_p]
+        L.ref_logpdf.argtypes = [C.c_int, dp, C.c_int, dp, C.c_uint64, dp]
         L.ref_stats_text.restype = C.c_char_p
         self.L = L
 
@@ -124,6 +126,15 @@ class Ref:
                                      C.byref(mp), C.byref(npts))
         assert k >= 0
         return dict(zip(values[:k].tolist(), probs[:k].tolist())), mp.value, npts.value
+
+    # ---- logpdf<> of utils_uniform_smallint.hpp / utils_discrete.hpp / utils_poisson.hpp ----
+    def logpdf(self, kind, params, x):
+        kinds = {"uniform_smallint": 2, "discrete": 3, "poisson": 4}
+        params, x = np.ascontiguousarray(params, np.float64), np.ascontiguousarray(x, np.float64)
+        out = np.empty_like(x)
+        dp = C.POINTER(C.c_double)
+        assert self.L.ref_logpdf(kinds[kind], params.ctypes.data_as(dp), params.size, x.ctypes.data_as(dp), x.size, out.ctypes.data_as(dp)) == 0
+        return out
 
     # ---- StatsPrinter ----
     def stats_text(self, prefix):

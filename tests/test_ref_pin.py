@@ -104,3 +104,29 @@ def test_reference_parser_quirks(ref):
     assert ref.parse(b"([(0 1.000000000000000e+00)] -inf)", "real") is None
     assert ref.parse_ndarray_ok(b"([(0 1.500000000000000e+00)] -1.000000000000000e+00)") == 1
     assert ref.parse_ndarray_ok(b"([(0 [1.500000000000000e+00 -2.000000000000000e+00])] -1.000000000000000e+00)") == -1
+
+
+LOGPDF_CASES = [  # rows (a)4c-4e: no reference test pins them (its "poisson" test re-tests the normal, tests/cpprob/logpdf.cpp:43-53)
+    ("uniform_smallint", [0, 2], np.arange(-3, 7.0)),
+    ("uniform_smallint", [-4, 11], np.arange(-8, 16.0)),
+    ("uniform_smallint", [5, 5], np.arange(3, 8.0)),
+    ("discrete", [0.1, 0.5, 0.4], np.arange(-2, 6.0)),
+    ("discrete", [1.0, 5.0, 4.0, 2.0, 8.0], np.arange(-1, 7.0)),
+    ("discrete", [3.0], np.arange(-1, 3.0)),
+    ("discrete", [0.0, 2.0, 0.0, 6.0], np.arange(0, 4.0)),          # zero-weight categories: log(0) = -inf
+    ("poisson", [0.8], np.arange(0, 40.0)),
+    ("poisson", [0.0], np.arange(0, 3.0)),                           # lambda == 0: -inf everywhere (utils_poisson.hpp:28-31)
+    ("poisson", [37.5], np.arange(0, 160.0)),
+    ("poisson", [1e-3], np.arange(0, 12.0)),
+    ("poisson", [2.0], np.arange(-3, 3.0)),                          # negative counts: the loop is empty, x*log(l) - l comes back
+]
+
+
+@pytest.mark.parametrize("kind,params,xs", LOGPDF_CASES)
+def test_oracle_logpdfs_are_the_references(oracle, ref, kind, params, xs):
+    """The restated uniform_smallint / discrete / poisson log-pdfs against the reference's own logpdf<> structs
+    (utils_uniform_smallint.hpp:17-27, utils_discrete.hpp:17-27, utils_poisson.hpp:17-36), compiled unmodified: same
+    operations in the same order, so the same bits."""
+    got = oracle.logpdf(kind, params, xs)
+    exp = ref.logpdf(kind, params, xs)
+    assert got.tobytes() == exp.tobytes(), (got, exp)

@@ -96,3 +96,25 @@ def test_reference_stats_printer_prints_the_device_estimators(engine, ref, oracl
         maps = re.findall(r"  MAP: (\d+)\n  Num points: (\d+)\n", text)
         assert len(maps) == per
         assert [int(m) for m, _ in maps] == st["int_map"].tolist() and all(int(c) == n for _, c in maps)
+
+
+@pytest.mark.parametrize("kind,params,xs", [
+    ("uniform_smallint", [0, 2], np.arange(-3, 7.0)),
+    ("uniform_smallint", [-4, 11], np.arange(-8, 16.0)),
+    ("discrete", [0.1, 0.5, 0.4], np.arange(-2, 6.0)),
+    ("discrete", [1.0, 5.0, 4.0, 2.0, 8.0], np.arange(-1, 7.0)),
+    ("discrete", [0.0, 2.0, 0.0, 6.0], np.arange(0, 4.0)),
+    ("poisson", [0.8], np.arange(0, 40.0)),
+    ("poisson", [0.0], np.arange(0, 3.0)),
+    ("poisson", [37.5], np.arange(0, 160.0)),
+    ("poisson", [1e-3], np.arange(0, 12.0)),
+])
+def test_device_logpdfs_equal_the_references(engine, ref, kind, params, xs):
+    """Rows (a)4c-4e: the device log-pdfs against the reference's own logpdf<> (utils_uniform_smallint.hpp:17-27,
+    utils_discrete.hpp:17-27, utils_poisson.hpp:17-36 compiled unmodified).  Tolerance 1e-12 relative: the device `log` is
+    this repo's own (<= 2 ulp), the sequence of operations is the reference's."""
+    got = engine.logpdf(kind, params, xs)
+    exp = ref.logpdf(kind, params, xs)
+    assert (np.isneginf(got) == np.isneginf(exp)).all()
+    fin = np.isfinite(exp)
+    np.testing.assert_allclose(got[fin], exp[fin], rtol=1e-12, atol=1e-300)
