@@ -681,31 +681,34 @@ public:
     using result_type = vecn<RealType, N>;
     using input_type = RealType;
 
-    // (means..., one sigma for every component) — multivariate_normal.hpp:38-42, :64-68
+    // The second argument is the COVARIANCE diagonal, as in the reference: every component is stored as
+    // normal_distribution(mean, sqrt(covariance)) (multivariate_normal.hpp:167-186, "boost::random::normal uses the
+    // standard deviation").  models.hpp:42 passes {sqrt(5), sqrt(3)} there, so its components have sigma 5^(1/4), 3^(1/4).
+    // (means..., one covariance for every component) — multivariate_normal.hpp:38-42, :64-68
     template<class RangeMean>
-    CPPROB_HD multivariate_normal_distribution(const RangeMean & mean, RealType sigma)
+    CPPROB_HD multivariate_normal_distribution(const RangeMean & mean, RealType covariance)
     {
         int i = 0;
-        for (auto it = mean.begin(); it != mean.end() && i < N; ++it, ++i) { mean_[i] = *it; sigma_[i] = sigma; }
+        for (auto it = mean.begin(); it != mean.end() && i < N; ++it, ++i) { mean_[i] = *it; sigma_[i] = dm::sqrt(covariance); }
     }
-    // (means..., sigmas...) — multivariate_normal.hpp:44-61, :70-75
-    template<class RangeMean, class RangeSigma>
-    CPPROB_HD multivariate_normal_distribution(const RangeMean & mean, const RangeSigma & sigma)
+    // (means..., covariances...) — multivariate_normal.hpp:44-61, :70-75
+    template<class RangeMean, class RangeCov>
+    CPPROB_HD multivariate_normal_distribution(const RangeMean & mean, const RangeCov & covariance)
     {
         int i = 0;
-        auto is = sigma.begin();
-        for (auto it = mean.begin(); it != mean.end() && i < N; ++it, ++is, ++i) { mean_[i] = *it; sigma_[i] = *is; }
+        auto is = covariance.begin();
+        for (auto it = mean.begin(); it != mean.end() && i < N; ++it, ++is, ++i) { mean_[i] = *it; sigma_[i] = dm::sqrt(*is); }
     }
-    CPPROB_HD multivariate_normal_distribution(std::initializer_list<RealType> mean, std::initializer_list<RealType> sigma)
+    CPPROB_HD multivariate_normal_distribution(std::initializer_list<RealType> mean, std::initializer_list<RealType> covariance)
     {
         int i = 0;
-        auto is = sigma.begin();
-        for (auto it = mean.begin(); it != mean.end() && i < N; ++it, ++is, ++i) { mean_[i] = *it; sigma_[i] = *is; }
+        auto is = covariance.begin();
+        for (auto it = mean.begin(); it != mean.end() && i < N; ++it, ++is, ++i) { mean_[i] = *it; sigma_[i] = dm::sqrt(*is); }
     }
-    CPPROB_HD multivariate_normal_distribution(std::initializer_list<RealType> mean, RealType sigma)
+    CPPROB_HD multivariate_normal_distribution(std::initializer_list<RealType> mean, RealType covariance)
     {
         int i = 0;
-        for (auto it = mean.begin(); it != mean.end() && i < N; ++it, ++i) { mean_[i] = *it; sigma_[i] = sigma; }
+        for (auto it = mean.begin(); it != mean.end() && i < N; ++it, ++i) { mean_[i] = *it; sigma_[i] = dm::sqrt(covariance); }
     }
 
     CPPROB_HD RealType mean(int i) const { return mean_[i]; }

@@ -125,13 +125,14 @@ struct poisson_distribution {
 struct multivariate_normal_distribution {
     using result_type = std::vector<double>;
     std::vector<normal_distribution<>> distr_;
-    multivariate_normal_distribution(const std::vector<double> & mean, const std::vector<double> & sigma)
+    // the second argument is the covariance diagonal; the components carry its square root (multivariate_normal.hpp:167-186)
+    multivariate_normal_distribution(const std::vector<double> & mean, const std::vector<double> & covariance)
     {
-        for (std::size_t i = 0; i < mean.size(); ++i) distr_.emplace_back(mean[i], sigma[i]);
+        for (std::size_t i = 0; i < mean.size(); ++i) distr_.emplace_back(mean[i], std::sqrt(covariance[i]));
     }
-    multivariate_normal_distribution(const std::vector<double> & mean, double sigma)
+    multivariate_normal_distribution(const std::vector<double> & mean, double covariance)
     {
-        for (double m : mean) distr_.emplace_back(m, sigma);
+        for (double m : mean) distr_.emplace_back(m, std::sqrt(covariance));
     }
     template<class G> result_type operator()(G & g) const
     {

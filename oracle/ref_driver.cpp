@@ -9,6 +9,8 @@
 //     include/cpprob/utils.hpp, include/cpprob/traits.hpp   (helpers the above include)
 //     include/cpprob/distributions/utils_{discrete,uniform_smallint,poisson}.hpp   logpdf<> of the three distributions no
 //                                                           reference test pins (:17-27, :17-27, :17-36)
+//     include/cpprob/distributions/utils_normal_distribution.hpp (:20-45), utils_uniform_real.hpp (:21-31),
+//     utils_multivariate_normal.hpp (:20-33) + multivariate_normal.hpp   the log-pdfs of the README / BASELINE models
 // None of those files is copied or modified.  The third-party headers they name and this image lacks are
 // stood in for by oracle/ref_shim/ (Boost has_less, filesystem::path/exists, declarations of mpl::at_c and
 // function_types::*; and an empty cpprob/state.hpp, which stats_printer.hpp includes but does not use and
@@ -30,13 +32,17 @@
 
 #include "cpprob/postprocess/stats_printer.hpp"
 
-// The three log-pdf headers of the reference that no reference test pins and that need
-// nothing but a Boost.Random distribution type: compiled unmodified; Boost's classes are stood in for by accessor-only
-// shims (oracle/ref_shim/boost/random/), the FlatBuffers names their CSIS members mention by a declaration-only stub.
+// The log-pdf headers of the reference.  Their logpdf<> bodies need nothing but the accessors
+// of a Boost.Random distribution type (and pi): compiled unmodified; Boost's classes are stood in for by accessor-only
+// shims (oracle/ref_shim/boost/random/, boost/math/constants: the correctly rounded pi), the FlatBuffers and Boost.Math
+// names their CSIS members mention by declaration-only stubs.
 namespace cpprob { template<class IntType, class RealType> class min_max_discrete_distribution; }   // named by proposal<uniform_smallint>
 #include "cpprob/distributions/utils_discrete.hpp"
 #include "cpprob/distributions/utils_uniform_smallint.hpp"
 #include "cpprob/distributions/utils_poisson.hpp"
+#include "cpprob/distributions/utils_normal_distribution.hpp"
+#include "cpprob/distributions/utils_uniform_real.hpp"
+#include "cpprob/distributions/utils_multivariate_normal.hpp"
 
 namespace {
 
@@ -75,7 +81,8 @@ const char * ref_describe(void)
 {
     return "reference code compiled from /root/reference/include: cpprob/serialization.hpp, cpprob/ndarray.hpp, "
            "cpprob/postprocess/empirical_distribution.hpp, cpprob/postprocess/stats_printer.hpp, "
-           "cpprob/distributions/utils_discrete.hpp, utils_uniform_smallint.hpp, utils_poisson.hpp";
+           "cpprob/distributions/utils_discrete.hpp, utils_uniform_smallint.hpp, utils_poisson.hpp, "
+           "utils_normal_distribution.hpp, utils_uniform_real.hpp, utils_multivariate_normal.hpp, multivariate_normal.hpp";
 }
 
 // ---- writer: serialization.hpp operator<< with dump_predicts' stream state --------------------------------------
@@ -177,12 +184,23 @@ int ref_empirical_int(const int * x, const double * log_w, unsigned long long n,
     return k;
 }
 
-// ---- logpdf<> of utils_uniform_smallint.hpp:17-27 (kind 2), utils_discrete.hpp:17-27 (3), utils_poisson.hpp:17-36 (4) ------
+// ---- logpdf<> of utils_normal_distribution.hpp:20-45 (kind 0), utils_uniform_real.hpp:21-31 (1),
+// utils_uniform_smallint.hpp:17-27 (2), utils_discrete.hpp:17-27 (3), utils_poisson.hpp:17-36 (4) ------
 // kind ids and parameter layout are those of include/cpprob_sis.h (CPPROB_SIS_DIST_*)
 int ref_logpdf(int kind, const double * q, int nq, const double * x, unsigned long long n, double * out)
 {
     for (unsigned long long i = 0; i < n; ++i) {
         switch (kind) {
+        case 0: {
+            const boost::random::normal_distribution<double> d(q[0], q[1]);
+            out[i] = cpprob::logpdf<boost::random::normal_distribution<double>>()(d, x[i]);
+            break;
+        }
+        case 1: {
+            const boost::random::uniform_real_distribution<double> d(q[0], q[1]);
+            out[i] = cpprob::logpdf<boost::random::uniform_real_distribution<double>>()(d, x[i]);
+            break;
+        }
         case 2: {
             const boost::random::uniform_smallint<long long> d(static_cast<long long>(q[0]), static_cast<long long>(q[1]));
             out[i] = cpprob::logpdf<boost::random::uniform_smallint<long long>>()(d, static_cast<long long>(x[i]));
@@ -200,6 +218,19 @@ int ref_logpdf(int kind, const double * q, int nq, const double * x, unsigned lo
         }
         default: return -1;
         }
+    }
+    return 0;
+}
+
+// ---- logpdf<multivariate_normal_distribution> (utils_multivariate_normal.hpp:20-33): n points of dimension dim, the
+// distribution built from (mean[dim], covariance[dim]) as models.hpp does (multivariate_normal.hpp:211-213; the components
+// get sigma = sqrt(covariance), :178-186)
+int ref_logpdf_mvn(const double * mean, const double * covariance, int dim, const double * x, unsigned long long n, double * out)
+{
+    const cpprob::multivariate_normal_distribution<double> d(mean, mean + dim, covariance, covariance + dim);
+    for (unsigned long long i = 0; i < n; ++i) {
+        const cpprob::NDArray<double> xi(std::vector<double>(x + i * dim, x + (i + 1) * dim));
+        out[i] = cpprob::logpdf<cpprob::multivariate_normal_distribution<double>>()(d, xi);
     }
     return 0;
 }

@@ -15,8 +15,16 @@ namespace protocol {
 struct Discrete;
 struct Poisson;
 struct UniformDiscrete;
+struct Normal;
+struct UniformContinuous;
+struct MultivariateNormal;
+struct NDArray;
 template<class... A> flatbuffers::Offset<Discrete> CreateDiscrete(A &&...);
 template<class... A> flatbuffers::Offset<Poisson> CreatePoisson(A &&...);
 template<class... A> flatbuffers::Offset<UniformDiscrete> CreateUniformDiscrete(A &&...);
+template<class... A> flatbuffers::Offset<Normal> CreateNormal(A &&...);
+template<class... A> flatbuffers::Offset<UniformContinuous> CreateUniformContinuous(A &&...);
+template<class... A> flatbuffers::Offset<MultivariateNormal> CreateMultivariateNormal(A &&...);
+template<class... A> flatbuffers::Offset<NDArray> CreateNDArray(A &&...);
 }
 #endif

@@ -1,7 +1,7 @@
 """ctypes wrapper of oracle/_ref/libcpprob_ref.so — TEST INFRASTRUCTURE.
 
 That library is the REFERENCE'S OWN serialization / NDArray / EmpiricalDistribution / StatsPrinter headers and its
-uniform_smallint / discrete / poisson log-pdf headers, compiled from
+log-pdf headers (normal, uniform_real, uniform_smallint, discrete, poisson, diagonal multivariate normal), compiled from
 /root/reference by oracle/Makefile (target _ref) behind the C driver oracle/ref_driver.cpp.  It is built in the container
 that has /root/reference and travels to the GPU box as a built file; nothing here reads /root/reference at run time."""
 import ctypes as C
@@ -37,6 +37,7 @@ class Ref:
         L.ref_empirical_int.argtypes = [ip, dp, C.c_uint64, C.c_int, ip, dp, ip, u64p]
         L.ref_stats_text.argtypes = [C.c_char_p]
         L.ref_logpdf.argtypes = [C.c_int, dp, C.c_int, dp, C.c_uint64, dp]
+        L.ref_logpdf_mvn.argtypes = [dp, dp, C.c_int, dp, C.c_uint64, dp]
         L.ref_stats_text.restype = C.c_char_p
         self.L = L
 
@@ -127,13 +128,23 @@ class Ref:
         assert k >= 0
         return dict(zip(values[:k].tolist(), probs[:k].tolist())), mp.value, npts.value
 
-    # ---- logpdf<> of utils_uniform_smallint.hpp / utils_discrete.hpp / utils_poisson.hpp ----
+    # ---- logpdf<> of utils_normal_distribution.hpp / utils_uniform_real.hpp / utils_uniform_smallint.hpp / utils_discrete.hpp / utils_poisson.hpp ----
     def logpdf(self, kind, params, x):
-        kinds = {"uniform_smallint": 2, "discrete": 3, "poisson": 4}
+        kinds = {"normal": 0, "uniform_real": 1, "uniform_smallint": 2, "discrete": 3, "poisson": 4}
         params, x = np.ascontiguousarray(params, np.float64), np.ascontiguousarray(x, np.float64)
         out = np.empty_like(x)
         dp = C.POINTER(C.c_double)
         assert self.L.ref_logpdf(kinds[kind], params.ctypes.data_as(dp), params.size, x.ctypes.data_as(dp), x.size, out.ctypes.data_as(dp)) == 0
+        return out
+
+    def logpdf_mvn(self, mean, covariance, x):
+        """logpdf<multivariate_normal_distribution> (utils_multivariate_normal.hpp:20-33) at the rows of x[n][dim]; the second
+        argument is the covariance diagonal (the reference takes its square root, multivariate_normal.hpp:178-186)."""
+        mean, sigma = np.ascontiguousarray(mean, np.float64), np.ascontiguousarray(covariance, np.float64)
+        x = np.ascontiguousarray(x, np.float64).reshape(-1, mean.size)
+        out = np.empty(x.shape[0])
+        dp = C.POINTER(C.c_double)
+        assert self.L.ref_logpdf_mvn(mean.ctypes.data_as(dp), sigma.ctypes.data_as(dp), mean.size, x.ctypes.data_as(dp), x.shape[0], out.ctypes.data_as(dp)) == 0
         return out
 
     # ---- StatsPrinter ----
@@ -142,6 +153,26 @@ class Ref:
         r = subprocess.run([STATS_PRINTER, prefix], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         return r.stdout
+
+
+def ref_log_w(ref, model, obs, values):
+    """log_w of one trace: `log_w += logpdf(distr, x)` per observe statement in program order (state.cpp:212-223,
+    cpprob.hpp:79-90), every term from the REFERENCE'S logpdf<> and added in IEEE double (Python floats)."""
+    lw = 0.0
+    if model in ("gaussian_unknown_mean", "gaussian_unknown_mean_mu"):
+        sd = 2.0 if model == "gaussian_unknown_mean" else np.sqrt(2.0)
+        for y in obs:
+            lw += float(ref.logpdf("normal", [values[0], sd], [y])[0])
+    elif model == "linear_gaussian_1d":
+        for state, y in zip(values, obs):
+            lw += float(ref.logpdf("normal", [state, 1.0], [y])[0])
+    elif model == "hmm":
+        for s, y in zip(values, obs):
+            lw += float(ref.logpdf("normal", [[-1.0, 0.0, 1.0][int(s)], 1.0], [y])[0])
+    elif model == "gaussian_2d_unk_mean":
+        s2 = np.sqrt(2.0)
+        lw += float(ref.logpdf_mvn(values, [s2, s2], obs)[0])
+    return lw
 
 
 _cached = None

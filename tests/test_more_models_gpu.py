@@ -33,9 +33,11 @@ def test_gaussian_2d_posterior_and_file_format(engine, oracle, tmp_path):
     y = [3.0, 4.0]
     n = 1 << 22
     st = engine.run("gaussian_2d_unk_mean", y, n)
-    for i, (m0, s0) in enumerate(((1.0, math.sqrt(5)), (2.0, math.sqrt(3)))):
-        prec = 1 / s0 ** 2 + 1 / 2.0
-        assert abs(st["real_mean"][i] - (m0 / s0 ** 2 + y[i] / 2.0) / prec) < 5e-3
+    # the reference's multivariate normal takes the COVARIANCE diagonal (multivariate_normal.hpp:178-186 stores its square
+    # root as the component's sigma): models.hpp:42-46 therefore has prior variances sqrt 5, sqrt 3 and noise variance sqrt 2
+    for i, (m0, c0) in enumerate(((1.0, math.sqrt(5)), (2.0, math.sqrt(3)))):
+        prec = 1 / c0 + 1 / math.sqrt(2.0)
+        assert abs(st["real_mean"][i] - (m0 / c0 + y[i] / math.sqrt(2.0)) / prec) < 5e-3
         assert abs(st["real_var"][i] - 1 / prec) < 5e-3
     prefix = str(tmp_path / "g2")
     st = engine.infer_to_files("gaussian_2d_unk_mean", y, 5000, prefix)

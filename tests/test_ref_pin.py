@@ -130,3 +130,34 @@ def test_oracle_logpdfs_are_the_references(oracle, ref, kind, params, xs):
     got = oracle.logpdf(kind, params, xs)
     exp = ref.logpdf(kind, params, xs)
     assert got.tobytes() == exp.tobytes(), (got, exp)
+
+
+def test_oracle_normal_and_uniform_logpdfs_are_the_references(oracle, ref):
+    """Rows (a)4a / 4b on the reference's own test grid (tests/cpprob/logpdf.cpp:23-35: mu and x in -10..10 by 0.5, sigma
+    0.5..10 by 0.5; :61-78 for the uniform) plus the special cases of utils_normal_distribution.hpp:28-36: same bits."""
+    grid = np.arange(-10, 10.25, 0.5)
+    xs = np.concatenate([grid, [np.inf, -np.inf, 1e-300, 1e300, -0.0]])
+    for mu in grid:
+        for sd in np.arange(0.5, 10.25, 0.5):
+            assert oracle.logpdf("normal", [mu, sd], xs).tobytes() == ref.logpdf("normal", [mu, sd], xs).tobytes()
+    for mu, sd in [(1.0, 0.0), (0.7, 2 ** 0.5), (-3.0, 1e-8), (2.0, 1e12)]:
+        x = np.concatenate([xs, [mu]])
+        assert oracle.logpdf("normal", [mu, sd], x).tobytes() == ref.logpdf("normal", [mu, sd], x).tobytes()
+    for a, b in [(2.0, 9.5), (-1.0, 1.0), (0.0, 1e-9), (-1e6, 1e6)]:
+        x = np.concatenate([np.linspace(a - 1, b + 1, 101), [a, b, np.nextafter(a, -np.inf), np.nextafter(b, np.inf)]])
+        assert oracle.logpdf("uniform_real", [a, b], x).tobytes() == ref.logpdf("uniform_real", [a, b], x).tobytes()
+
+
+@pytest.mark.parametrize("model,obs_key,per", [("gaussian_unknown_mean", None, 1), ("gaussian_unknown_mean_mu", None, 1),
+                                                ("linear_gaussian_1d", "obs_linear_gaussian_32", 32), ("hmm", "obs_hmm_64", 64),
+                                                ("hmm", "obs_hmm_1000", 1000), ("gaussian_2d_unk_mean", "2d", 2)])
+def test_oracle_log_weights_are_the_references_logpdfs_accumulated(oracle, ref, model, obs_key, per):
+    """Row (a)5: the oracle's replayed log-weights equal, BIT FOR BIT, the sum the reference's own logpdf<> code gives when
+    accumulated statement by statement in program order."""
+    rng = np.random.default_rng(11)
+    obs = [3.0, 4.0] if obs_key is None else ([1.5, 2.5] if obs_key == "2d" else G[obs_key])
+    n = 64 if per < 1000 else 8
+    values = rng.integers(0, 3, (n, per)).astype(np.float64) if model == "hmm" else rng.normal(0.5, 2.0, (n, per))
+    got = oracle.replay_logw(model, obs, values)
+    exp = np.array([ref_lib.ref_log_w(ref, model, obs, v) for v in values])
+    assert got.tobytes() == exp.tobytes(), np.abs(got - exp).max()

@@ -118,3 +118,23 @@ def test_device_logpdfs_equal_the_references(engine, ref, kind, params, xs):
     assert (np.isneginf(got) == np.isneginf(exp)).all()
     fin = np.isfinite(exp)
     np.testing.assert_allclose(got[fin], exp[fin], rtol=1e-12, atol=1e-300)
+
+
+@pytest.mark.parametrize("model,obs_key,per", [("gaussian_unknown_mean", None, 1), ("linear_gaussian_1d", "obs_linear_gaussian_32", 32),
+                                                ("hmm", "obs_hmm_64", 64), ("hmm", "obs_hmm_1000", 1000),
+                                                ("gaussian_2d_unk_mean", "2d", 2)])
+def test_device_log_weights_equal_the_references_logpdfs_accumulated(engine, ref, model, obs_key, per):
+    """Row (a)5 against the reference's own code: the log-weight the device computes for a given trace equals the sum of the
+    reference's logpdf<> values (utils_normal_distribution.hpp:20-45, utils_multivariate_normal.hpp:20-33 compiled
+    unmodified) accumulated statement by statement, within 1e-12 relative (the device `log` is this repo's own, <= 2 ulp)."""
+    rng = np.random.default_rng(12)
+    obs = [3.0, 4.0] if obs_key is None else ([1.5, 2.5] if obs_key == "2d" else G[obs_key])
+    n = 256 if per < 1000 else 16
+    if model == "hmm":
+        values = rng.integers(0, 3, (n, per))
+        got = engine.replay(model, obs, int_rows=values.T.astype(np.int32))
+    else:
+        values = rng.normal(0.5, 2.0, (n, per))
+        got = engine.replay(model, obs, real_rows=values.T)
+    exp = np.array([ref_lib.ref_log_w(ref, model, obs, v) for v in values])
+    np.testing.assert_allclose(got, exp, rtol=1e-12)
