@@ -28,7 +28,7 @@ SYMBOLS = [
     "cpprob_sis_sample", "cpprob_sis_philox", "cpprob_sis_dmath", "cpprob_sis_measure_dfma_peak",
     "cpprob_sis_measure_store_peak", "cpprob_sis_plan_shard", "cpprob_sis_probe_issue", "cpprob_sis_probe_dfma_chains", "cpprob_sis_run_multi", "cpprob_sis_write_summary",
     "cpprob_sis_text_stage_stats", "cpprob_sis_plan_rows", "cpprob_sis_merge_padded",
-    "cpprob_sis_set_seed", "cpprob_sis_infer_to_files_multi", "cpprob_sis_comm_get_id", "cpprob_sis_comm_init", "cpprob_sis_comm_init_local", "cpprob_sis_comm_destroy", "cpprob_sis_run_dist",
+    "cpprob_sis_set_seed", "cpprob_sis_infer_to_files_multi", "cpprob_sis_comm_get_id", "cpprob_sis_comm_init", "cpprob_sis_comm_init_local", "cpprob_sis_comm_destroy", "cpprob_sis_comm_exchange", "cpprob_sis_run_dist",
 ]
 COMM_ID_BYTES = 128
 
@@ -124,6 +124,7 @@ def lib():
         L.cpprob_sis_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.cpprob_sis_comm_init_local.argtypes = [C.POINTER(C.c_void_p), C.c_int]
         L.cpprob_sis_comm_destroy.argtypes = [C.c_void_p]
+        L.cpprob_sis_comm_exchange.argtypes = [C.c_void_p]
         L.cpprob_sis_run_dist.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t, u64, C.POINTER(Stats)]
         L.cpprob_sis_text_stage_stats.argtypes = [C.c_void_p, dp, dp, dp, C.POINTER(u64), C.POINTER(u64)]
         L.cpprob_sis_probe_issue.argtypes = [C.c_void_p, C.c_int, dp]
@@ -306,12 +307,45 @@ class Engine:
         buf = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(bytes(comm_id))
         _check(self._L.cpprob_sis_comm_init(self._h, buf, rank, world))
 
+    def comm_exchange(self):
+        """How this engine's communicator moves the partial rows: "none" (one rank), "nccl" or "peer" (peer memory)."""
+        return ("none", "nccl", "peer")[self._L.cpprob_sis_comm_exchange(self._h)]
+
     def run_dist(self, model, obs, n_total):
         """cpprob_sis_run_dist (collective): this rank's shard, one NCCL all-gather, the merge; bit-identical everywhere."""
         obs = _f64(obs)
         st = Stats()
         _check(self._L.cpprob_sis_run_dist(self._h, self.model_id(model), _dptr(obs), obs.size, int(n_total), C.byref(st)))
         return stats_to_dict(st)
+
+    def prepared(self, model, obs, n_total, dist=False):
+        """A zero-argument callable that makes exactly one cpprob_sis_run (dist=False) or cpprob_sis_run_dist call with
+        everything marshalled beforehand and returns the raw Stats struct (valid until the engine's next call;
+        stats_to_dict turns it into the usual dict).  For timing loops: nothing but the C-ABI call is inside."""
+        obs = _f64(obs)
+        obs_p, n_obs, mid, n = _dptr(obs), obs.size, self.model_id(model), C.c_uint64(int(n_total))
+        st, h = Stats(), self._h
+        st_ref = C.byref(st)
+        if dist:
+            fn = self._L.cpprob_sis_run_dist
+
+            def call():
+                rc = fn(h, mid, obs_p, n_obs, n, st_ref)
+                if rc < 0:
+                    _check(rc)
+                return st
+        else:
+            fn = self._L.cpprob_sis_run
+            opt = RunOptions(EMIT_NONE, 0, C.cast(None, BLOCK_FN), None)
+            opt_ref = C.byref(opt)
+
+            def call():
+                rc = fn(h, mid, obs_p, n_obs, n, opt_ref, st_ref)
+                if rc < 0:
+                    _check(rc)
+                return st
+        call.keepalive = (obs, st)
+        return call
 
     def run_shard(self, model, obs, n_total, rank, world, m_ref=None):
         obs = _f64(obs)

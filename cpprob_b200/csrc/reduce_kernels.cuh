@@ -149,9 +149,11 @@ __global__ void __launch_bounds__(kBlock) k_rows_hist(const int * __restrict__ i
 // raw[3 t] = max log_w of pilot tile t; raw[0] becomes m_ref: the override if given, else the maximum if it is
 // finite and sane, else 0 (every pilot weight was -inf / nan).
 // ------------------------------------------------------------------------------------------------
-__global__ void k_pilot_finalize(double * raw, int tiles, int has_override, double override_value)
+// Also zeroes the unit counter of the particle kernel that follows (no memset node between the kernels).
+__global__ void k_pilot_finalize(double * raw, int tiles, int has_override, double override_value, unsigned * unit_counter)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (unit_counter) *unit_counter = 0u;
     double mx = dm::neg_inf();
     for (int t = 0; t < tiles; ++t) mx = fmax(mx, raw[3 * t]);
     const double m = (mx > -1.0e300 && mx < 1.0e300) ? mx : 0.0;
@@ -186,9 +188,12 @@ __global__ void __launch_bounds__(kBlock) k_fold_rows(const double * __restrict_
 // The input is the concatenation of every rank's partials in chunk order, so the result is
 // bit-identical on every rank and for every GPU count.
 // ------------------------------------------------------------------------------------------------
+// out[n_cols] = *m_ref_dev (when given): the run's reference log-weight comes back with the sums, in one copy.
 __global__ void __launch_bounds__(kBlock) k_merge_columns(const double * __restrict__ partials, unsigned n_rows, int n_cols,
-                                                          unsigned long long max_mask, double * __restrict__ out)
+                                                          unsigned long long max_mask, double * __restrict__ out,
+                                                          const double * __restrict__ m_ref_dev)
 {
+    if (blockIdx.x == 0 && threadIdx.x == 32 && m_ref_dev) out[n_cols] = *m_ref_dev;
     __shared__ double smem[kWarps];
     const int c = blockIdx.x;
     const bool is_max = c < 64 && ((max_mask >> c) & 1ull);
@@ -213,9 +218,96 @@ struct gather_layout {
     unsigned rows_per_rank;
 };
 
-__global__ void __launch_bounds__(kBlock) k_merge_columns_gathered(const double * __restrict__ gathered, const __grid_constant__ gather_layout lay,
-                                                                   int n_cols, unsigned long long max_mask, double * __restrict__ out)
+// ------------------------------------------------------------------------------------------------
+// The exchange of a multi-GPU inference over peer memory (NVLink / NVSwitch), fused with the kernels on either side of it.
+// Every rank owns a window: [kPeerFlagBytes of flags][two gather buffers]; every rank holds a pointer to every other rank's
+// window (cudaIpcOpenMemHandle between processes, cudaDeviceEnablePeerAccess within one).
+//   k_push_rows      (the producer's last step): this rank's partial rows are stored straight into its segment of EVERY
+//                    rank's gather buffer (its own included), then — by the last CTA to finish, after a system-wide fence
+//                    — the inference's epoch into its slot of every rank's flag array;
+//   k_merge_columns_gathered (the consumer): waits until all `world` flags of its own window carry the epoch, then merges
+//                    the gathered rows where they lie.
+// No NCCL kernel, no host round trip: the exchange costs one small kernel and the NVLink latency of a store + a flag.
+// Two gather buffers alternate by the epoch's parity: a rank can run at most one inference ahead of the slowest peer (its
+// next merge waits for that peer's push, which that peer's stream orders behind its own previous merge).
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned kPeerFlagBytes = 1024;     // 64 epoch slots (unsigned long long) + an error word + the push kernel's CTA counter
+constexpr unsigned kPeerErrorWord = 64;       // index (in unsigned long long) of the error word
+constexpr unsigned kPeerDoneWord = 65;        // index of the CTA-done counter of k_push_rows (local use only)
+
+struct peer_targets {
+    unsigned char * window[kMaxMergeRanks];   // every rank's window as seen from this device
+    unsigned world;
+    unsigned rank;
+};
+
+__global__ void __launch_bounds__(kBlock) k_push_rows(const double * __restrict__ rows, unsigned long long n_doubles,
+                                                      const __grid_constant__ peer_targets t, unsigned long long buffer_offset_bytes,
+                                                      unsigned long long segment_doubles, unsigned long long epoch)
 {
+    // rows[0, n_doubles) -> window[p] + buffer_offset + rank * segment, for every p
+    const unsigned long long i0 = blockIdx.x * static_cast<unsigned long long>(kBlock) + threadIdx.x;
+    const unsigned long long step = static_cast<unsigned long long>(gridDim.x) * kBlock;
+    for (unsigned long long i = i0; i < n_doubles; i += step) {
+        const double v = rows[i];
+        for (unsigned p = 0; p < t.world; ++p) {
+            double * dst = reinterpret_cast<double *>(t.window[p] + buffer_offset_bytes) + static_cast<unsigned long long>(t.rank) * segment_doubles;
+            dst[i] = v;
+        }
+    }
+    // the last CTA to get here publishes the epoch (the pattern of the threadFenceReduction sample, at system scope)
+    __shared__ bool last;
+    __threadfence_system();
+    __syncthreads();
+    unsigned long long * const mine = reinterpret_cast<unsigned long long *>(t.window[t.rank]);
+    if (threadIdx.x == 0) {
+        const unsigned long long done = atomicAdd(mine + kPeerDoneWord, 1ull);
+        last = done + 1 == gridDim.x;
+    }
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) mine[kPeerDoneWord] = 0ull;             // ready for the next launch
+    __threadfence_system();
+    if (threadIdx.x < t.world) {
+        volatile unsigned long long * flag = reinterpret_cast<volatile unsigned long long *>(t.window[threadIdx.x]) + t.rank;
+        *flag = epoch;
+    }
+}
+
+// the consumer's wait: all `world` slots of this rank's own flag array reach `epoch` (or ~20 s pass: a peer died; the
+// error word is raised, the merge goes on over whatever is there and the host reports the failure)
+__device__ __forceinline__ void peer_wait(const unsigned long long * flags_in, unsigned world, unsigned long long epoch)
+{
+    if (threadIdx.x < world) {
+        const volatile unsigned long long * f = flags_in + threadIdx.x;
+        unsigned long long t0 = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        unsigned spins = 0;
+        while (*f < epoch) {
+            if ((++spins & 0x3ffu) == 0u) {
+                unsigned long long t1 = 0;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 20000000000ull) {
+                    const_cast<unsigned long long *>(flags_in)[kPeerErrorWord] = epoch;
+                    break;
+                }
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+}
+
+// With `peer_flags` the rows were pushed by the peers themselves (k_push_rows): wait for their epoch flags first and read
+// the rows past L1 (they were written by other GPUs).
+__global__ void __launch_bounds__(kBlock) k_merge_columns_gathered(const double * gathered, const __grid_constant__ gather_layout lay,
+                                                                   int n_cols, unsigned long long max_mask, double * __restrict__ out,
+                                                                   const double * __restrict__ m_ref_dev,
+                                                                   const unsigned long long * peer_flags, unsigned long long epoch)
+{
+    if (peer_flags) peer_wait(peer_flags, lay.world, epoch);
+    if (blockIdx.x == 0 && threadIdx.x == 32 && m_ref_dev) out[n_cols] = *m_ref_dev;
+    if (blockIdx.x == 0 && threadIdx.x == 33 && peer_flags) out[n_cols + 1] = peer_flags[kPeerErrorWord] == epoch ? 1.0 : 0.0;
     __shared__ double smem[kWarps];
     const int c = blockIdx.x;
     const bool is_max = c < 64 && ((max_mask >> c) & 1ull);
@@ -226,7 +318,7 @@ __global__ void __launch_bounds__(kBlock) k_merge_columns_gathered(const double 
     for (unsigned r = threadIdx.x; r < n_rows; r += kBlock) {
         while (r >= lay.first[rank + 1]) ++rank;                  // rows only grow: the owner is found by walking on
         const size_t phys = static_cast<size_t>(rank) * lay.rows_per_rank + (r - lay.first[rank]);
-        const double x = gathered[phys * n_cols + c];
+        const double x = __ldcg(gathered + phys * n_cols + c);
         v[0] = is_max ? fmax(v[0], x) : v[0] + x;
     }
     const double res = block_reduce<1>(v, is_max ? 1ull : 0ull, smem);

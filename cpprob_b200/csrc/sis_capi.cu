@@ -208,6 +208,16 @@ struct cpprob_sis_engine {
     // communicator of a multi-GPU run (cpprob_sis_comm_init / _init_local); rank 0 of 1 without one
     ncclComm_t comm = nullptr;
     int comm_rank = 0, comm_world = 1;
+    // peer window of the communicator's ranks (reduce_kernels.cuh, k_push_rows): the exchange of an inference goes through
+    // it when every rank could map every other rank's window; otherwise (or with CPPROB_SIS_EXCHANGE=nccl) ncclAllGather
+    struct peer_window {
+        unsigned char * local = nullptr;                   // [kPeerFlagBytes][2][buffer_bytes]
+        unsigned char * peer[kMaxMergeRanks] = {};         // peer[comm_rank] == local
+        bool opened[kMaxMergeRanks] = {};                  // mapped with cudaIpcOpenMemHandle (to be closed)
+        size_t buffer_bytes = 0;
+        unsigned long long epoch = 0;
+        bool ready = false;
+    } pw;
 
     // results kept alive for the caller
     model_structure structure;
@@ -409,8 +419,8 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     const int n_real = static_cast<int>(e->structure.n_real);
     const int n_int = static_cast<int>(e->structure.n_int);
     const shard_plan plan = plan_shard(n_total, rank, world);
-    if (plan.n_chunks_local > (1u << 28)) {      // the fused kernel counts (chunk, warp slot) units in 32 bits
-        return fail(CPPROB_SIS_EINVAL, "more than 2^43 (8.8e12) particles per GPU in one call");
+    if (plan.n_chunks_local > (1u << 27)) {      // the fused kernel counts (chunk, part <= 4, warp slot) units in 32 bits
+        return fail(CPPROB_SIS_EINVAL, "more than 2^42 (4.4e12) particles per GPU in one call");
     }
     res->plan = plan;
     res->launches = 0;
@@ -443,12 +453,14 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     const bool fused_early = fused || staged_warps >= kMinStagedWarps;
     if (fused_early) {
         const int n_pilot = static_cast<int>(std::min<uint64_t>(n_total, kPilot));
+        // Nothing but kernels between here and the end of the particle pass: the finalize kernel also zeroes the unit
+        // counter, and m_ref is read back with the results (copy-engine operations in the middle of the chain cost
+        // several microseconds each, which is what a short run — one GPU's share of a strong-scaling run — is made of).
         CU_TRY(e->h_pilot.reserve(1));
         CU_TRY(vt->launch_pilot(e->compute, &keys, e->d_obs.ptr, static_cast<int>(n_obs), n_pilot, e->d_pilot.ptr));
         k_pilot_finalize<<<1, 32, 0, e->compute>>>(e->d_pilot.ptr, (n_pilot + 511) / 512, m_ref_override ? 1 : 0,
-                                                  m_ref_override ? *m_ref_override : 0.0);
+                                                  m_ref_override ? *m_ref_override : 0.0, e->d_counter.ptr);
         CU_TRY(cudaGetLastError());
-        CU_TRY(cudaMemcpyAsync(e->h_pilot.ptr, e->d_pilot.ptr, sizeof(double), cudaMemcpyDeviceToHost, e->compute));
         res->launches += 2;
     } else {
         if (int rc = run_pilot(e, vt, keys, n_obs, n_total, m_ref_override, pilot)) return rc;
@@ -496,8 +508,14 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         res->n_rows_local = kernel_rows;
     }
     res->rows = nullptr;
+    // m_ref to the host, queued behind the kernels (a caller that goes on to the merge gets it from there instead)
+    auto fetch_m_ref = [&]() -> int {
+        CU_TRY(cudaMemcpyAsync(e->h_pilot.ptr, e->d_pilot.ptr, sizeof(double), cudaMemcpyDeviceToHost, e->compute));
+        return 0;
+    };
     if (plan.n_chunks_local == 0) {
         if (fused_early) {                     // a rank without particles still reports the run's m_ref
+            if (int rc = fetch_m_ref()) return rc;
             CU_TRY(cudaStreamSynchronize(e->compute));
             res->m_ref = e->h_pilot.ptr[0];
         }
@@ -541,11 +559,11 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         a.n_int = n_int;
         CU_TRY(e->d_warp_partials.reserve(static_cast<size_t>(units) * n_cols));
         a.warp_partials = e->d_warp_partials.ptr;
-        CU_TRY(cudaMemsetAsync(e->d_counter.ptr, 0, sizeof(unsigned), e->compute));
+        if (!fused_early) CU_TRY(cudaMemsetAsync(e->d_counter.ptr, 0, sizeof(unsigned), e->compute));   // else: zeroed by k_pilot_finalize
         CU_TRY(vt->launch_staged(e->compute, grid, staged_warps, &a));
         const unsigned long long fold_n = static_cast<unsigned long long>(kernel_rows) * n_cols;
         k_fold_warp_partials<<<static_cast<unsigned>((fold_n + kBlock - 1) / kBlock), kBlock, 0, e->compute>>>(
-            e->d_warp_partials.ptr, kernel_rows, n_cols, e->d_partials.ptr, n_cols);
+            e->d_warp_partials.ptr, kernel_rows, n_cols, e->d_partials.ptr, n_cols, kSlotsPerChunk);
         CU_TRY(cudaGetLastError());
         res->launches += 2;
         if (int rc = fold_rows()) return rc;
@@ -554,6 +572,7 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
             res->waiting = true;
             return 0;
         }
+        if (fused_early) { if (int rc = fetch_m_ref()) return rc; }
         CU_TRY(cudaStreamSynchronize(e->compute));
         if (fused_early) res->m_ref = e->h_pilot.ptr[0];
         float ms = 0.f;
@@ -568,20 +587,19 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         if (occ <= 0) occ = 1;
         if (e->blocks_per_sm > 0) occ = std::min(occ, e->blocks_per_sm);
         // warp-autonomous kernel: enough CTAs to give every (chunk, warp slot) unit a warp, at most the resident set
-        const uint64_t ctas_needed = (static_cast<uint64_t>(plan.n_chunks_local) * kSlotsPerChunk * 32 + fused_block(nr) - 1) / fused_block(nr);
+        const uint64_t ctas_needed = (static_cast<uint64_t>(plan.n_chunks_local) * kFusedRowsPerChunk * 32 + fused_block(nr) - 1) / fused_block(nr);
         const int grid = static_cast<int>(std::min<uint64_t>(ctas_needed, static_cast<uint64_t>(e->sm_count) * occ));
         a.first_particle = plan.first_particle;
         a.n_particles = plan.n_local;
         a.n_chunks = plan.n_chunks_local;
         a.partials = e->d_partials.ptr;
         const int nv = kBaseCols + 2 * nr;
-        CU_TRY(e->d_warp_partials.reserve(static_cast<size_t>(plan.n_chunks_local) * kSlotsPerChunk * nv));
+        CU_TRY(e->d_warp_partials.reserve(static_cast<size_t>(plan.n_chunks_local) * kFusedRowsPerChunk * nv));
         a.warp_partials = e->d_warp_partials.ptr;
-        CU_TRY(cudaMemsetAsync(e->d_counter.ptr, 0, sizeof(unsigned), e->compute));
-        CU_TRY(vt->launch_fused(e->compute, grid, nr, &a));
+        CU_TRY(vt->launch_fused(e->compute, grid, nr, &a));      // (unit counter: zeroed by k_pilot_finalize)
         const unsigned long long fold_n = static_cast<unsigned long long>(plan.n_chunks_local) * nv;
         k_fold_warp_partials<<<static_cast<unsigned>((fold_n + kBlock - 1) / kBlock), kBlock, 0, e->compute>>>(
-            e->d_warp_partials.ptr, plan.n_chunks_local, nv, e->d_partials.ptr, n_cols);
+            e->d_warp_partials.ptr, plan.n_chunks_local, nv, e->d_partials.ptr, n_cols, kFusedRowsPerChunk);
         CU_TRY(cudaGetLastError());
         res->launches += 2;
         if (int rc = fold_rows()) return rc;
@@ -590,6 +608,7 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
             res->waiting = true;
             return 0;
         }
+        if (int rc = fetch_m_ref()) return rc;
         CU_TRY(cudaStreamSynchronize(e->compute));
         res->m_ref = e->h_pilot.ptr[0];
         float ms = 0.f;
@@ -876,28 +895,37 @@ constexpr double kRebaseLimit = 300.0;
 // device time are collected here, after the one synchronisation of the inference.
 int merge_impl(cpprob_sis_engine * e, const double * gathered, uint32_t n_chunks, int n_cols, int n_real, int n_int,
                hist_window hw, double m_ref, uint64_t n_total, cpprob_sis_stats * out, uint64_t * launches, double * ms_out,
-               shard_result * pending = nullptr, const gather_layout * layout = nullptr)
+               shard_result * pending = nullptr, const gather_layout * layout = nullptr,
+               const unsigned long long * peer_flags = nullptr, unsigned long long peer_epoch = 0)
 {
     if (n_cols != kBaseCols + 2 * n_real + n_int * hw.bins) return fail(CPPROB_SIS_EINVAL, "n_cols does not match the model structure");
-    CU_TRY(e->d_merged.reserve(static_cast<size_t>(n_cols)));
-    CU_TRY(e->h_merged.reserve(static_cast<size_t>(n_cols)));
+    CU_TRY(e->d_merged.reserve(static_cast<size_t>(n_cols) + 2));
+    CU_TRY(e->h_merged.reserve(static_cast<size_t>(n_cols) + 2));
     CU_TRY(cudaEventRecord(e->ev_merge_begin, e->compute));
+    // a particle pass that is still in flight left m_ref on the device (e->d_pilot[0]): it comes back behind the sums
+    const bool m_ref_pending = pending && pending->waiting;
+    const double * m_ref_dev = m_ref_pending ? e->d_pilot.ptr : nullptr;
     if (layout) {        // the raw output of an all-gather: read in place (k_merge_columns_gathered)
-        k_merge_columns_gathered<<<n_cols, kBlock, 0, e->compute>>>(gathered, *layout, n_cols, kMaxColsMask, e->d_merged.ptr);
+        k_merge_columns_gathered<<<n_cols, kBlock, 0, e->compute>>>(gathered, *layout, n_cols, kMaxColsMask, e->d_merged.ptr, m_ref_dev,
+                                                                   peer_flags, peer_epoch);
     } else {
-        k_merge_columns<<<n_cols, kBlock, 0, e->compute>>>(gathered, n_chunks, n_cols, kMaxColsMask, e->d_merged.ptr);
+        k_merge_columns<<<n_cols, kBlock, 0, e->compute>>>(gathered, n_chunks, n_cols, kMaxColsMask, e->d_merged.ptr, m_ref_dev);
     }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(e->ev_merge_end, e->compute));
     ++*launches;
-    CU_TRY(cudaMemcpyAsync(e->h_merged.ptr, e->d_merged.ptr, n_cols * sizeof(double), cudaMemcpyDeviceToHost, e->compute));
+    CU_TRY(cudaMemcpyAsync(e->h_merged.ptr, e->d_merged.ptr, (n_cols + ((m_ref_pending || peer_flags) ? 2 : 0)) * sizeof(double), cudaMemcpyDeviceToHost,
+                           e->compute));
     CU_TRY(cudaStreamSynchronize(e->compute));
+    if (peer_flags && e->h_merged.ptr[n_cols + 1] != 0.0) {
+        return fail(CPPROB_SIS_ENCCL, "a peer's partial rows did not arrive within 20 s (peer-memory exchange): a rank failed or left the collective");
+    }
     float ms = 0.f;
     CU_TRY(cudaEventElapsedTime(&ms, e->ev_merge_begin, e->ev_merge_end));
     *ms_out = ms;
-    if (pending && pending->waiting) {
+    if (m_ref_pending) {
         pending->waiting = false;
-        pending->m_ref = m_ref = e->h_pilot.ptr[0];
+        pending->m_ref = m_ref = e->h_merged.ptr[n_cols];
         CU_TRY(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));
         pending->device_ms = ms;
     }
@@ -1327,7 +1355,37 @@ int run_dist_impl(cpprob_sis_engine * const * local, int n_local, const cpprob_s
         if (int rc = make_gather_layout(n_total, world, static_cast<int>(r0.rows_per_chunk), &lay)) return rc;
         const size_t count = static_cast<size_t>(lay.rows_per_rank) * n_cols;
         const double * merged_from = nullptr;
-        if (world > 1) {
+        // the exchange: through the ranks' peer windows (k_push_rows -> flags -> the merge kernel's wait) when every rank
+        // has them and the rows fit, else one ncclAllGather.  Both decisions come out the same on every rank.
+        bool use_peer = world > 1 && count * static_cast<size_t>(world) * sizeof(double) <= primary->pw.buffer_bytes;
+        for (int i = 0; i < n_local; ++i) use_peer = use_peer && local[i]->pw.ready;
+        const unsigned long long * peer_flags = nullptr;
+        unsigned long long peer_epoch = 0;
+        if (use_peer) {
+            for (int i = 0; i < n_local; ++i) {
+                cpprob_sis_engine * e = local[i];
+                if (int rc = use_device(e)) return rc;
+                const unsigned long long epoch = ++e->pw.epoch;
+                const unsigned long long offset = kPeerFlagBytes + (epoch & 1ull) * e->pw.buffer_bytes;
+                const unsigned r = static_cast<unsigned>(e->comm_rank);
+                const unsigned long long n_doubles = res[static_cast<size_t>(i)].rows
+                    ? static_cast<unsigned long long>(lay.first[r + 1] - lay.first[r]) * n_cols : 0ull;
+                peer_targets t;
+                std::memset(&t, 0, sizeof t);
+                for (int p = 0; p < world; ++p) t.window[p] = e->pw.peer[p];
+                t.world = static_cast<unsigned>(world);
+                t.rank = r;
+                const unsigned grid = static_cast<unsigned>(std::min<unsigned long long>(std::max<unsigned long long>((n_doubles + kBlock - 1) / kBlock, 1ull), 64ull));
+                k_push_rows<<<grid, kBlock, 0, e->compute>>>(res[static_cast<size_t>(i)].rows, n_doubles, t, offset, count, epoch);
+                CU_TRY(cudaGetLastError());
+                ++launches;
+                if (i == 0) {
+                    merged_from = reinterpret_cast<const double *>(e->pw.local + offset);
+                    peer_flags = reinterpret_cast<const unsigned long long *>(e->pw.local);
+                    peer_epoch = epoch;
+                }
+            }
+        } else if (world > 1) {
             if (n_local > 1) NCCL_TRY(nc.GroupStart());
             for (int i = 0; i < n_local; ++i) {
                 cpprob_sis_engine * e = local[i];
@@ -1348,7 +1406,8 @@ int run_dist_impl(cpprob_sis_engine * const * local, int n_local, const cpprob_s
         int mrc;
         if (world > 1) {
             mrc = merge_impl(primary, merged_from, lay.first[world], n_cols, static_cast<int>(primary->structure.n_real),
-                             static_cast<int>(primary->structure.n_int), r0.hw, r0.m_ref, n_total, out, &launches, &merge_ms, &res[0], &lay);
+                             static_cast<int>(primary->structure.n_int), r0.hw, r0.m_ref, n_total, out, &launches, &merge_ms, &res[0], &lay,
+                             peer_flags, peer_epoch);
         } else {
             mrc = merge_impl(primary, r0.rows, r0.n_rows_total, n_cols, static_cast<int>(primary->structure.n_real),
                              static_cast<int>(primary->structure.n_int), r0.hw, r0.m_ref, n_total, out, &launches, &merge_ms, &res[0]);
@@ -1403,6 +1462,123 @@ int run_dist_impl(cpprob_sis_engine * const * local, int n_local, const cpprob_s
 
 }  // namespace
 
+namespace {
+
+constexpr size_t kPeerBufferBytes = 8u << 20;      // one gather buffer of a peer window (two per window)
+
+bool peer_exchange_wanted()
+{
+    const char * v = std::getenv("CPPROB_SIS_EXCHANGE");       // "nccl": always ncclAllGather; default: peer memory where possible
+    return !(v && std::strcmp(v, "nccl") == 0);
+}
+
+void peer_window_release(cpprob_sis_engine * e)
+{
+    cpprob_sis_engine::peer_window & w = e->pw;
+    for (int p = 0; p < kMaxMergeRanks; ++p) {
+        if (w.opened[p] && w.peer[p]) cudaIpcCloseMemHandle(w.peer[p]);
+        w.opened[p] = false;
+        w.peer[p] = nullptr;
+    }
+    if (w.local) cudaFree(w.local);
+    w = cpprob_sis_engine::peer_window();
+}
+
+cudaError_t peer_window_alloc(cpprob_sis_engine * e)
+{
+    cpprob_sis_engine::peer_window & w = e->pw;
+    w.buffer_bytes = kPeerBufferBytes;
+    const size_t bytes = kPeerFlagBytes + 2 * w.buffer_bytes;
+    cudaError_t err = cudaMalloc(reinterpret_cast<void **>(&w.local), bytes);
+    if (err != cudaSuccess) { w.local = nullptr; return err; }
+    err = cudaMemset(w.local, 0, bytes);
+    return err;
+}
+
+// One process per GPU: the windows are exchanged as CUDA IPC handles over the communicator that was just made, and the
+// peer path is switched on only if EVERY rank mapped EVERY window (the ranks must agree, or one would wait in NCCL for
+// peers that push through memory).  Any failure leaves the NCCL path in place; it is not an error.
+int peer_window_setup_ipc(cpprob_sis_engine * e)
+{
+    const nccl_api & nc = nccl();
+    const int world = e->comm_world, rank = e->comm_rank;
+    struct record { cudaIpcMemHandle_t handle; unsigned long long ok; };
+    static_assert(sizeof(record) == 72, "IPC handle record");
+    record mine;
+    std::memset(&mine, 0, sizeof mine);
+    bool ok = peer_exchange_wanted() && peer_window_alloc(e) == cudaSuccess;
+    if (ok) ok = cudaIpcGetMemHandle(&mine.handle, e->pw.local) == cudaSuccess;
+    cudaGetLastError();
+    mine.ok = ok ? 1ull : 0ull;
+    device_buffer<unsigned char> d_rec;
+    CU_TRY(d_rec.reserve(sizeof(record) * static_cast<size_t>(world)));
+    std::vector<record> all(static_cast<size_t>(world));
+    auto gather = [&]() -> int {
+        CU_TRY(cudaMemcpyAsync(d_rec.ptr + sizeof(record) * static_cast<size_t>(rank), &mine, sizeof mine, cudaMemcpyHostToDevice, e->compute));
+        NCCL_TRY(nc.AllGather(d_rec.ptr + sizeof(record) * static_cast<size_t>(rank), d_rec.ptr, sizeof(record), ncclChar, e->comm, e->compute));
+        CU_TRY(cudaMemcpyAsync(all.data(), d_rec.ptr, sizeof(record) * static_cast<size_t>(world), cudaMemcpyDeviceToHost, e->compute));
+        CU_TRY(cudaStreamSynchronize(e->compute));
+        return 0;
+    };
+    int rc = gather();
+    if (rc) { d_rec.release(); return rc; }
+    bool everyone = true;
+    for (const record & r : all) everyone = everyone && r.ok == 1ull;
+    if (everyone) {
+        for (int p = 0; p < world && ok; ++p) {
+            if (p == rank) { e->pw.peer[p] = e->pw.local; continue; }
+            void * ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[static_cast<size_t>(p)].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = false;
+                break;
+            }
+            e->pw.peer[p] = static_cast<unsigned char *>(ptr);
+            e->pw.opened[p] = true;
+        }
+    }
+    // second round: did every rank map every window?
+    mine.ok = (everyone && ok) ? 1ull : 0ull;
+    rc = gather();
+    d_rec.release();
+    if (rc) return rc;
+    bool ready = true;
+    for (const record & r : all) ready = ready && r.ok == 1ull;
+    if (ready) e->pw.ready = true;
+    else peer_window_release(e);
+    return 0;
+}
+
+// One process, one engine per GPU: peer access between the devices, plain pointers.
+void peer_window_setup_local(cpprob_sis_engine * const * engines, int n)
+{
+    if (!peer_exchange_wanted()) return;
+    bool ok = true;
+    for (int i = 0; i < n && ok; ++i) {
+        if (cudaSetDevice(engines[i]->device) != cudaSuccess) { ok = false; break; }
+        for (int j = 0; j < n && ok; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, engines[i]->device, engines[j]->device) != cudaSuccess || !can) { ok = false; break; }
+            const cudaError_t err = cudaDeviceEnablePeerAccess(engines[j]->device, 0);
+            if (err != cudaSuccess && err != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+            cudaGetLastError();
+        }
+        if (ok) ok = peer_window_alloc(engines[i]) == cudaSuccess;
+    }
+    cudaGetLastError();
+    if (!ok) {
+        for (int i = 0; i < n; ++i) { cudaSetDevice(engines[i]->device); peer_window_release(engines[i]); }
+        return;
+    }
+    for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < n; ++j) engines[i]->pw.peer[j] = engines[j]->pw.local;
+        engines[i]->pw.ready = true;
+    }
+}
+
+}  // namespace
+
 int cpprob_sis_comm_get_id(void * id_out)
 {
     if (!id_out) return fail(CPPROB_SIS_EINVAL, "null argument");
@@ -1428,6 +1604,9 @@ int cpprob_sis_comm_init(cpprob_sis_engine * e, const void * id_in, int rank, in
     NCCL_TRY(nc.CommInitRank(&e->comm, world, id, rank));
     e->comm_rank = rank;
     e->comm_world = world;
+    if (world > 1) {
+        if (int rc = peer_window_setup_ipc(e)) return rc;
+    }
     return 0;
 }
 
@@ -1451,6 +1630,7 @@ int cpprob_sis_comm_init_local(cpprob_sis_engine * const * engines, int n_engine
         engines[r]->comm_rank = r;
         engines[r]->comm_world = n_engines;
     }
+    peer_window_setup_local(engines, n_engines);
     return 0;
 }
 
@@ -1463,9 +1643,20 @@ int cpprob_sis_comm_destroy(cpprob_sis_engine * e)
         nccl().CommDestroy(e->comm);
         e->comm = nullptr;
     }
+    if (e->pw.local) {
+        cudaSetDevice(e->device);
+        if (e->compute) cudaStreamSynchronize(e->compute);
+        peer_window_release(e);
+    }
     e->comm_rank = 0;
     e->comm_world = 1;
     return 0;
+}
+
+int cpprob_sis_comm_exchange(const cpprob_sis_engine * e)
+{
+    if (!e || e->comm_world <= 1) return CPPROB_SIS_EXCHANGE_NONE;
+    return e->pw.ready ? CPPROB_SIS_EXCHANGE_PEER : CPPROB_SIS_EXCHANGE_NCCL;
 }
 
 int cpprob_sis_run_dist(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs, uint64_t n_particles_total, cpprob_sis_stats * out)

@@ -420,11 +420,73 @@ __global__ void __launch_bounds__(kBlock) k_pilot(const __grid_constant__ philox
 // 256-thread CTA would own in chunk c (4096 particles).  Any warp of the grid takes any unit from the atomic
 // counter, sums it with a fixed shuffle tree and writes NV values to warp_partials[c*8 + w][*]; after the one
 // barrier of the table load no warp ever waits for another (the ziggurat's rare slow draws make warps finish
-// at different times).  k_fold_warp_partials then adds the 8 slots of a chunk in slot order, which is the sum
+// at different times).  k_fold_warp_partials then adds the 8 rows of a chunk in row order, which is the sum
 // the CTA-wide tree used to form: chunk partials are bit-identical for any grid size / schedule / GPU count.
 // Partial columns: kBaseCols then (S1, S2) per real predict slot.
 // ------------------------------------------------------------------------------------------------
 constexpr int kSlotsPerChunk = kBlock / 32;          // warp slots of one chunk
+// The fused kernel can cut every (chunk, warp slot) into kFusedParts units of consecutive stream tiles.  Measured with 2
+// (2048-particle units, profiles/r02_notes.md): the end of a short run does not get shorter (1.25e8 particles: 0.425 vs
+// 0.427 ms) and a long one pays the second reduction (1e9: 3.080 vs 3.037 ms), so the shipped value is 1.
+#ifndef CPPROB_FUSED_PARTS
+#define CPPROB_FUSED_PARTS 1
+#endif
+constexpr int kFusedParts = CPPROB_FUSED_PARTS;
+constexpr int kFusedRowsPerChunk = kSlotsPerChunk * kFusedParts;   // warp_partials rows of one chunk, folded in row order
+constexpr unsigned kFusedPart = kChunk / kFusedParts;              // particles a part spans (all eight slots together)
+static_assert(kFusedPart % (4 * kPairStride) == 0, "a part holds whole pairs of stream tiles");
+static_assert(kFusedParts >= 1 && kFusedParts <= 4, "the unit counter is 32 bits wide (run_shard_impl's limit assumes <= 4 parts)");
+
+// ------------------------------------------------------------------------------------------------
+// Warp sum of C columns at once ("transpose-reduce").  Every lane brings v[0..C); at the xor-16 stage the lanes with
+// bit 4 clear keep the lower half of the columns and hand the upper half to their partner (and vice versa), so each
+// exchange finishes one column pair instead of one column; once a lane is down to one column the remaining stages are
+// the plain butterfly.  Every column is summed by exactly the tree the plain xor-butterfly forms (same pairs, IEEE
+// addition commutes), so the result has the same bits; it just costs 6 exchanges instead of 20 for four columns.
+// Afterwards v[0] of lane L holds the total of column transpose_col<C>(L) (or nothing: -1).
+// ------------------------------------------------------------------------------------------------
+template<int P, int OFF>
+__device__ __forceinline__ void warp_transpose_sum(double * v, unsigned lane)
+{
+    if constexpr (OFF >= 1) {
+        if constexpr (P == 1) {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], OFF);
+            warp_transpose_sum<1, OFF / 2>(v, lane);
+        } else {
+            constexpr int H = (P + 1) / 2;
+            const bool hi = (lane & OFF) != 0u;
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                const double upper = (H + j) < P ? v[H + j] : 0.0;
+                const double send = hi ? v[j] : upper;
+                const double keep = hi ? upper : v[j];
+                v[j] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+            }
+            warp_transpose_sum<H, OFF / 2>(v, lane);
+        }
+    }
+}
+
+// the column whose total lane `lane` holds after warp_transpose_sum<C, 16>, or -1 (a lane that duplicates another's
+// total, or whose slot was padding)
+template<int C>
+__device__ __forceinline__ int transpose_col(unsigned lane)
+{
+    int base = 0, valid = C, p = C;
+    bool owner = true;
+#pragma unroll
+    for (unsigned off = 16; off >= 1; off >>= 1) {
+        const bool hi = (lane & off) != 0u;
+        if (p == 1) {
+            owner = owner && !hi;              // plain stage: both partners end up with the same total
+        } else {
+            const int h = (p + 1) / 2;
+            if (hi) { base += h; valid -= h; } else { valid = valid < h ? valid : h; }
+            p = h;
+        }
+    }
+    return owner && valid >= 1 ? base : -1;
+}
 
 template<class Model, int NR>
 __global__ void __launch_bounds__(fused_block(NR), NR == 1 ? CPPROB_FUSED_MIN_BLOCKS : 1) k_sis_fused(const __grid_constant__ run_args a)
@@ -437,18 +499,21 @@ __global__ void __launch_bounds__(fused_block(NR), NR == 1 ? CPPROB_FUSED_MIN_BL
     const double * const scratch = model_scratch_prepare<Model>(a.obs, a.n_obs, a.scratch_doubles);
     const unsigned exp_tab = dm::exp2_table_load();
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned n_units = a.n_chunks * kSlotsPerChunk;
+    const unsigned n_units = a.n_chunks * kFusedRowsPerChunk;
+    constexpr int NS = 2 + 2 * NR;                                  // columns that are sums of doubles: S0, S00, (S1, S2) per predict
+    const int sum_col = transpose_col<NS>(lane);                    // which of them this lane writes (-1: none)
+    const int out_col = sum_col < 0 ? -1 : (sum_col == 0 ? static_cast<int>(col::s0) : (sum_col == 1 ? static_cast<int>(col::s00) : kBaseCols + sum_col - 2));
 
     for (;;) {
         unsigned unit = 0;
         if (lane == 0) unit = atomicAdd(a.chunk_counter, 1u);
         unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= n_units) break;
-        const unsigned c = unit / kSlotsPerChunk;
+        // unit = (chunk * kFusedParts + part) * 8 + warp slot
         const unsigned vt = (unit % kSlotsPerChunk) * 32u + lane;
-        const unsigned long long base = static_cast<unsigned long long>(c) * kChunk;
-        const unsigned long long left = a.n_particles - base;
-        const unsigned n_here = left < kChunk ? static_cast<unsigned>(left) : kChunk;
+        const unsigned long long base = static_cast<unsigned long long>(unit / kSlotsPerChunk) * kFusedPart;
+        const unsigned long long left = a.n_particles > base ? a.n_particles - base : 0ull;
+        const unsigned n_here = left < kFusedPart ? static_cast<unsigned>(left) : kFusedPart;
 
         double max_lw, s0, s00;
         unsigned n_neginf, n_nan;
@@ -501,47 +566,48 @@ __global__ void __launch_bounds__(fused_block(NR), NR == 1 ? CPPROB_FUSED_MIN_BL
             });
         }
 
-        double v[NV];
-        v[col::max_lw] = max_lw;
-        v[col::s0] = s0;
-        v[col::s00] = s00;
-        v[col::n_neginf] = static_cast<double>(n_neginf);
-        v[col::neg_imin] = dm::neg_inf();
-        v[col::imax] = dm::neg_inf();
-        v[col::int_oor] = 0.0;
-        v[col::n_nan] = static_cast<double>(n_nan);
+        // The unit's row of warp_partials.  Sums of doubles: transpose-reduce (the butterfly's tree, a third of its
+        // exchanges); the maximum: butterfly; the two counters: integer warp sums (exact either way); the three columns
+        // only int predicts feed are constants here.
+        double t[NS];
+        t[0] = s0;
+        t[1] = s00;
 #pragma unroll
-        for (int j = 0; j < NR; ++j) { v[kBaseCols + 2 * j] = s1[j]; v[kBaseCols + 2 * j + 1] = s2[j]; }
-        // the warp stage of block_reduce, same tree
-        double mine = 0.0;
+        for (int j = 0; j < NR; ++j) { t[2 + 2 * j] = s1[j]; t[3 + 2 * j] = s2[j]; }
+        warp_transpose_sum<NS, 16>(t, lane);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            double x = v[i];
-            const bool is_max = (kMaxColsMask >> i) & 1ull;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const double y = __shfl_xor_sync(0xffffffffu, x, off);
-                x = is_max ? fmax(x, y) : x + y;
-            }
-            if (static_cast<int>(lane) == i) mine = x;
+        for (int off = 16; off > 0; off >>= 1) max_lw = fmax(max_lw, __shfl_xor_sync(0xffffffffu, max_lw, off));
+        n_neginf = __reduce_add_sync(0xffffffffu, n_neginf);
+        n_nan = __reduce_add_sync(0xffffffffu, n_nan);
+        double * const out = a.warp_partials + static_cast<size_t>(unit) * NV;
+        if (out_col >= 0) out[out_col] = t[0];
+        if (lane == 1) {
+            out[col::max_lw] = max_lw;
+            out[col::n_neginf] = static_cast<double>(n_neginf);
+            out[col::n_nan] = static_cast<double>(n_nan);
         }
-        if (static_cast<int>(lane) < NV) a.warp_partials[static_cast<size_t>(unit) * NV + lane] = mine;
+        if (lane == 2) {
+            out[col::neg_imin] = dm::neg_inf();
+            out[col::imax] = dm::neg_inf();
+            out[col::int_oor] = 0.0;
+        }
     }
 }
 
-// chunk partial = warp slots 0..7 combined in slot order (the second stage of block_reduce)
+// chunk partial = the chunk's `per` rows of warp_partials (fused kernel: 2 parts x 8 warp slots, staged kernel: 8 warp
+// slots) combined in row order
 static __global__ void __launch_bounds__(kBlock) k_fold_warp_partials(const double * __restrict__ warp_partials, unsigned n_chunks, int nv,
-                                                               double * __restrict__ partials, int n_cols)
+                                                               double * __restrict__ partials, int n_cols, int per)
 {
     const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(kBlock) + threadIdx.x;
     if (i >= static_cast<unsigned long long>(n_chunks) * nv) return;
     const unsigned c = static_cast<unsigned>(i / nv);
     const int j = static_cast<int>(i % nv);
     const bool is_max = (kMaxColsMask >> j) & 1ull;
-    const double * p = warp_partials + static_cast<size_t>(c) * kSlotsPerChunk * nv + j;
+    const double * p = warp_partials + static_cast<size_t>(c) * per * nv + j;
     double r = p[0];
-#pragma unroll
-    for (int w = 1; w < kSlotsPerChunk; ++w) {
+#pragma unroll 8
+    for (int w = 1; w < per; ++w) {
         const double y = p[static_cast<size_t>(w) * nv];
         r = is_max ? fmax(r, y) : r + y;
     }

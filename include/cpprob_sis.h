@@ -229,6 +229,12 @@ int cpprob_sis_run_shard(cpprob_sis_engine * e, int model_id, const double * obs
  * kernels that wrote them; every rank then merges the gathered rows in place (k_merge_columns_gathered), which gives the
  * same bits on every rank and for every rank count.  The host synchronises once per inference.
  * NCCL is opened at run time (libnccl.so.2; CPPROB_SIS_NCCL_LIB overrides): nothing here is needed on one GPU.
+ * How the rows travel: when every rank of the communicator can map every other rank's memory (one node, NVLink /
+ * NVSwitch: CUDA IPC between processes, peer access within one), each rank's kernels store its rows straight into every
+ * peer's gather buffer and raise a flag there, and the merge kernel waits for the flags — no collective kernel at all
+ * (CPPROB_SIS_EXCHANGE_PEER).  Otherwise, or with the environment variable CPPROB_SIS_EXCHANGE=nccl, one ncclAllGather
+ * (CPPROB_SIS_EXCHANGE_NCCL).  The communicator decides once, at cpprob_sis_comm_init, alike on every rank; the results
+ * are the same bits either way.
  *
  * Process per GPU: rank 0 calls cpprob_sis_comm_get_id and hands the 128 bytes to the others by any means (MPI,
  * torch.distributed, a file); every rank calls cpprob_sis_comm_init on its engine (collective), then
@@ -237,6 +243,9 @@ int cpprob_sis_run_shard(cpprob_sis_engine * e, int model_id, const double * obs
 int cpprob_sis_comm_get_id(void * id_out /* [CPPROB_SIS_COMM_ID_BYTES] */);
 int cpprob_sis_comm_init(cpprob_sis_engine * e, const void * id, int rank, int world);
 int cpprob_sis_comm_destroy(cpprob_sis_engine * e);
+enum { CPPROB_SIS_EXCHANGE_NONE = 0, CPPROB_SIS_EXCHANGE_NCCL = 1, CPPROB_SIS_EXCHANGE_PEER = 2 };
+/* which exchange the engine's communicator uses (NONE: rank 0 of 1) */
+int cpprob_sis_comm_exchange(const cpprob_sis_engine * e);
 int cpprob_sis_run_dist(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs, uint64_t n_particles_total,
                         cpprob_sis_stats * out);
 /* One process driving several GPUs: a communicator among engines[0..n) (rank r = engines[r]; ncclCommInitAll). */

@@ -47,7 +47,7 @@ for model, obs, n in CASES:
     ok = ok and same_everywhere
     out.append(row)
 if rank == 0:
-    print(json.dumps({"world": world, "ok": ok, "cases": out}))
+    print(json.dumps({"world": world, "ok": ok, "exchange": engine.comm_exchange(), "cases": out}))
 engine.close()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
