@@ -25,7 +25,9 @@ struct cpprob_sis_model_vtable {
     int replayable;
     // host-side structure probe; `out` is a cpprob::model_structure*
     int (*probe)(const double * obs, int n_obs, unsigned long long seed, void * out);
-    cudaError_t (*launch_pilot)(cudaStream_t s, const cpprob::philox_keys * keys, const double * obs, int n_obs, int n_pilot, double * out);
+    // fin: null = per-tile maxima only; else the last CTA folds them into out[0] = m_ref (sis_kernels.cuh, pilot_finalize)
+    cudaError_t (*launch_pilot)(cudaStream_t s, const cpprob::philox_keys * keys, const double * obs, int n_obs, int n_pilot, double * out,
+                                const cpprob::engine::pilot_finalize * fin);
     // nr = register-staged real predict slots (1, 2 or 4)
     cudaError_t (*launch_fused)(cudaStream_t s, int grid, int nr, cpprob::engine::run_args * a);
     cudaError_t (*launch_rows)(cudaStream_t s, int grid, cpprob::engine::run_args * a);
@@ -75,10 +77,11 @@ struct model_launchers {
         *static_cast<model_structure *>(out) = probe_model(Model{}, obs, n_obs, seed);
         return 0;
     }
-    static cudaError_t pilot(cudaStream_t s, const philox_keys * keys, const double * obs, int n_obs, int n_pilot, double * out)
+    static cudaError_t pilot(cudaStream_t s, const philox_keys * keys, const double * obs, int n_obs, int n_pilot, double * out, const pilot_finalize * fin)
     {
         if (cudaError_t err = allow_smem(k_pilot<Model>, model_smem<Model>(n_obs))) return err;
-        k_pilot<Model><<<(n_pilot + 511) / 512, kBlock, model_smem<Model>(n_obs), s>>>(*keys, obs, n_obs, n_pilot, model_scratch_doubles<Model>(n_obs), out);
+        const pilot_finalize f = fin ? *fin : pilot_finalize{nullptr, 0, 0.0};
+        k_pilot<Model><<<(n_pilot + 511) / 512, kBlock, model_smem<Model>(n_obs), s>>>(*keys, obs, n_obs, n_pilot, model_scratch_doubles<Model>(n_obs), out, f);
         return cudaGetLastError();
     }
     static cudaError_t fused(cudaStream_t s, int grid, int nr, run_args * a)

@@ -145,22 +145,6 @@ __global__ void __launch_bounds__(kBlock) k_rows_hist(const int * __restrict__ i
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_pilot_finalize: the host fold of run_pilot on the device, for models that need nothing else from the pilot.
-// raw[3 t] = max log_w of pilot tile t; raw[0] becomes m_ref: the override if given, else the maximum if it is
-// finite and sane, else 0 (every pilot weight was -inf / nan).
-// ------------------------------------------------------------------------------------------------
-// Also zeroes the unit counter of the particle kernel that follows (no memset node between the kernels).
-__global__ void k_pilot_finalize(double * raw, int tiles, int has_override, double override_value, unsigned * unit_counter)
-{
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (unit_counter) *unit_counter = 0u;
-    double mx = dm::neg_inf();
-    for (int t = 0; t < tiles; ++t) mx = fmax(mx, raw[3 * t]);
-    const double m = (mx > -1.0e300 && mx < 1.0e300) ? mx : 0.0;
-    raw[0] = has_override ? override_value : m;
-}
-
-// ------------------------------------------------------------------------------------------------
 // k_fold_rows: super-chunk rows.  out[s][c] = rows [s*per, min((s+1)*per, n_rows)) of `in` combined in row
 // order by one thread (max columns with fmax, the others with +).  What a rank hands to the gather.
 // ------------------------------------------------------------------------------------------------
@@ -241,25 +225,28 @@ struct peer_targets {
     unsigned rank;
 };
 
-__global__ void __launch_bounds__(kBlock) k_push_rows(const double * __restrict__ rows, unsigned long long n_doubles,
-                                                      const __grid_constant__ peer_targets t, unsigned long long buffer_offset_bytes,
-                                                      unsigned long long segment_doubles, unsigned long long epoch)
+// what a producing kernel needs to push: the windows, where this inference's gather buffer starts in them, the length
+// of a rank's segment, and the epoch to publish (world == 0: nothing to push)
+struct peer_push {
+    peer_targets t;
+    unsigned long long buffer_offset_bytes;
+    unsigned long long segment_doubles;
+    unsigned long long epoch;
+};
+
+__device__ __forceinline__ double * peer_segment(const peer_push & pp, unsigned p)
 {
-    // rows[0, n_doubles) -> window[p] + buffer_offset + rank * segment, for every p
-    const unsigned long long i0 = blockIdx.x * static_cast<unsigned long long>(kBlock) + threadIdx.x;
-    const unsigned long long step = static_cast<unsigned long long>(gridDim.x) * kBlock;
-    for (unsigned long long i = i0; i < n_doubles; i += step) {
-        const double v = rows[i];
-        for (unsigned p = 0; p < t.world; ++p) {
-            double * dst = reinterpret_cast<double *>(t.window[p] + buffer_offset_bytes) + static_cast<unsigned long long>(t.rank) * segment_doubles;
-            dst[i] = v;
-        }
-    }
-    // the last CTA to get here publishes the epoch (the pattern of the threadFenceReduction sample, at system scope)
+    return reinterpret_cast<double *>(pp.t.window[p] + pp.buffer_offset_bytes) + static_cast<unsigned long long>(pp.t.rank) * pp.segment_doubles;
+}
+
+// Called by every thread of every CTA after its stores: the last CTA to get here publishes the epoch in every rank's
+// window (the pattern of the threadFenceReduction sample, at system scope).
+__device__ __forceinline__ void peer_publish(const peer_push & pp)
+{
     __shared__ bool last;
     __threadfence_system();
     __syncthreads();
-    unsigned long long * const mine = reinterpret_cast<unsigned long long *>(t.window[t.rank]);
+    unsigned long long * const mine = reinterpret_cast<unsigned long long *>(pp.t.window[pp.t.rank]);
     if (threadIdx.x == 0) {
         const unsigned long long done = atomicAdd(mine + kPeerDoneWord, 1ull);
         last = done + 1 == gridDim.x;
@@ -268,10 +255,57 @@ __global__ void __launch_bounds__(kBlock) k_push_rows(const double * __restrict_
     if (!last) return;
     if (threadIdx.x == 0) mine[kPeerDoneWord] = 0ull;             // ready for the next launch
     __threadfence_system();
-    if (threadIdx.x < t.world) {
-        volatile unsigned long long * flag = reinterpret_cast<volatile unsigned long long *>(t.window[threadIdx.x]) + t.rank;
-        *flag = epoch;
+    if (threadIdx.x < pp.t.world) {
+        volatile unsigned long long * flag = reinterpret_cast<volatile unsigned long long *>(pp.t.window[threadIdx.x]) + pp.t.rank;
+        *flag = pp.epoch;
     }
+}
+
+// rows that already lie in a buffer of this rank (row path): copy + publish
+__global__ void __launch_bounds__(kBlock) k_push_rows(const double * __restrict__ rows, unsigned long long n_doubles, const __grid_constant__ peer_push pp)
+{
+    const unsigned long long i0 = blockIdx.x * static_cast<unsigned long long>(kBlock) + threadIdx.x;
+    const unsigned long long step = static_cast<unsigned long long>(gridDim.x) * kBlock;
+    for (unsigned long long i = i0; i < n_doubles; i += step) {
+        const double v = rows[i];
+        for (unsigned p = 0; p < pp.t.world; ++p) peer_segment(pp, p)[i] = v;
+    }
+    peer_publish(pp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_fold_units: the particle kernels' per-unit rows -> the rows a rank hands on, in one step, and (multi-GPU, peer
+// exchange) straight into every rank's gather buffer.  Output row s, column c = kernel rows [s*per_super, (s+1)*per_super)
+// combined in row order, each kernel row being its `per_unit` unit rows of `units` combined in row order — the very
+// additions a fold of the unit rows followed by k_fold_rows would make (same bits, round 2's first version did exactly
+// that), without the intermediate array and the second launch.  One thread per output element.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_fold_units(const double * __restrict__ units, unsigned n_rows, int per_unit, int nv, unsigned per_super,
+                                                       int n_cols, unsigned long long max_mask, double * __restrict__ out, unsigned n_out_rows,
+                                                       const __grid_constant__ peer_push pp)
+{
+    const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(kBlock) + threadIdx.x;
+    if (i < static_cast<unsigned long long>(n_out_rows) * n_cols) {
+        const unsigned s = static_cast<unsigned>(i / n_cols);
+        const int c = static_cast<int>(i % n_cols);
+        const bool is_max = c < 64 && ((max_mask >> c) & 1ull);
+        const unsigned long long r0 = static_cast<unsigned long long>(s) * per_super;
+        const unsigned long long r1 = r0 + per_super < n_rows ? r0 + per_super : n_rows;
+        double acc = is_max ? dm::neg_inf() : 0.0;                  // (k_fold_rows starts from the identity too: same bits down to -0.0)
+        for (unsigned long long r = r0; r < r1; ++r) {
+            const double * p = units + (r * per_unit) * nv + c;
+            double x = p[0];
+#pragma unroll 8
+            for (int w = 1; w < per_unit; ++w) {
+                const double y = p[static_cast<size_t>(w) * nv];
+                x = is_max ? fmax(x, y) : x + y;
+            }
+            acc = per_super == 1u ? x : (is_max ? fmax(acc, x) : acc + x);   // (one row per output row: the row itself)
+        }
+        out[i] = acc;
+        for (unsigned p = 0; p < pp.t.world; ++p) peer_segment(pp, p)[i] = acc;
+    }
+    if (pp.t.world) peer_publish(pp);
 }
 
 // the consumer's wait: all `world` slots of this rank's own flag array reach `epoch` (or ~20 s pass: a peer died; the

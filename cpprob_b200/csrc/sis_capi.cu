@@ -348,7 +348,7 @@ int run_pilot(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, const p
     const int tiles = (n_pilot + 511) / 512;
     double raw[3 * kPilotTiles];
     CU_TRY(e->d_pilot.reserve(3 * kPilotTiles));
-    CU_TRY(vt->launch_pilot(e->compute, &keys, e->d_obs.ptr, static_cast<int>(n_obs), n_pilot, e->d_pilot.ptr));
+    CU_TRY(vt->launch_pilot(e->compute, &keys, e->d_obs.ptr, static_cast<int>(n_obs), n_pilot, e->d_pilot.ptr, nullptr));
     CU_TRY(cudaMemcpyAsync(raw, e->d_pilot.ptr, 3 * tiles * sizeof(double), cudaMemcpyDeviceToHost, e->compute));
     CU_TRY(cudaStreamSynchronize(e->compute));
     double mx = -std::numeric_limits<double>::infinity(), nmin = mx, imax = mx;
@@ -377,6 +377,7 @@ struct shard_options {
     cpprob::text::posterior_writer * text_writer = nullptr;   // EMIT_ALL with the records formatted on the GPU
     bool no_wait = false;    // fused path only: return right after the launches; merge_impl(..., pending) collects m_ref and the time
     bool count_text_only = false;   // with text_writer: only measure the text of this shard (shard_result::text_total), write nothing
+    bool push_peers = false;        // multi-GPU: hand the rows on through the ranks' peer windows (if there are any and the rows fit)
 };
 
 constexpr int kMinStagedWarps = 4;          // fewer resident warps than this: the row path is the better choice
@@ -393,6 +394,8 @@ bool staged_enabled()
 
 struct shard_result {
     int path = CPPROB_SIS_PATH_ROWS;
+    bool pushed = false;                                           // the rows are in every rank's peer window (epoch / offset below)
+    unsigned long long push_epoch = 0, push_offset = 0;
     unsigned long long text_total[2] = {0, 0};                     // count_text_only: bytes of this shard's .real / .int text
     shard_plan plan;
     uint32_t rows_per_chunk = 1;       // partial rows per kChunk particles: 1 (fused) or kChunk / kSubChunk (row path)
@@ -405,6 +408,25 @@ struct shard_result {
     double device_ms = 0.0;
     uint64_t launches = 0;
 };
+
+// the rows every rank owns (host arithmetic, identical on every rank) as the layout of the gathered buffer
+int make_gather_layout(uint64_t n_total, int world, int rows_per_chunk, gather_layout * lay)
+{
+    if (world > kMaxMergeRanks) return fail(CPPROB_SIS_EINVAL, "more than 64 ranks");
+    uint32_t seen = 0, most = 0, total = 0;
+    for (int r = 0; r < world; ++r) {
+        uint32_t first = 0, n_local = 0;
+        if (int rc = cpprob_sis_plan_rows(n_total, r, world, rows_per_chunk, &first, &n_local, &total)) return rc;
+        if (first != seen) return fail(CPPROB_SIS_EINVAL, "inconsistent row plan");
+        lay->first[r] = first;
+        seen += n_local;
+        most = std::max(most, n_local);
+    }
+    lay->first[world] = seen;
+    lay->world = static_cast<unsigned>(world);
+    lay->rows_per_rank = std::max<uint32_t>(most, 1u);
+    return 0;
+}
 
 // The particle pass of one rank.  Leaves [n_chunks_local][n_cols] partial sums in e->d_partials.
 int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, const double * obs, size_t n_obs,
@@ -428,7 +450,10 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
 
     CU_TRY(e->d_obs.reserve(n_obs));
     CU_TRY(e->d_pilot.reserve(3 * kPilotTiles));
-    CU_TRY(e->d_counter.reserve(1));
+    if (e->d_counter.cap < 2) {                  // [unit counter of the particle kernel][CTA-done counter of the pilot], zero between launches
+        CU_TRY(e->d_counter.reserve(2));
+        CU_TRY(cudaMemsetAsync(e->d_counter.ptr, 0, 2 * sizeof(unsigned), e->compute));
+    }
     CU_TRY(cudaMemcpyAsync(e->d_obs.ptr, obs, n_obs * sizeof(double), cudaMemcpyHostToDevice, e->compute));
 
     // pilot: m_ref and the int window, identical on every rank.  The device-timed region of a run
@@ -453,15 +478,14 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     const bool fused_early = fused || staged_warps >= kMinStagedWarps;
     if (fused_early) {
         const int n_pilot = static_cast<int>(std::min<uint64_t>(n_total, kPilot));
-        // Nothing but kernels between here and the end of the particle pass: the finalize kernel also zeroes the unit
-        // counter, and m_ref is read back with the results (copy-engine operations in the middle of the chain cost
-        // several microseconds each, which is what a short run — one GPU's share of a strong-scaling run — is made of).
+        // Nothing but kernels between here and the end of the particle pass: the pilot's last CTA folds the tiles into m_ref
+        // and zeroes the unit counter, and m_ref is read back with the results (a second launch, a copy and a memset in the
+        // middle of the chain cost several microseconds each, which is what a short run — one GPU's share of a
+        // strong-scaling run — is made of).
         CU_TRY(e->h_pilot.reserve(1));
-        CU_TRY(vt->launch_pilot(e->compute, &keys, e->d_obs.ptr, static_cast<int>(n_obs), n_pilot, e->d_pilot.ptr));
-        k_pilot_finalize<<<1, 32, 0, e->compute>>>(e->d_pilot.ptr, (n_pilot + 511) / 512, m_ref_override ? 1 : 0,
-                                                  m_ref_override ? *m_ref_override : 0.0, e->d_counter.ptr);
-        CU_TRY(cudaGetLastError());
-        res->launches += 2;
+        const pilot_finalize fin = {e->d_counter.ptr, m_ref_override ? 1 : 0, m_ref_override ? *m_ref_override : 0.0};
+        CU_TRY(vt->launch_pilot(e->compute, &keys, e->d_obs.ptr, static_cast<int>(n_obs), n_pilot, e->d_pilot.ptr, &fin));
+        res->launches += 1;
     } else {
         if (int rc = run_pilot(e, vt, keys, n_obs, n_total, m_ref_override, pilot)) return rc;
         ++res->launches;
@@ -508,13 +532,40 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         res->n_rows_local = kernel_rows;
     }
     res->rows = nullptr;
+    // Multi-GPU over peer memory: the kernel that produces the rows this rank hands on also stores them into every rank's
+    // gather buffer and publishes the inference's epoch there (reduce_kernels.cuh).  Whether that happens is a function of
+    // the communicator and the run's shape only, so every rank decides alike.
+    peer_push pp;
+    std::memset(&pp, 0, sizeof pp);
+    res->pushed = false;
+    if (opt.push_peers && world > 1 && e->pw.ready && world == e->comm_world && rank == e->comm_rank) {
+        gather_layout lay;
+        if (int rc = make_gather_layout(n_total, world, static_cast<int>(res->rows_per_chunk), &lay)) return rc;
+        const size_t count = static_cast<size_t>(lay.rows_per_rank) * n_cols;
+        if (count * static_cast<size_t>(world) * sizeof(double) <= e->pw.buffer_bytes) {
+            pp.epoch = ++e->pw.epoch;
+            pp.buffer_offset_bytes = kPeerFlagBytes + (pp.epoch & 1ull) * e->pw.buffer_bytes;
+            pp.segment_doubles = count;
+            for (int p = 0; p < world; ++p) pp.t.window[p] = e->pw.peer[p];
+            pp.t.world = static_cast<unsigned>(world);
+            pp.t.rank = static_cast<unsigned>(rank);
+            res->pushed = true;
+            res->push_epoch = pp.epoch;
+            res->push_offset = pp.buffer_offset_bytes;
+        }
+    }
     // m_ref to the host, queued behind the kernels (a caller that goes on to the merge gets it from there instead)
     auto fetch_m_ref = [&]() -> int {
         CU_TRY(cudaMemcpyAsync(e->h_pilot.ptr, e->d_pilot.ptr, sizeof(double), cudaMemcpyDeviceToHost, e->compute));
         return 0;
     };
     if (plan.n_chunks_local == 0) {
-        if (fused_early) {                     // a rank without particles still reports the run's m_ref
+        if (res->pushed) {                     // a rank without particles still publishes its (empty) segment
+            k_push_rows<<<1, kBlock, 0, e->compute>>>(nullptr, 0ull, pp);
+            CU_TRY(cudaGetLastError());
+            ++res->launches;
+        }
+        if (fused_early) {                     // and reports the run's m_ref
             if (int rc = fetch_m_ref()) return rc;
             CU_TRY(cudaStreamSynchronize(e->compute));
             res->m_ref = e->h_pilot.ptr[0];
@@ -523,16 +574,41 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
     }
     CU_TRY(e->d_partials.reserve(static_cast<size_t>(kernel_rows + 1) * n_cols));   // + 1: see cpprob_sis_merge_padded
     res->rows = e->d_partials.ptr;
-    // kernel rows -> super-chunk rows (in row order), on the compute stream
+    // kernel rows -> super-chunk rows (in row order), on the compute stream; then, with peers, into their windows
     auto fold_rows = [&]() -> int {
-        if (rows_per_super == 1) return 0;
-        CU_TRY(e->d_super.reserve(static_cast<size_t>(plan.n_super_local + 1) * n_cols));
-        const unsigned long long n_out = static_cast<unsigned long long>(plan.n_super_local) * n_cols;
-        k_fold_rows<<<static_cast<unsigned>((n_out + kBlock - 1) / kBlock), kBlock, 0, e->compute>>>(
-            e->d_partials.ptr, kernel_rows, rows_per_super, n_cols, kMaxColsMask, e->d_super.ptr, plan.n_super_local);
+        if (rows_per_super > 1) {
+            CU_TRY(e->d_super.reserve(static_cast<size_t>(plan.n_super_local + 1) * n_cols));
+            const unsigned long long n_out = static_cast<unsigned long long>(plan.n_super_local) * n_cols;
+            k_fold_rows<<<static_cast<unsigned>((n_out + kBlock - 1) / kBlock), kBlock, 0, e->compute>>>(
+                e->d_partials.ptr, kernel_rows, rows_per_super, n_cols, kMaxColsMask, e->d_super.ptr, plan.n_super_local);
+            CU_TRY(cudaGetLastError());
+            ++res->launches;
+            res->rows = e->d_super.ptr;
+        }
+        if (res->pushed) {
+            const unsigned long long n_doubles = static_cast<unsigned long long>(res->n_rows_local) * n_cols;
+            const unsigned grid = static_cast<unsigned>(std::min<unsigned long long>(std::max<unsigned long long>((n_doubles + kBlock - 1) / kBlock, 1ull), 64ull));
+            k_push_rows<<<grid, kBlock, 0, e->compute>>>(res->rows, n_doubles, pp);
+            CU_TRY(cudaGetLastError());
+            ++res->launches;
+        }
+        return 0;
+    };
+    // the particle kernels' unit rows (`per_unit` per kernel row, nv columns each) -> the rows handed on (-> the peers), one launch
+    auto fold_units = [&](int per_unit, int nv) -> int {
+        double * out = e->d_partials.ptr;
+        unsigned n_out_rows = kernel_rows;
+        if (rows_per_super > 1) {
+            CU_TRY(e->d_super.reserve(static_cast<size_t>(plan.n_super_local + 1) * n_cols));
+            out = e->d_super.ptr;
+            n_out_rows = plan.n_super_local;
+        }
+        const unsigned long long n_out = static_cast<unsigned long long>(n_out_rows) * n_cols;
+        k_fold_units<<<static_cast<unsigned>((n_out + kBlock - 1) / kBlock), kBlock, 0, e->compute>>>(
+            e->d_warp_partials.ptr, kernel_rows, per_unit, nv, rows_per_super, n_cols, kMaxColsMask, out, n_out_rows, pp);
         CU_TRY(cudaGetLastError());
         ++res->launches;
-        res->rows = e->d_super.ptr;
+        res->rows = out;
         return 0;
     };
 
@@ -559,14 +635,10 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         a.n_int = n_int;
         CU_TRY(e->d_warp_partials.reserve(static_cast<size_t>(units) * n_cols));
         a.warp_partials = e->d_warp_partials.ptr;
-        if (!fused_early) CU_TRY(cudaMemsetAsync(e->d_counter.ptr, 0, sizeof(unsigned), e->compute));   // else: zeroed by k_pilot_finalize
+        if (!fused_early) CU_TRY(cudaMemsetAsync(e->d_counter.ptr, 0, sizeof(unsigned), e->compute));   // else: zeroed by the pilot's last CTA
         CU_TRY(vt->launch_staged(e->compute, grid, staged_warps, &a));
-        const unsigned long long fold_n = static_cast<unsigned long long>(kernel_rows) * n_cols;
-        k_fold_warp_partials<<<static_cast<unsigned>((fold_n + kBlock - 1) / kBlock), kBlock, 0, e->compute>>>(
-            e->d_warp_partials.ptr, kernel_rows, n_cols, e->d_partials.ptr, n_cols, kSlotsPerChunk);
-        CU_TRY(cudaGetLastError());
-        res->launches += 2;
-        if (int rc = fold_rows()) return rc;
+        ++res->launches;
+        if (int rc = fold_units(kSlotsPerChunk, n_cols)) return rc;
         CU_TRY(cudaEventRecord(e->ev_end, e->compute));
         if (opt.no_wait && fused_early) {          // m_ref still on the device: collected after the merge
             res->waiting = true;
@@ -596,13 +668,9 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
         const int nv = kBaseCols + 2 * nr;
         CU_TRY(e->d_warp_partials.reserve(static_cast<size_t>(plan.n_chunks_local) * kFusedRowsPerChunk * nv));
         a.warp_partials = e->d_warp_partials.ptr;
-        CU_TRY(vt->launch_fused(e->compute, grid, nr, &a));      // (unit counter: zeroed by k_pilot_finalize)
-        const unsigned long long fold_n = static_cast<unsigned long long>(plan.n_chunks_local) * nv;
-        k_fold_warp_partials<<<static_cast<unsigned>((fold_n + kBlock - 1) / kBlock), kBlock, 0, e->compute>>>(
-            e->d_warp_partials.ptr, plan.n_chunks_local, nv, e->d_partials.ptr, n_cols, kFusedRowsPerChunk);
-        CU_TRY(cudaGetLastError());
-        res->launches += 2;
-        if (int rc = fold_rows()) return rc;
+        CU_TRY(vt->launch_fused(e->compute, grid, nr, &a));      // (unit counter: zeroed by the pilot's last CTA)
+        ++res->launches;
+        if (int rc = fold_units(kFusedRowsPerChunk, nv)) return rc;
         CU_TRY(cudaEventRecord(e->ev_end, e->compute));
         if (opt.no_wait) {
             res->waiting = true;
@@ -1297,25 +1365,6 @@ int cpprob_sis_write_summary(cpprob_sis_engine * e, const char * prefix, const c
 // ---- multi-GPU inside the library ------------------------------------------------------------------------------------
 namespace {
 
-// the rows every rank owns (host arithmetic, identical on every rank) as the layout of the gathered buffer
-int make_gather_layout(uint64_t n_total, int world, int rows_per_chunk, gather_layout * lay)
-{
-    if (world > kMaxMergeRanks) return fail(CPPROB_SIS_EINVAL, "more than 64 ranks");
-    uint32_t seen = 0, most = 0, total = 0;
-    for (int r = 0; r < world; ++r) {
-        uint32_t first = 0, n_local = 0;
-        if (int rc = cpprob_sis_plan_rows(n_total, r, world, rows_per_chunk, &first, &n_local, &total)) return rc;
-        if (first != seen) return fail(CPPROB_SIS_EINVAL, "inconsistent row plan");
-        lay->first[r] = first;
-        seen += n_local;
-        most = std::max(most, n_local);
-    }
-    lay->first[world] = seen;
-    lay->world = static_cast<unsigned>(world);
-    lay->rows_per_rank = std::max<uint32_t>(most, 1u);
-    return 0;
-}
-
 // One inference over the ranks of a communicator.  `local`: the engines of THIS process (one per GPU; one in the usual
 // process-per-GPU set-up), each carrying its rank of the same communicator.  Every rank queues its shard, the ONE
 // collective of the path — an all-gather of the per-(super-)chunk partial rows, straight from the buffer the shard
@@ -1344,6 +1393,7 @@ int run_dist_impl(cpprob_sis_engine * const * local, int n_local, const cpprob_s
     for (int pass = 1;; ++pass) {
         shard_options so;
         so.no_wait = true;
+        so.push_peers = true;
         for (int i = 0; i < n_local; ++i) {
             res[static_cast<size_t>(i)] = shard_result();
             if (int rc = run_shard_impl(local[i], vt, obs, n_obs, n_total, local[i]->comm_rank, world, mo, ho, so, &res[static_cast<size_t>(i)])) return rc;
@@ -1355,36 +1405,17 @@ int run_dist_impl(cpprob_sis_engine * const * local, int n_local, const cpprob_s
         if (int rc = make_gather_layout(n_total, world, static_cast<int>(r0.rows_per_chunk), &lay)) return rc;
         const size_t count = static_cast<size_t>(lay.rows_per_rank) * n_cols;
         const double * merged_from = nullptr;
-        // the exchange: through the ranks' peer windows (k_push_rows -> flags -> the merge kernel's wait) when every rank
-        // has them and the rows fit, else one ncclAllGather.  Both decisions come out the same on every rank.
-        bool use_peer = world > 1 && count * static_cast<size_t>(world) * sizeof(double) <= primary->pw.buffer_bytes;
-        for (int i = 0; i < n_local; ++i) use_peer = use_peer && local[i]->pw.ready;
+        // the exchange: through the ranks' peer windows (the shard's last kernel stored the rows there and raised the flags;
+        // the merge kernel waits for them) when every rank has them and the rows fit, else one ncclAllGather.  Both
+        // decisions come out the same on every rank.
+        bool use_peer = world > 1;
+        for (int i = 0; i < n_local; ++i) use_peer = use_peer && res[static_cast<size_t>(i)].pushed;
         const unsigned long long * peer_flags = nullptr;
         unsigned long long peer_epoch = 0;
-        if (use_peer) {
-            for (int i = 0; i < n_local; ++i) {
-                cpprob_sis_engine * e = local[i];
-                if (int rc = use_device(e)) return rc;
-                const unsigned long long epoch = ++e->pw.epoch;
-                const unsigned long long offset = kPeerFlagBytes + (epoch & 1ull) * e->pw.buffer_bytes;
-                const unsigned r = static_cast<unsigned>(e->comm_rank);
-                const unsigned long long n_doubles = res[static_cast<size_t>(i)].rows
-                    ? static_cast<unsigned long long>(lay.first[r + 1] - lay.first[r]) * n_cols : 0ull;
-                peer_targets t;
-                std::memset(&t, 0, sizeof t);
-                for (int p = 0; p < world; ++p) t.window[p] = e->pw.peer[p];
-                t.world = static_cast<unsigned>(world);
-                t.rank = r;
-                const unsigned grid = static_cast<unsigned>(std::min<unsigned long long>(std::max<unsigned long long>((n_doubles + kBlock - 1) / kBlock, 1ull), 64ull));
-                k_push_rows<<<grid, kBlock, 0, e->compute>>>(res[static_cast<size_t>(i)].rows, n_doubles, t, offset, count, epoch);
-                CU_TRY(cudaGetLastError());
-                ++launches;
-                if (i == 0) {
-                    merged_from = reinterpret_cast<const double *>(e->pw.local + offset);
-                    peer_flags = reinterpret_cast<const unsigned long long *>(e->pw.local);
-                    peer_epoch = epoch;
-                }
-            }
+        if (use_peer) {                            // the shard kernels pushed the rows themselves
+            merged_from = reinterpret_cast<const double *>(primary->pw.local + r0.push_offset);
+            peer_flags = reinterpret_cast<const unsigned long long *>(primary->pw.local);
+            peer_epoch = r0.push_epoch;
         } else if (world > 1) {
             if (n_local > 1) NCCL_TRY(nc.GroupStart());
             for (int i = 0; i < n_local; ++i) {

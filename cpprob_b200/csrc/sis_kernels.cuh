@@ -385,9 +385,20 @@ private:
 // out[3*cta + {0,1,2}] = max log_w, max(-int), max(int) of that tile (-inf where there is none); the
 // host takes the maximum over the kPilot/512 tiles (max is order-independent: deterministic).
 // ------------------------------------------------------------------------------------------------
+// With `fin.sync` (two zero-initialised words; word 1 counts the CTAs that are done and is left at zero again) the last
+// CTA to finish also does what the host would: out[0] = m_ref — the override if given, else the maximum over the tiles if
+// it is finite and sane, else 0 (every pilot weight was -inf / nan) — and zeroes word 0, the unit counter of the particle
+// kernel that follows.  No second launch, no copy, no memset between the pilot and the particle kernel.
+struct pilot_finalize {
+    unsigned * sync;            // nullptr: leave the tiles' maxima for the host (run_pilot)
+    int has_override;
+    double override_value;
+};
+
 template<class Model>
 __global__ void __launch_bounds__(kBlock) k_pilot(const __grid_constant__ philox_keys keys, const double * __restrict__ obs,
-                                                  int n_obs, int n_pilot, int scratch_doubles, double * __restrict__ out)
+                                                  int n_obs, int n_pilot, int scratch_doubles, double * __restrict__ out,
+                                                  const pilot_finalize fin)
 {
     constexpr unsigned kTile = 2 * kPairStride;
     __shared__ double smem[kWarps * 3];
@@ -410,6 +421,21 @@ __global__ void __launch_bounds__(kBlock) k_pilot(const __grid_constant__ philox
     });
     const double r = block_reduce<3>(v, 0x7ull, smem);
     if (threadIdx.x < 3) out[3 * blockIdx.x + threadIdx.x] = r;
+    if (fin.sync == nullptr) return;
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(fin.sync + 1, 1u) + 1u == gridDim.x;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double mx = dm::neg_inf();
+        for (unsigned t = 0; t < gridDim.x; ++t) mx = fmax(mx, __ldcg(out + 3 * t));   // written by the other CTAs
+        const double m = (mx > -1.0e300 && mx < 1.0e300) ? mx : 0.0;
+        out[0] = fin.has_override ? fin.override_value : m;
+        fin.sync[1] = 0u;
+        fin.sync[0] = 0u;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -420,7 +446,7 @@ __global__ void __launch_bounds__(kBlock) k_pilot(const __grid_constant__ philox
 // 256-thread CTA would own in chunk c (4096 particles).  Any warp of the grid takes any unit from the atomic
 // counter, sums it with a fixed shuffle tree and writes NV values to warp_partials[c*8 + w][*]; after the one
 // barrier of the table load no warp ever waits for another (the ziggurat's rare slow draws make warps finish
-// at different times).  k_fold_warp_partials then adds the 8 rows of a chunk in row order, which is the sum
+// at different times).  k_fold_units (reduce_kernels.cuh) then adds the 8 rows of a chunk in row order, which is the sum
 // the CTA-wide tree used to form: chunk partials are bit-identical for any grid size / schedule / GPU count.
 // Partial columns: kBaseCols then (S1, S2) per real predict slot.
 // ------------------------------------------------------------------------------------------------
@@ -592,26 +618,6 @@ __global__ void __launch_bounds__(fused_block(NR), NR == 1 ? CPPROB_FUSED_MIN_BL
             out[col::int_oor] = 0.0;
         }
     }
-}
-
-// chunk partial = the chunk's `per` rows of warp_partials (fused kernel: 2 parts x 8 warp slots, staged kernel: 8 warp
-// slots) combined in row order
-static __global__ void __launch_bounds__(kBlock) k_fold_warp_partials(const double * __restrict__ warp_partials, unsigned n_chunks, int nv,
-                                                               double * __restrict__ partials, int n_cols, int per)
-{
-    const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(kBlock) + threadIdx.x;
-    if (i >= static_cast<unsigned long long>(n_chunks) * nv) return;
-    const unsigned c = static_cast<unsigned>(i / nv);
-    const int j = static_cast<int>(i % nv);
-    const bool is_max = (kMaxColsMask >> j) & 1ull;
-    const double * p = warp_partials + static_cast<size_t>(c) * per * nv + j;
-    double r = p[0];
-#pragma unroll 8
-    for (int w = 1; w < per; ++w) {
-        const double y = p[static_cast<size_t>(w) * nv];
-        r = is_max ? fmax(r, y) : r + y;
-    }
-    if (j < n_cols) partials[static_cast<size_t>(c) * n_cols + j] = r;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -18,7 +18,7 @@
 //   work unit = (sub-chunk c of 4096 particles, warp slot s) = the 512 particles p = 512 t + 256 u + 32 s + l
 //   (tile t < 8, turn u < 2, lane l) that slot s of a 256-thread CTA owns; the unit's sums are formed sequentially over
 //   those particles in (t, u, l) order, per row and per bin; the 8 slots are then added in slot order
-//   (k_fold_warp_partials), sub-chunks in order (k_fold_rows, k_merge_columns).  Base columns (max log_w, sum w, sum w^2,
+//   (k_fold_units), sub-chunks in order (k_fold_units, k_merge_columns).  Base columns (max log_w, sum w, sum w^2,
 //   counts) keep the order of k_row_base: per (slot, lane) over the 16 rounds, then the xor tree over lanes, then slots.
 //   The row path's reduction kernels (k_rows_moments / k_rows_hist in reduce_kernels.cuh) stage the rows they read from
 //   HBM the same way and call the same round functions, so both paths produce the same bits.

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define CPPROB_SIS_ABI_VERSION 2
+#define CPPROB_SIS_ABI_VERSION 3
 
 enum {
     CPPROB_SIS_OK = 0,

@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported():
 
 def test_abi_version_and_builtin_models():
     L = capi.lib()
-    assert L.cpprob_sis_abi_version() == 2
+    assert L.cpprob_sis_abi_version() == 3
     names = [L.cpprob_sis_model_name(i).decode() for i in range(L.cpprob_sis_model_count())]
     for m in ("gaussian_unknown_mean", "gaussian_unknown_mean_mu", "linear_gaussian_1d", "hmm"):
         assert m in names
