@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """A small pass over every path for compute-sanitizer (memcheck / racecheck / initcheck): fused, staged (reals, ints, packed
-ints, accumulators in L2), rows with both reductions, emission with the text stage, replay, reduce_records.
+ints, accumulators in L2), rows with both reductions, emission with the text stage, replay, reduce_records, and (on >= 2
+GPUs) the peer-memory exchange of run_multi.
 usage: compute-sanitizer --tool racecheck python tools/sanitize_once.py"""
 import os
 import sys
@@ -30,4 +31,18 @@ with Engine(seed=7, max_batch=capi.CHUNK) as e, tempfile.TemporaryDirectory() as
     rec = e.run("hmm", g["obs_hmm_64"][:9], 3000, collect=True)
     e.reduce_records(rec["log_w"], int_rows=rec["int_rows"])
     e.run_dist("hmm", g["obs_hmm_64"][:9], 3000)
+# with two GPUs: the multi-GPU exchange over peer memory (k_fold_units / k_push_rows into the peers' windows, the merge
+# kernel's wait on the epoch flags) on the fused, staged and row-fed shapes, three inferences each (both gather buffers)
+import torch  # noqa: E402
+if torch.cuda.device_count() >= 2:
+    engines = [Engine(device=d, seed=7) for d in range(2)]
+    try:
+        for model, obs, m in (("gaussian_unknown_mean", [3.0, 4.0], 5 * capi.CHUNK + 77), ("hmm", g["obs_hmm_64"][:9], 3 * capi.CHUNK + 5),
+                              ("linear_gaussian_1d", g["obs_linear_gaussian_32"][:6], 3 * capi.CHUNK + 5)):
+            for _ in range(3):
+                st = capi.run_multi(engines, model, obs, m)
+            print("run_multi", model, engines[0].comm_exchange(), st["path"])
+    finally:
+        for x in engines:
+            x.close()
 print("sanitize pass done")
