@@ -240,13 +240,12 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
         flush.fill_(1)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.02)
+    sampler = ClockSampler(local_rank)      # every rank watches its own GPU: the step is as slow as the slowest of them
+    sampler.start()
+    time.sleep(0.02)
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    kernel_ms_total, launches_total, last = 0.0, 0, None
+    kernel_ms_total, particle_ms_total, launches_total, last = 0.0, 0.0, 0, None
     barrier()
     for i in range(args.steps):
         flush.fill_(i & 0xFF)                 # L2 flush between steps (outside the timed brackets)
@@ -255,13 +254,22 @@ def run_ours(args):
         raw = call_main()
         ev1[i].record()
         kernel_ms_total += raw.device_ms
+        particle_ms_total += raw.particle_ms
         launches_total += raw.kernel_launches
     last = stats_to_dict(raw)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
     step_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
     t = torch.tensor([step_ms, kernel_ms_total], dtype=torch.float64, device="cuda")
+    per_rank = None
     if world > 1:
+        # what every rank saw: its own device time per step (pilot + particle kernel + fold + merge, the merge including the
+        # wait for the slowest peer's rows) and its own GPU's clocks — B200s of one box differ by a few per cent
+        mine = {"rank": rank, "particle_pass_ms_per_step": particle_ms_total / args.steps, "kernel_ms_per_step": kernel_ms_total / args.steps,
+                "step_ms": step_ms / args.steps,
+                "sm_mhz": clocks["sm_mhz"], "reasons": clocks["reasons"], "power_w_max": clocks["power_w_max"]}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     step_ms, kernel_ms_total = t.tolist()
 
@@ -330,6 +338,7 @@ def run_ours(args):
                 "merge kernel waits on the flags: no collective kernel, one host sync per inference (cpprob_sis_run_dist)"
                 if engine.comm_exchange() == "peer" else "one ncclAllGather per inference inside libcpprob_sis.so (cpprob_sis_run_dist)"),
             "exchange": engine.comm_exchange(),
+            "per_rank": per_rank,
         }
         if world == 1:
             peak_tflops, est_mhz = engine.dfma_peak()

@@ -13,6 +13,24 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CPPROB_SIS_LIB") or os.path.join(_HERE, "lib", "libcpprob_sis.so")   # override: kernel-variant sweeps
 
+
+
+def _prefer_bundled_nccl():
+    """The library opens NCCL by name at its first multi-GPU call (libnccl.so.2, CPPROB_SIS_NCCL_LIB overrides).  A Python
+    process that imports torch LATER needs the NCCL torch was built against (its wheel's nvidia/nccl/lib/libnccl.so.2): the
+    loader keeps one object per soname, so if the system's older libnccl got in first, `import torch` fails on a missing
+    symbol.  Point the library at the wheel's copy when there is one (no import of torch needed for that)."""
+    if os.environ.get("CPPROB_SIS_NCCL_LIB"):
+        return
+    import sys
+    for p in sys.path:
+        cand = os.path.join(p, "nvidia", "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            os.environ["CPPROB_SIS_NCCL_LIB"] = cand
+            return
+
+
+_prefer_bundled_nccl()
 EMIT_NONE, EMIT_ALL = 0, 1
 DIST = {"normal": 0, "uniform_real": 1, "uniform_smallint": 2, "discrete": 3, "poisson": 4, "gamma": 5, "beta": 6}
 PATHS = ("fused", "staged", "rows")      # cpprob_sis_stats.path (CPPROB_SIS_PATH_*)
@@ -55,7 +73,8 @@ class Stats(C.Structure):
                 ("int_lo", C.c_longlong), ("int_bins", C.c_int),
                 ("int_prob", C.POINTER(C.c_double)), ("int_map", C.POINTER(C.c_longlong)),
                 ("n_cols", C.c_int), ("sums", C.POINTER(C.c_double)),
-                ("device_ms", C.c_double), ("kernel_launches", C.c_uint64), ("passes", C.c_int), ("path", C.c_int)]
+                ("device_ms", C.c_double), ("kernel_launches", C.c_uint64), ("passes", C.c_int), ("path", C.c_int),
+                ("particle_ms", C.c_double)]
 
 
 class Block(C.Structure):
@@ -174,7 +193,7 @@ def _f64(a):
 def stats_to_dict(st, structure=None):
     d = {k: getattr(st, k) for k in ("n_particles", "n_neg_inf", "n_nan", "m_ref", "max_log_w", "log_sum_exp",
                                       "log_evidence", "ess", "n_real", "n_int", "int_lo", "int_bins", "n_cols",
-                                      "device_ms", "kernel_launches", "passes")}
+                                      "device_ms", "kernel_launches", "passes", "particle_ms")}
     d["path"] = PATHS[st.path] if 0 <= st.path < len(PATHS) else str(st.path)
     d["real_mean"] = np.array([st.real_mean[i] for i in range(st.n_real)])
     d["real_var"] = np.array([st.real_var[i] for i in range(st.n_real)])

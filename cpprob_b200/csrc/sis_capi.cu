@@ -1095,7 +1095,7 @@ int run_full(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, const do
     const double * mo = nullptr;
     hist_window hw_override;
     const hist_window * ho = nullptr;
-    double total_ms = 0.0;
+    double total_ms = 0.0, particle_ms = 0.0;
     uint64_t launches = 0;
     int passes = 0;
     opt.no_wait = true;      // one synchronisation per inference on the fused path: after the merge
@@ -1109,6 +1109,7 @@ int run_full(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, const do
                                   static_cast<int>(e->structure.n_int), res.hw, res.m_ref, n, out, &launches, &merge_ms, &res);
         if (rc < 0) return rc;
         total_ms += res.device_ms + merge_ms;
+        particle_ms += res.device_ms;
         bool again = false;
         if (rc == 1 && passes < 3) {
             m_ref_override = out->max_log_w;
@@ -1134,6 +1135,7 @@ int run_full(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, const do
         opt.force_rows = opt_in.force_rows || opt_in.emit == CPPROB_SIS_EMIT_ALL;
     }
     out->device_ms = total_ms;
+    out->particle_ms = particle_ms;
     out->kernel_launches = launches;
     out->passes = passes;
     out->path = res.path;
@@ -1409,7 +1411,7 @@ int run_dist_impl(cpprob_sis_engine * const * local, int n_local, const cpprob_s
     const double * mo = nullptr;
     hist_window hw_override;
     const hist_window * ho = nullptr;
-    double total_ms = 0.0;
+    double total_ms = 0.0, particle_ms = 0.0;
     uint64_t launches = 0;
     std::vector<shard_result> res(static_cast<size_t>(n_local));
     for (int pass = 1;; ++pass) {
@@ -1481,6 +1483,7 @@ int run_dist_impl(cpprob_sis_engine * const * local, int n_local, const cpprob_s
             shard_ms = std::max(shard_ms, res[static_cast<size_t>(i)].device_ms);
         }
         total_ms += shard_ms + merge_ms;
+        particle_ms += res[0].device_ms;
         bool again = false;
         if (mrc == 1 && pass < 3) {
             m_ref_override = out->max_log_w;
@@ -1508,6 +1511,7 @@ int run_dist_impl(cpprob_sis_engine * const * local, int n_local, const cpprob_s
         }
     }
     out->device_ms = total_ms;
+    out->particle_ms = particle_ms;
     out->kernel_launches = launches;
     primary->launches += launches;
     return 0;

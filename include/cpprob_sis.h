@@ -117,6 +117,8 @@ typedef struct cpprob_sis_stats {
     uint64_t kernel_launches;    /* kernels launched by this call */
     int passes;                  /* 1, or 2 if m_ref had to be re-based */
     int path;                    /* CPPROB_SIS_PATH_*: where the traces lived while the estimators were formed */
+    double particle_ms;          /* the part of device_ms that is this GPU's own particle pass (pilot, particle kernels, row
+                                    reductions): without the merge, which on several GPUs includes the wait for the peers */
 } cpprob_sis_stats;
 
 enum {
