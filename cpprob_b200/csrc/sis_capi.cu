@@ -1400,9 +1400,9 @@ int run_dist_impl(cpprob_sis_engine * const * local, int n_local, const cpprob_s
 {
     const nccl_api & nc = nccl();
     const int world = local[0]->comm_world;
-    if (world > 1 && !nc.handle) return fail(CPPROB_SIS_ENCCL, nc.why);
+    if (world > 1 && local[0]->comm && !nc.handle) return fail(CPPROB_SIS_ENCCL, nc.why);
     for (int i = 0; i < n_local; ++i) {
-        if (world > 1 && !local[i]->comm) return fail(CPPROB_SIS_EINVAL, "engine has no communicator (cpprob_sis_comm_init)");
+        if (world > 1 && !local[i]->comm && !local[i]->pw.ready) return fail(CPPROB_SIS_EINVAL, "engine has no communicator (cpprob_sis_comm_init)");
         if (local[i]->comm_world != world) return fail(CPPROB_SIS_EINVAL, "engines belong to different communicators");
         if (local[i]->seed != local[0]->seed) return fail(CPPROB_SIS_EINVAL, "all engines of a multi-GPU run must share one seed");
     }
@@ -1441,6 +1441,7 @@ int run_dist_impl(cpprob_sis_engine * const * local, int n_local, const cpprob_s
             peer_flags = reinterpret_cast<const unsigned long long *>(primary->pw.local);
             peer_epoch = r0.push_epoch;
         } else if (world > 1) {
+            if (!primary->comm) return fail(CPPROB_SIS_EINVAL, "the partial rows of this run do not fit the peer windows and the engines have no NCCL communicator");
             if (n_local > 1) NCCL_TRY(nc.GroupStart());
             for (int i = 0; i < n_local; ++i) {
                 cpprob_sis_engine * e = local[i];
@@ -1607,14 +1608,15 @@ int peer_window_setup_ipc(cpprob_sis_engine * e)
 }
 
 // One process, one engine per GPU: peer access between the devices, plain pointers.
-void peer_window_setup_local(cpprob_sis_engine * const * engines, int n)
+void peer_window_setup_local(cpprob_sis_engine * const * engines, int n, bool shared_device)
 {
+    (void)shared_device;
     if (!peer_exchange_wanted()) return;
     bool ok = true;
     for (int i = 0; i < n && ok; ++i) {
         if (cudaSetDevice(engines[i]->device) != cudaSuccess) { ok = false; break; }
         for (int j = 0; j < n && ok; ++j) {
-            if (i == j) continue;
+            if (i == j || engines[i]->device == engines[j]->device) continue;
             int can = 0;
             if (cudaDeviceCanAccessPeer(&can, engines[i]->device, engines[j]->device) != cudaSuccess || !can) { ok = false; break; }
             const cudaError_t err = cudaDeviceEnablePeerAccess(engines[j]->device, 0);
@@ -1671,23 +1673,32 @@ int cpprob_sis_comm_init_local(cpprob_sis_engine * const * engines, int n_engine
 {
     if (!engines || n_engines <= 0 || n_engines > kMaxMergeRanks) return fail(CPPROB_SIS_EINVAL, "bad argument");
     std::vector<int> devs;
+    bool shared_device = false;
     for (int r = 0; r < n_engines; ++r) {
         if (!engines[r]) return fail(CPPROB_SIS_EINVAL, "null engine");
-        for (int d : devs) if (d == engines[r]->device) return fail(CPPROB_SIS_EINVAL, "two engines on one device cannot share a local communicator");
+        for (int d : devs) shared_device = shared_device || d == engines[r]->device;
         devs.push_back(engines[r]->device);
         if (int rc = cpprob_sis_comm_destroy(engines[r])) return rc;
     }
     if (n_engines == 1) return 0;                       // rank 0 of 1 needs no communicator
-    const nccl_api & nc = nccl();
-    if (!nc.handle) return fail(CPPROB_SIS_ENCCL, nc.why);
-    std::vector<ncclComm_t> comms(static_cast<size_t>(n_engines));
-    NCCL_TRY(nc.CommInitAll(comms.data(), n_engines, devs.data()));
+    // Engines that share a device can be the ranks of one run only through the peer windows (NCCL refuses two ranks on
+    // one device): several shards of a run on one GPU — what the single-GPU tests use to exercise the exchange.
+    if (!shared_device) {
+        const nccl_api & nc = nccl();
+        if (!nc.handle) return fail(CPPROB_SIS_ENCCL, nc.why);
+        std::vector<ncclComm_t> comms(static_cast<size_t>(n_engines));
+        NCCL_TRY(nc.CommInitAll(comms.data(), n_engines, devs.data()));
+        for (int r = 0; r < n_engines; ++r) engines[r]->comm = comms[static_cast<size_t>(r)];
+    }
     for (int r = 0; r < n_engines; ++r) {
-        engines[r]->comm = comms[static_cast<size_t>(r)];
         engines[r]->comm_rank = r;
         engines[r]->comm_world = n_engines;
     }
-    peer_window_setup_local(engines, n_engines);
+    peer_window_setup_local(engines, n_engines, shared_device);
+    if (shared_device && !engines[0]->pw.ready) {
+        for (int r = 0; r < n_engines; ++r) cpprob_sis_comm_destroy(engines[r]);
+        return fail(CPPROB_SIS_EINVAL, "engines on one device can only share a communicator through peer windows (CPPROB_SIS_EXCHANGE=nccl or no memory for them)");
+    }
     return 0;
 }
 
@@ -1733,7 +1744,9 @@ int cpprob_sis_run_multi(cpprob_sis_engine * const * engines, int n_engines, int
     if (!vt) return fail(CPPROB_SIS_ENOMODEL, "unknown model id");
     // the engines need one communicator among themselves, rank r = position in the list; made on first use and kept
     bool ready = true;
-    for (int r = 0; r < n_engines; ++r) ready = ready && engines[r]->comm_world == n_engines && engines[r]->comm_rank == r && (n_engines == 1 || engines[r]->comm);
+    for (int r = 0; r < n_engines; ++r) {
+        ready = ready && engines[r]->comm_world == n_engines && engines[r]->comm_rank == r && (n_engines == 1 || engines[r]->comm || engines[r]->pw.ready);
+    }
     if (!ready) {
         if (int rc = cpprob_sis_comm_init_local(engines, n_engines)) return rc;
     }

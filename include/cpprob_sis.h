@@ -250,7 +250,9 @@ enum { CPPROB_SIS_EXCHANGE_NONE = 0, CPPROB_SIS_EXCHANGE_NCCL = 1, CPPROB_SIS_EX
 int cpprob_sis_comm_exchange(const cpprob_sis_engine * e);
 int cpprob_sis_run_dist(cpprob_sis_engine * e, int model_id, const double * obs, size_t n_obs, uint64_t n_particles_total,
                         cpprob_sis_stats * out);
-/* One process driving several GPUs: a communicator among engines[0..n) (rank r = engines[r]; ncclCommInitAll). */
+/* One process driving several GPUs: a communicator among engines[0..n) (rank r = engines[r]; ncclCommInitAll + peer
+ * windows).  Engines that share a device are accepted too — several shards of one run on one GPU, exchanged through the
+ * peer windows only (NCCL has no two ranks on one device): what the single-GPU tests use to exercise the exchange. */
 int cpprob_sis_comm_init_local(cpprob_sis_engine * const * engines, int n_engines);
 
 /* Single-process form of the same scheme: engines[r] (one per GPU, created by the caller with ONE seed) is rank r; the

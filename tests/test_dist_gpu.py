@@ -43,6 +43,27 @@ def test_communicator_of_one_rank(engine):
     assert (a["sums"] == b["sums"]).all()
 
 
+@pytest.mark.parametrize("ranks", [2, 3, 8])
+@pytest.mark.parametrize("model,obs,n", CASES + [("gaussian_unknown_mean", [3.0, 4.0], 5000 * capi.CHUNK + 777), ("gaussian_unknown_mean", [3.0, 4.0], 1000)],
+                         ids=[c[0] for c in CASES] + ["super_chunks", "fewer_chunks_than_ranks"])
+def test_peer_exchange_between_ranks_on_one_gpu(engine, model, obs, n, ranks):
+    """The peer-memory exchange on ONE GPU: `ranks` engines on device 0 are the ranks of one run; every rank's kernels
+    store its partial rows into every rank's window and raise the epoch flags, rank 0's merge kernel waits for them.  Same
+    bits as a single engine, for the fused, staged and super-chunk shapes, over three inferences (both gather buffers)."""
+    from cpprob_b200 import Engine
+    engines = [Engine(device=0, seed=0x5EED) for _ in range(ranks)]
+    try:
+        runs = [capi.run_multi(engines, model, obs, n) for _ in range(3)]
+        assert engines[0].comm_exchange() == "peer"
+    finally:
+        for e in engines:
+            e.close()
+    solo = engine.run(model, obs, n)
+    for r in runs:
+        assert (r["sums"] == solo["sums"]).all() and r["path"] == solo["path"]
+    assert np.array_equal(runs[0]["real_mean"], solo["real_mean"]) and np.array_equal(runs[0]["int_prob"], solo["int_prob"])
+
+
 @pytest.mark.skipif(n_gpus() < 2, reason="needs at least 2 GPUs")
 @pytest.mark.parametrize("exchange", ["peer", "nccl"])
 @pytest.mark.parametrize("model,obs,n", CASES + [("gaussian_unknown_mean", [3.0, 4.0], 5000 * capi.CHUNK + 777)],

@@ -31,11 +31,12 @@ with Engine(seed=7, max_batch=capi.CHUNK) as e, tempfile.TemporaryDirectory() as
     rec = e.run("hmm", g["obs_hmm_64"][:9], 3000, collect=True)
     e.reduce_records(rec["log_w"], int_rows=rec["int_rows"])
     e.run_dist("hmm", g["obs_hmm_64"][:9], 3000)
-# with two GPUs: the multi-GPU exchange over peer memory (k_fold_units / k_push_rows into the peers' windows, the merge
+# the multi-GPU exchange over peer memory (k_fold_units / k_push_rows into the peers' windows, the merge
 # kernel's wait on the epoch flags) on the fused, staged and row-fed shapes, three inferences each (both gather buffers)
 import torch  # noqa: E402
-if torch.cuda.device_count() >= 2:
-    engines = [Engine(device=d, seed=7) for d in range(2)]
+if True:
+    # two GPUs if there are two, else two ranks on one GPU (the exchange kernels are the same)
+    engines = [Engine(device=d if torch.cuda.device_count() >= 2 else 0, seed=7) for d in range(2)]
     try:
         for model, obs, m in (("gaussian_unknown_mean", [3.0, 4.0], 5 * capi.CHUNK + 77), ("hmm", g["obs_hmm_64"][:9], 3 * capi.CHUNK + 5),
                               ("linear_gaussian_1d", g["obs_linear_gaussian_32"][:6], 3 * capi.CHUNK + 5)):
