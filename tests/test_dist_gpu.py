@@ -43,9 +43,13 @@ def test_communicator_of_one_rank(engine):
     assert (a["sums"] == b["sums"]).all()
 
 
+LONG_OBS = (G["obs_linear_gaussian_32"] * 5)[:150]       # 150 real predicts per trace do not fit the staging areas: row path
+
+
 @pytest.mark.parametrize("ranks", [2, 3, 8])
-@pytest.mark.parametrize("model,obs,n", CASES + [("gaussian_unknown_mean", [3.0, 4.0], 5000 * capi.CHUNK + 777), ("gaussian_unknown_mean", [3.0, 4.0], 1000)],
-                         ids=[c[0] for c in CASES] + ["super_chunks", "fewer_chunks_than_ranks"])
+@pytest.mark.parametrize("model,obs,n", CASES + [("gaussian_unknown_mean", [3.0, 4.0], 5000 * capi.CHUNK + 777), ("gaussian_unknown_mean", [3.0, 4.0], 1000),
+                                                 ("linear_gaussian_1d", LONG_OBS, 3 * capi.CHUNK + 5)],
+                         ids=[c[0] for c in CASES] + ["super_chunks", "fewer_chunks_than_ranks", "row_path"])
 def test_peer_exchange_between_ranks_on_one_gpu(engine, model, obs, n, ranks):
     """The peer-memory exchange on ONE GPU: `ranks` engines on device 0 are the ranks of one run; every rank's kernels
     store its partial rows into every rank's window and raise the epoch flags, rank 0's merge kernel waits for them.  Same
@@ -62,6 +66,8 @@ def test_peer_exchange_between_ranks_on_one_gpu(engine, model, obs, n, ranks):
     for r in runs:
         assert (r["sums"] == solo["sums"]).all() and r["path"] == solo["path"]
     assert np.array_equal(runs[0]["real_mean"], solo["real_mean"]) and np.array_equal(runs[0]["int_prob"], solo["int_prob"])
+    if len(obs) == 150:
+        assert solo["path"] == "rows"
 
 
 @pytest.mark.skipif(n_gpus() < 2, reason="needs at least 2 GPUs")
