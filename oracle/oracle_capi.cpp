@@ -72,6 +72,29 @@ double oracle_run(const char * model, const double * obs, int n_obs, unsigned lo
     return -1.0;
 }
 
+// The restated inference loop on PRESCRIBED sampled values (`values`: program order, trace after trace): writes
+// <prefix>.real / .int / .ids exactly as a sampling run would.  Counterpart of oracle/ref_sis.cpp --replay, which runs the
+// reference's own loop on the same values (tests/test_ref_sis.py compares the files byte for byte).
+int oracle_replay_files(const char * model, const double * obs, int n_obs, const double * values, unsigned long long n_values,
+                        unsigned long long n_traces, const char * prefix, int how)
+{
+    engine & e = engine::get();
+    e.progress = nullptr;
+    e.replay_values = values;
+    e.replay_pos = 0;
+    const std::string m(model);
+    const std::vector<double> o(obs, obs + n_obs);
+    double s = -1.0;
+    if (m == "gaussian_unknown_mean" && n_obs == 2) s = timed_inference([&] { models::gaussian_unknown_mean(o[0], o[1]); }, n_traces, prefix, how);
+    else if (m == "gaussian_unknown_mean_mu" && n_obs == 2) s = timed_inference([&] { models::gaussian_unknown_mean_mu(o[0], o[1]); }, n_traces, prefix, how);
+    else if (m == "linear_gaussian_1d") s = timed_inference([&] { models::linear_gaussian_1d(o); }, n_traces, prefix, how);
+    else if (m == "hmm") s = timed_inference([&] { models::hmm(o); }, n_traces, prefix, how);
+    else if (m == "gaussian_2d_unk_mean") s = timed_inference([&] { models::gaussian_2d_unk_mean(o); }, n_traces, prefix, how);
+    const bool all_used = e.replay_pos == n_values;
+    e.replay_values = nullptr;
+    return s < 0 ? -1 : (all_used ? 0 : -2);
+}
+
 // log_w of one trace whose sample statements return `values` in order (replay gate).
 int oracle_replay_logw(const char * model, const double * obs, int n_obs, const double * values, unsigned long long n_traces,
                        int values_per_trace, double * logw_out)

@@ -1,6 +1,2 @@
-// ORACLE shim (test infrastructure): declaration only.  /root/reference include/cpprob/traits.hpp:52-93 names
-// boost::function_types::function_arity inside templates that the post-processing path never instantiates.
-#ifndef CPPROB_REF_SHIM_FT_function_arity_HPP
-#define CPPROB_REF_SHIM_FT_function_arity_HPP
-namespace boost { namespace function_types { template<class F> struct function_arity; } }
-#endif
+// ORACLE shim: see components.hpp
+#include <boost/function_types/components.hpp>

@@ -1,6 +1,9 @@
-// ORACLE shim (test infrastructure): declaration only.  /root/reference include/cpprob/traits.hpp:83 names
-// boost::mpl::at_c inside a template that the post-processing path never instantiates.
+// ORACLE shim (test infrastructure): boost::mpl::at_c over the parameter list of function_types/components.hpp
+// (/root/reference include/cpprob/traits.hpp:83)
 #ifndef CPPROB_REF_SHIM_MPL_AT_HPP
 #define CPPROB_REF_SHIM_MPL_AT_HPP
-namespace boost { namespace mpl { template<class Seq, long N> struct at_c; } }
+#include <tuple>
+namespace boost { namespace mpl {
+template<class Seq, long N> struct at_c { typedef typename std::tuple_element<N, typename Seq::as_tuple>::type type; };
+}}
 #endif

@@ -1,0 +1,2 @@
+// ORACLE shim: see uuid.hpp
+#include <boost/uuid/uuid.hpp>

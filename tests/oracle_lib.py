@@ -26,6 +26,7 @@ class Oracle:
         L.oracle_run.argtypes = [C.c_char_p, dp, C.c_int, u64, C.c_char_p, C.c_int, C.c_uint, C.c_int]
         L.oracle_run.restype = C.c_double
         L.oracle_replay_logw.argtypes = [C.c_char_p, dp, C.c_int, dp, u64, C.c_int, dp]
+        L.oracle_replay_files.argtypes = [C.c_char_p, dp, C.c_int, dp, u64, u64, C.c_char_p, C.c_int]
         L.oracle_stats_text.argtypes = [C.c_char_p]
         L.oracle_stats_text.restype = C.c_char_p
         ip = C.POINTER(C.c_int)
@@ -49,6 +50,13 @@ class Oracle:
         s = self.L.oracle_run(model.encode(), _dp(obs), obs.size, int(n), prefix.encode(), 0 if how == "faithful" else 1, seed, progress)
         assert s >= 0, "oracle does not know this model"
         return s
+
+    def replay_files(self, model, obs, values, prefix, how="faithful"):
+        """The restated inference loop on prescribed sampled values [n_traces][per trace]: writes <prefix>.real/.int/.ids."""
+        obs, values = _f64(obs), _f64(values)
+        rc = self.L.oracle_replay_files(model.encode(), _dp(obs), obs.size, _dp(values), values.size, values.shape[0], prefix.encode(),
+                                        0 if how == "faithful" else 1)
+        assert rc == 0, f"oracle_replay_files: {rc}"
 
     def replay_logw(self, model, obs, values):
         """values: [n_traces][values_per_trace] sampled values in program order."""

@@ -13,6 +13,28 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "oracle", "_ref", "libcpprob_ref.so")
 STATS_PRINTER = os.path.join(ROOT, "oracle", "_ref", "ref_stats_printer")
+REF_SIS = os.path.join(ROOT, "oracle", "_ref", "ref_sis")
+
+
+def ref_sis(model, obs, n, prefix, replay=None):
+    """The REFERENCE'S OWN cpprob::inference(StateType::sis, ...) (oracle/ref_sis.cpp: its state.cpp, trace.cpp, utils.cpp,
+    models ... linked unmodified).  `replay`: the values its sample statements return, [n][per trace] in program order
+    (None: it draws by itself).  Writes <prefix>.real / .int / .any / .ids as the reference does; returns the wall seconds of
+    the inference call."""
+    args = [REF_SIS, model, str(int(n)), prefix]
+    tmp = None
+    if replay is not None:
+        tmp = prefix + ".replay.f64"
+        np.ascontiguousarray(replay, dtype=np.float64).tofile(tmp)
+        args.append(tmp)
+    else:
+        args.append("-")
+    args += [repr(float(x)) for x in obs]
+    r = subprocess.run(args, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    if tmp:
+        os.remove(tmp)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return float(r.stderr.strip().split()[-1])
 
 
 def available():

@@ -1,0 +1,61 @@
+"""The restated oracle against the REFERENCE'S OWN SIS LOOP (oracle/_ref/ref_sis: cpprob::inference of cpprob.hpp:173-203 with
+src/cpprob/{state,trace,sample,utils,serialization,cpprob,socket}.cpp and the reference's models linked unmodified; only
+third-party Boost / FlatBuffers / ZeroMQ names are stood in for).  Both run on the SAME prescribed sampled values, so
+everything downstream of a draw is compared: log-pdfs, the statement-by-statement log-weight accumulation, the routing of
+predicts to .real / .int, first-seen address ids, the posterior-file bytes and the .ids file (SURVEY.md section 8 rows (a)5,
+(a)6, (a)7)."""
+import os
+
+import numpy as np
+import pytest
+
+import analytic
+import ref_lib
+
+G = analytic.golden()
+pytestmark = pytest.mark.skipif(not (ref_lib.available() and os.path.exists(ref_lib.REF_SIS)), reason="oracle/_ref/ref_sis not built and /root/reference absent")
+
+CASES = [  # (model, obs, sampled values per trace, kind of the sampled values, traces)
+    ("gaussian_unknown_mean", [3.0, 4.0], 1, "real", 300),
+    ("gaussian_unknown_mean_mu", [3.0, 4.0], 1, "real", 300),
+    ("linear_gaussian_1d", G["obs_linear_gaussian_32"][:5], 5, "real", 200),
+    ("linear_gaussian_1d", G["obs_linear_gaussian_32"][:8], 8, "real", 200),
+    ("linear_gaussian_1d", G["obs_linear_gaussian_32"], 32, "real", 150),
+    ("hmm", G["obs_hmm_64"][:9], 9, "state", 200),
+    ("hmm", G["obs_hmm_64"][:12], 12, "state", 200),
+    ("hmm", G["obs_hmm_64"], 64, "state", 150),
+    ("hmm", G["obs_hmm_1000"], 1000, "state", 12),
+    ("gaussian_2d_unk_mean", [1.5, 2.5], 2, "real", 200),
+]
+
+
+def read(path):
+    return open(path, "rb").read() if os.path.exists(path) else None
+
+
+@pytest.mark.parametrize("model,obs,per,kind,n", CASES, ids=[f"{c[0]}-{c[2]}" for c in CASES])
+def test_oracle_files_equal_the_references_own_loop(oracle, tmp_path, model, obs, per, kind, n):
+    rng = np.random.default_rng(per * 7 + n)
+    values = rng.integers(0, 3, (n, per)).astype(np.float64) if kind == "state" else rng.normal(0.5, 2.0, (n, per))
+    a, b = str(tmp_path / "oracle"), str(tmp_path / "ref")
+    oracle.replay_files(model, obs, values, a)
+    ref_lib.ref_sis(model, obs, n, b, replay=values)
+    for ext in (".real", ".int", ".any", ".ids"):
+        assert read(a + ext) == read(b + ext), ext
+    assert read(b + ".ids") is not None and (read(b + ".real") is not None) != (read(b + ".int") is not None)
+
+
+def test_reference_loop_reproduces_the_readme_posterior(ref_sis_stats=None):
+    """The reference's own loop drawing by itself (standard-library normals through its get_rng()): README.md:118 says mean
+    2.32353, variance 1.05882 — the same pin the CUDA path is held to."""
+    import tempfile
+    ref = ref_lib.load()
+    with tempfile.TemporaryDirectory() as tmp:
+        prefix = os.path.join(tmp, "posterior_sis")
+        ref_lib.ref_sis("gaussian_unknown_mean", [3.0, 4.0], 200_000, prefix)
+        text = ref.stats_text(prefix)
+    import re
+    m = re.search(r"Mean:\n  Mean: (\S+)\n  Variance: (\S+)", text)
+    assert m, text
+    assert abs(float(m.group(1)) - 2.323529411764706) < 4 * 1.2973 / np.sqrt(200_000) * 1.5
+    assert abs(float(m.group(2)) - 1.0588235294117647) < 0.03
