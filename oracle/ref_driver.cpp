@@ -12,9 +12,9 @@
 //     include/cpprob/distributions/utils_normal_distribution.hpp (:20-45), utils_uniform_real.hpp (:21-31),
 //     utils_multivariate_normal.hpp (:20-33) + multivariate_normal.hpp   the log-pdfs of the README / BASELINE models
 // None of those files is copied or modified.  The third-party headers they name and this image lacks are
-// stood in for by oracle/ref_shim/ (Boost has_less, filesystem::path/exists, declarations of mpl::at_c and
-// function_types::*; and an empty cpprob/state.hpp, which stats_printer.hpp includes but does not use and
-// which would otherwise pull in FlatBuffers and ZeroMQ).
+// stood in for by oracle/ref_shim/ (Boost type traits, any, filesystem::path/exists, function types, Boost.Random's
+// distribution classes, the FlatBuffers runtime and cppzmq as do-nothing classes: see oracle/ref_sis.cpp, which links
+// the reference's whole SIS loop against the same stand-ins).
 //
 // What this pins: the posterior-file grammar as the reference writes and
 // parses it, and the StatsPrinter / EmpiricalDistribution arithmetic and console text.  The writer's stream state
