@@ -394,7 +394,9 @@ def run_ours(args):
                                      "what": "cpprob_sis_infer_to_files, wall clock, files complete: like for like with the reference's inference()"}
                 line["vs_cpu_1thread"] = {"files_vs_faithful": cf["value"] / cb["value"], "files_vs_buffered": cf["value"] / cb["fast_flavour_value"],
                                           "estimators_only_vs_faithful": line["e2e"]["value"] / cb["value"],
-                                          "note": "faithful = 3 file appends per trace as the reference; buffered = one ofstream per file kept open; "
+                                          "note": ("faithful = the reference's own SIS loop + StatsPrinter (oracle/_ref, one thread)" if cpu_kind() == "reference"
+                                                   else "faithful = the restated loop, 3 file appends per trace as the reference") +
+                                                  "; buffered = the restated loop with one ofstream per file kept open; "
                                                   "estimators only = cpprob_sis_run (CPPROB_SIS_EMIT=none), which writes no posterior file"}
         emit(line)
     engine.close()
