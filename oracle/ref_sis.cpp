@@ -32,6 +32,7 @@
 
 #include "models/models.hpp"
 #include "models/gaussian.hpp"
+#include "models/poly_adjustment.hpp"
 #include "cpprob/cpprob.hpp"
 
 namespace models { void all_distr(int, int); }   // src/models/models.cpp:13 (no header declares it)
@@ -91,6 +92,13 @@ int main(int argc, char ** argv)
         seconds = run(&models::gaussian_2d_unk_mean<double>, std::make_tuple(obs), n, prefix);
     } else if (model == "all_distr") {                                      // src/models/models.cpp:13-47
         seconds = run(&models::all_distr, std::make_tuple(0, 0), n, prefix);
+    } else if (model.rfind("poly_adjustment_", 0) == 0 && k == 12) {       // poly_adjustment.hpp:85-95, six (x, y) points
+        std::array<std::array<double, 2>, 6> pts;
+        for (std::size_t i = 0; i < 6; ++i) pts[i] = {{obs[2 * i], obs[2 * i + 1]}};
+        const auto o = std::make_tuple(pts);
+        if (model == "poly_adjustment_1") seconds = run(&models::poly_adjustment<1, 6>, o, n, prefix);
+        else if (model == "poly_adjustment_2") seconds = run(&models::poly_adjustment<2, 6>, o, n, prefix);
+        else if (model == "poly_adjustment_3") seconds = run(&models::poly_adjustment<3, 6>, o, n, prefix);
     } else if (model == "linear_gaussian_1d" && k == 5) {                  // models.hpp:67-80
         seconds = run(&models::linear_gaussian_1d<5>, std::make_tuple(as_array<5>(obs)), n, prefix);
     } else if (model == "linear_gaussian_1d" && k == 8) {

@@ -15,6 +15,7 @@ import ref_lib
 G = analytic.golden()
 pytestmark = pytest.mark.skipif(not (ref_lib.available() and os.path.exists(ref_lib.REF_SIS)), reason="oracle/_ref/ref_sis not built and /root/reference absent")
 
+PTS = [1, 2.1, 2, 3.9, 3, 5.3, 4, 7.7, 5, 10.2, 6, 12.9]      # the points of poly_adjustment.hpp:33
 CASES = [  # (model, obs, sampled values per trace, kind of the sampled values, traces)
     ("gaussian_unknown_mean", [3.0, 4.0], 1, "real", 300),
     ("gaussian_unknown_mean_mu", [3.0, 4.0], 1, "real", 300),
@@ -26,6 +27,9 @@ CASES = [  # (model, obs, sampled values per trace, kind of the sampled values, 
     ("hmm", G["obs_hmm_64"], 64, "state", 150),
     ("hmm", G["obs_hmm_1000"], 1000, "state", 12),
     ("gaussian_2d_unk_mean", [1.5, 2.5], 2, "real", 200),
+    ("poly_adjustment_1", PTS, 2, "real", 200),          # main.cpp's "linear_regression" = poly_adjustment<1, 6>
+    ("poly_adjustment_2", PTS, 3, "real", 200),
+    ("poly_adjustment_3", PTS, 4, "real", 200),
 ]
 
 
