@@ -151,3 +151,20 @@ def test_replay_matches_emitted_logw(oracle, tmp_path):
     _, values, logw = oracle.parse_records(prefix + ".real", "real", 5, 1000)
     again = oracle.replay_logw("linear_gaussian_1d", obs, values)
     np.testing.assert_allclose(again, logw, rtol=1e-13)
+
+
+def test_oracle_files_equal_the_reference_loops_committed_outputs(oracle, tmp_path):
+    """tests/golden/ref_sis_golden.json: posterior files the REFERENCE'S OWN SIS loop wrote (oracle/_ref/ref_sis, generator
+    tests/golden/make_ref_sis_golden.py) for prescribed sampled values.  The restated oracle, given the same values, must
+    write the same bytes — this form of the pin needs neither /root/reference nor oracle/_ref at test time."""
+    import json
+    import os
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_sis_golden.json")))
+    assert len(fx["cases"]) >= 6
+    for i, c in enumerate(fx["cases"]):
+        values = np.array([[float.fromhex(v) for v in row] for row in c["values_hex"]])
+        prefix = str(tmp_path / f"c{i}")
+        oracle.replay_files(c["model"], c["obs"], values, prefix)
+        for ext in (".real", ".int", ".any", ".ids"):
+            got = open(prefix + ext).read() if os.path.exists(prefix + ext) else None
+            assert got == c["files"].get(ext), (c["model"], ext)
