@@ -368,8 +368,11 @@ struct linear_regression_model {
 
 // -------------------------------------------------------------------------------------------------
 // One statement of every distribution — /root/reference src/models/models.cpp:13-47.  It uses the
-// one-argument predict, whose address the reference takes from the call stack: at function granularity
-// that is the same string for all five statements, reproduced here by address().
+// one-argument predict, whose address the reference takes from the call stack (get_addr(), utils.cpp:71-128 — out of
+// scope here).  Known deviation (tests/test_ref_sis_gpu.py): built with -rdynamic, as the reference's CMake does, that
+// string carries the call site's code offset, so the reference gives each of the five statements its own id and routes
+// the non-const NDArray of the last one to <file>.any; the device has no call-site identity, address() names the
+// function once and the vector predict stays in <file>.real.
 // -------------------------------------------------------------------------------------------------
 struct all_distr_model {
     static constexpr int n_scalar_obs = 2;

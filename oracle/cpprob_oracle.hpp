@@ -610,8 +610,9 @@ inline void linear_regression(const std::vector<double> & flat_points)   // poly
     predict(b, "b");
 }
 
-// src/models/models.cpp:13-47.  One-argument predict: the reference's get_addr() (utils.cpp:71-128) yields the
-// same stack string for every statement of the function.
+// src/models/models.cpp:13-47.  One-argument predict: restated at FUNCTION granularity (one address), which is what the
+// device path does; the reference's get_addr() (utils.cpp:71-128), built with -rdynamic, adds the call site's offset and so
+// numbers the five statements separately (oracle/_ref/ref_sis shows it; tests/test_ref_sis_gpu.py records the deviation).
 inline void all_distr(int, int)
 {
     const std::string addr = "[models::all_distr(int, int)]";
