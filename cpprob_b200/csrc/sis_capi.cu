@@ -1608,9 +1608,8 @@ int peer_window_setup_ipc(cpprob_sis_engine * e)
 }
 
 // One process, one engine per GPU: peer access between the devices, plain pointers.
-void peer_window_setup_local(cpprob_sis_engine * const * engines, int n, bool shared_device)
+void peer_window_setup_local(cpprob_sis_engine * const * engines, int n)
 {
-    (void)shared_device;
     if (!peer_exchange_wanted()) return;
     bool ok = true;
     for (int i = 0; i < n && ok; ++i) {
@@ -1694,7 +1693,7 @@ int cpprob_sis_comm_init_local(cpprob_sis_engine * const * engines, int n_engine
         engines[r]->comm_rank = r;
         engines[r]->comm_world = n_engines;
     }
-    peer_window_setup_local(engines, n_engines, shared_device);
+    peer_window_setup_local(engines, n_engines);
     if (shared_device && !engines[0]->pw.ready) {
         for (int r = 0; r < n_engines; ++r) cpprob_sis_comm_destroy(engines[r]);
         return fail(CPPROB_SIS_EINVAL, "engines on one device can only share a communicator through peer windows (CPPROB_SIS_EXCHANGE=nccl or no memory for them)");
