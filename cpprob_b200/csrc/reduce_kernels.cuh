@@ -278,30 +278,50 @@ __global__ void __launch_bounds__(kBlock) k_push_rows(const double * __restrict_
 // exchange) straight into every rank's gather buffer.  Output row s, column c = kernel rows [s*per_super, (s+1)*per_super)
 // combined in row order, each kernel row being its `per_unit` unit rows of `units` combined in row order — the very
 // additions a fold of the unit rows followed by k_fold_rows would make (same bits, round 2's first version did exactly
-// that), without the intermediate array and the second launch.  One thread per output element.
+// that), without the intermediate array and the second launch.
+// A group of g = 2^k lanes (g >= per_super, at most 32; the host picks it) forms one output element: lane j of the group
+// loads and folds the unit rows of kernel row r0 + j (+ g, + 2g ... for super-chunks of more than 32 rows) — the loads of
+// a long super-chunk (64 rows x 8 units when 8e9 particles are spread over 8 GPUs) run side by side instead of one after
+// the other in a single thread — and the rows' values are then added IN ROW ORDER through shuffles, every lane of the
+// group forming the same sum.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_fold_units(const double * __restrict__ units, unsigned n_rows, int per_unit, int nv, unsigned per_super,
                                                        int n_cols, unsigned long long max_mask, double * __restrict__ out, unsigned n_out_rows,
-                                                       const __grid_constant__ peer_push pp)
+                                                       unsigned group, const __grid_constant__ peer_push pp)
 {
-    const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(kBlock) + threadIdx.x;
-    if (i < static_cast<unsigned long long>(n_out_rows) * n_cols) {
-        const unsigned s = static_cast<unsigned>(i / n_cols);
-        const int c = static_cast<int>(i % n_cols);
-        const bool is_max = c < 64 && ((max_mask >> c) & 1ull);
-        const unsigned long long r0 = static_cast<unsigned long long>(s) * per_super;
-        const unsigned long long r1 = r0 + per_super < n_rows ? r0 + per_super : n_rows;
-        double acc = is_max ? dm::neg_inf() : 0.0;                  // (k_fold_rows starts from the identity too: same bits down to -0.0)
-        for (unsigned long long r = r0; r < r1; ++r) {
+    const unsigned long long n_out = static_cast<unsigned long long>(n_out_rows) * n_cols;
+    const unsigned long long slot = (blockIdx.x * static_cast<unsigned long long>(kBlock) + threadIdx.x) / group;   // output element of this group
+    const unsigned sub = threadIdx.x % group;
+    // (whole warps stay together: an element beyond the end just idles through the shuffles)
+    const bool live = slot < n_out;
+    const unsigned long long i = live ? slot : 0ull;
+    const unsigned s = static_cast<unsigned>(i / n_cols);
+    const int c = static_cast<int>(i % n_cols);
+    const bool is_max = c < 64 && ((max_mask >> c) & 1ull);
+    const unsigned long long r0 = static_cast<unsigned long long>(s) * per_super;
+    const unsigned long long r1 = r0 + per_super < n_rows ? r0 + per_super : n_rows;
+    double acc = is_max ? dm::neg_inf() : 0.0;                      // (k_fold_rows starts from the identity too: same bits down to -0.0)
+    const unsigned trips = (per_super + group - 1) / group;         // the same for every lane of the grid: the shuffles below are warp-wide
+    for (unsigned k = 0; k < trips; ++k) {
+        const unsigned long long base = r0 + static_cast<unsigned long long>(k) * group;
+        const unsigned long long r = base + sub;
+        double x = 0.0;
+        if (live && r < r1) {
             const double * p = units + (r * per_unit) * nv + c;
-            double x = p[0];
+            x = p[0];
 #pragma unroll 8
             for (int w = 1; w < per_unit; ++w) {
                 const double y = p[static_cast<size_t>(w) * nv];
                 x = is_max ? fmax(x, y) : x + y;
             }
-            acc = per_super == 1u ? x : (is_max ? fmax(acc, x) : acc + x);   // (one row per output row: the row itself)
         }
+        const unsigned here = base >= r1 ? 0u : (r1 - base < group ? static_cast<unsigned>(r1 - base) : group);
+        for (unsigned j = 0; j < group; ++j) {                      // (uniform trip count across the warp; `here` masks the tail)
+            const double v = __shfl_sync(0xffffffffu, x, static_cast<int>(j), static_cast<int>(group));
+            if (j < here) acc = per_super == 1u ? v : (is_max ? fmax(acc, v) : acc + v);   // (one row per output row: the row itself)
+        }
+    }
+    if (live && sub == 0u) {
         out[i] = acc;
         for (unsigned p = 0; p < pp.t.world; ++p) peer_segment(pp, p)[i] = acc;
     }

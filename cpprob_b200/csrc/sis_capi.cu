@@ -627,8 +627,11 @@ int run_shard_impl(cpprob_sis_engine * e, const cpprob_sis_model_vtable * vt, co
             n_out_rows = plan.n_super_local;
         }
         const unsigned long long n_out = static_cast<unsigned long long>(n_out_rows) * n_cols;
-        k_fold_units<<<static_cast<unsigned>((n_out + kBlock - 1) / kBlock), kBlock, 0, e->compute>>>(
-            e->d_warp_partials.ptr, kernel_rows, per_unit, nv, rows_per_super, n_cols, kMaxColsMask, out, n_out_rows, pp);
+        unsigned group = 1;                          // lanes per output element: the power of two >= rows_per_super, at most a warp
+        while (group < rows_per_super && group < 32u) group <<= 1;
+        const unsigned long long threads = n_out * group;
+        k_fold_units<<<static_cast<unsigned>((threads + kBlock - 1) / kBlock), kBlock, 0, e->compute>>>(
+            e->d_warp_partials.ptr, kernel_rows, per_unit, nv, rows_per_super, n_cols, kMaxColsMask, out, n_out_rows, group, pp);
         CU_TRY(cudaGetLastError());
         ++res->launches;
         res->rows = out;
