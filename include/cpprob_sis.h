@@ -224,7 +224,7 @@ int cpprob_sis_run_shard(cpprob_sis_engine * e, int model_id, const double * obs
                          const double * m_ref_override /* NULL: pilot */,
                          cpprob_sis_partials * out);
 
-/* ---- multi-GPU inside the library: one NCCL all-gather per inference -------------------------------------------------
+/* ---- multi-GPU inside the library: one exchange of the partial rows per inference (peer memory, or an NCCL all-gather) ----
  * north_star: "each rank reduces locally, and one small NCCL [collective] over NVLink combines the global max
  * log-weight, the sum of exp-weights and the weighted moment sums".  The collective is an all-gather of the per-
  * (super-)chunk partial rows (<= 4096 rows of n_cols doubles in all) on the engine's own stream, right behind the
@@ -256,7 +256,7 @@ int cpprob_sis_run_dist(cpprob_sis_engine * e, int model_id, const double * obs,
 int cpprob_sis_comm_init_local(cpprob_sis_engine * const * engines, int n_engines);
 
 /* Single-process form of the same scheme: engines[r] (one per GPU, created by the caller with ONE seed) is rank r; the
- * calling thread queues every shard, the grouped all-gather and the merge, and waits once.  The local communicator is
+ * calling thread queues every shard, the exchange and the merge, and waits once.  The local communicator is
  * made on first use (cpprob_sis_comm_init_local) and kept.  Estimators only (no trace emission).  Results are owned by
  * engines[0] and are bit-identical to a single-GPU run of the same seed. */
 int cpprob_sis_run_multi(cpprob_sis_engine * const * engines, int n_engines, int model_id, const double * obs,
