@@ -51,11 +51,12 @@ class Oracle:
         assert s >= 0, "oracle does not know this model"
         return s
 
-    def replay_files(self, model, obs, values, prefix, how="faithful"):
-        """The restated inference loop on prescribed sampled values [n_traces][per trace]: writes <prefix>.real/.int/.ids."""
+    def replay_files(self, model, obs, values, prefix, how="faithful", n_traces=None):
+        """The restated inference loop on prescribed sampled values [n_traces][per trace] (or a flat list with n_traces given,
+        for traces of different lengths): writes <prefix>.real/.int/.ids."""
         obs, values = _f64(obs), _f64(values)
-        rc = self.L.oracle_replay_files(model.encode(), _dp(obs), obs.size, _dp(values), values.size, values.shape[0], prefix.encode(),
-                                        0 if how == "faithful" else 1)
+        rc = self.L.oracle_replay_files(model.encode(), _dp(obs), obs.size, _dp(values), values.size,
+                                        values.shape[0] if n_traces is None else int(n_traces), prefix.encode(), 0 if how == "faithful" else 1)
         assert rc == 0, f"oracle_replay_files: {rc}"
 
     def replay_logw(self, model, obs, values):

@@ -49,6 +49,26 @@ def test_oracle_files_equal_the_references_own_loop(oracle, tmp_path, model, obs
     assert read(b + ".ids") is not None and (read(b + ".real") is not None) != (read(b + ".int") is not None)
 
 
+def test_rejection_sampling_loop_equals_the_references(oracle, tmp_path):
+    """models.hpp:82-112: the prior is simulated by rejection inside `cpprob::rejection_sampling`.  Replay lists with a known
+    fate — k proposals far in the tails paired with the largest acceptance draw (rejected whatever the pdf's last bit is),
+    then one pair with acceptance draw 0 (accepted) — through the reference's loop and the restatement: same files."""
+    rng = np.random.default_rng(5)
+    n, values = 120, []
+    for _ in range(n):
+        for _ in range(int(rng.integers(0, 4))):
+            values += [float(rng.choice([-43.0, 45.0])), 0.178]          # pdf there ~ 1e-84, maxval = 0.1784...: rejected
+        values += [float(rng.normal(2.0, 1.5)), 0.0]                     # 0 > pdf is false: accepted
+    values = np.array(values)
+    a, b = str(tmp_path / "oracle"), str(tmp_path / "ref")
+    oracle.replay_files("normal_rejection_sampling", [3.0, 4.0], values, a, n_traces=n)      # (ragged traces: a flat list)
+    flat = values.reshape(1, -1)
+    ref_lib.ref_sis("normal_rejection_sampling", [3.0, 4.0], n, b, replay=flat)
+    for ext in (".real", ".int", ".any", ".ids"):
+        assert read(a + ext) == read(b + ext), ext
+    assert read(b + ".real").count(b"\n") == n and read(b + ".ids") == b"Mu\n"
+
+
 def test_reference_loop_reproduces_the_readme_posterior(ref_sis_stats=None):
     """The reference's own loop drawing by itself (standard-library normals through its get_rng()): README.md:118 says mean
     2.32353, variance 1.05882 — the same pin the CUDA path is held to."""
