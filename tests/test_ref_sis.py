@@ -69,6 +69,35 @@ def test_rejection_sampling_loop_equals_the_references(oracle, tmp_path):
     assert read(b + ".real").count(b"\n") == n and read(b + ".ids") == b"Mu\n"
 
 
+def test_all_distr_values_and_log_weights_equal_the_references_ids_do_not(oracle, tmp_path):
+    """src/models/models.cpp:13-47, one statement of every distribution, one-argument predicts.  On the same sampled values
+    the restatement and the reference's loop agree on every value and on every log-weight (bit for bit: normal,
+    uniform_smallint, uniform_real, poisson and diagonal multivariate-normal log-pdfs inside one trace).  They do NOT agree
+    on addresses — a recorded deviation: the reference's get_addr() (utils.cpp:71-128, out of scope) carries the call site's
+    offset when built with -rdynamic as its CMake does, so it numbers the five statements 0..4 and routes the non-const
+    NDArray of the last predict to <file>.any; the restatement, like the device model, names the function once."""
+    import re
+    rng = np.random.default_rng(9)
+    n = 150
+    values = np.column_stack([rng.normal(1, 2, n), rng.integers(2, 8, n), rng.uniform(2, 9.5, n), rng.poisson(0.8, n),
+                              rng.normal(1, 1.4, n), rng.normal(2, 1, n), rng.normal(3, 2.2, n), rng.normal(4, 1.7, n)]).astype(np.float64)
+    a, b = str(tmp_path / "oracle"), str(tmp_path / "ref")
+    oracle.replay_files("all_distr", [0.0, 0.0], values, a)
+    ref_lib.ref_sis("all_distr", [0.0, 0.0], n, b, replay=values)
+    ids = [i for i in open(b + ".ids").read().split("\n") if i]
+    assert len(ids) == 5 and all(re.match(r"^\[models::all_distr\(int, int\)\+0x[0-9a-f]+\]$", i) for i in ids)
+    assert open(a + ".ids").read() == "[models::all_distr(int, int)]\n"
+    lw = lambda path: [l.rsplit(b" ", 1)[1] for l in open(path, "rb").read().splitlines()]
+    assert lw(a + ".real") == lw(b + ".real") == lw(b + ".int") == lw(b + ".any") and len(lw(b + ".any")) == n
+    num = rb"-?\d\.\d{15}e[+-]\d\d"
+    real_a = [re.findall(num, l.rsplit(b"]", 1)[0]) for l in open(a + ".real", "rb").read().splitlines()]
+    real_b = [re.findall(num, l.rsplit(b"]", 1)[0]) + re.findall(num, m.rsplit(b"]", 1)[0])
+              for l, m in zip(open(b + ".real", "rb").read().splitlines(), open(b + ".any", "rb").read().splitlines())]
+    assert real_a == real_b                                            # normal, uniform_real, then the four vector components
+    ints = lambda path: [re.findall(rb"\(\d+ (\d+)\)", l) for l in open(path, "rb").read().splitlines()]
+    assert ints(a + ".int") == ints(b + ".int")
+
+
 def test_reference_loop_reproduces_the_readme_posterior(ref_sis_stats=None):
     """The reference's own loop drawing by itself (standard-library normals through its get_rng()): README.md:118 says mean
     2.32353, variance 1.05882 — the same pin the CUDA path is held to."""
