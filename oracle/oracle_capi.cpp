@@ -93,6 +93,7 @@ int oracle_replay_files(const char * model, const double * obs, int n_obs, const
     else if (m.rfind("poly_adjustment_", 0) == 0) s = timed_inference([&] { models::poly_adjustment(m.back() - '0', o); }, n_traces, prefix, how);
     else if (m == "normal_rejection_sampling" && n_obs == 2) s = timed_inference([&] { models::normal_rejection_sampling(o[0], o[1]); }, n_traces, prefix, how);
     else if (m == "all_distr") s = timed_inference([&] { models::all_distr(0, 0); }, n_traces, prefix, how);
+    else if (m == "linear_regression") s = timed_inference([&] { models::linear_regression(o); }, n_traces, prefix, how);
     const bool all_used = e.replay_pos == n_values;
     e.replay_values = nullptr;
     return s < 0 ? -1 : (all_used ? 0 : -2);

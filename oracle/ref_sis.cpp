@@ -99,6 +99,10 @@ int main(int argc, char ** argv)
         if (model == "poly_adjustment_1") seconds = run(&models::poly_adjustment<1, 6>, o, n, prefix);
         else if (model == "poly_adjustment_2") seconds = run(&models::poly_adjustment<2, 6>, o, n, prefix);
         else if (model == "poly_adjustment_3") seconds = run(&models::poly_adjustment<3, 6>, o, n, prefix);
+    } else if (model == "linear_regression" && k % 2 == 0) {               // poly_adjustment.hpp:57-82 (main.cpp's "dyn_linear_reg"; the Builder argument is default-made by call_f_tuple)
+        std::vector<std::pair<double, double>> pts;
+        for (std::size_t i = 0; i + 1 < k; i += 2) pts.emplace_back(obs[i], obs[i + 1]);
+        seconds = run(&models::linear_regression<double>, std::make_tuple(pts), n, prefix);
     } else if (model == "linear_gaussian_1d" && k == 5) {                  // models.hpp:67-80
         seconds = run(&models::linear_gaussian_1d<5>, std::make_tuple(as_array<5>(obs)), n, prefix);
     } else if (model == "linear_gaussian_1d" && k == 8) {

@@ -30,6 +30,7 @@ CASES = [  # (model, obs, sampled values per trace, kind of the sampled values, 
     ("poly_adjustment_1", PTS, 2, "real", 200),          # main.cpp's "linear_regression" = poly_adjustment<1, 6>
     ("poly_adjustment_2", PTS, 3, "real", 200),
     ("poly_adjustment_3", PTS, 4, "real", 200),
+    ("linear_regression", PTS, 2, "real", 200),          # poly_adjustment.hpp:57-82, the model with a Builder argument
 ]
 
 

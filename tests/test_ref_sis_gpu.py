@@ -28,6 +28,7 @@ CONFIGS = [  # (label, model, obs, kind, particles)
     ("C5", "hmm", G["obs_hmm_1000"], "int", 600),
     ("vector_predict", "gaussian_2d_unk_mean", [1.5, 2.5], "real", 5_000),
     ("poly_adjustment_2", "poly_adjustment_2", [1, 2.1, 2, 3.9, 3, 5.3, 4, 7.7, 5, 10.2, 6, 12.9], "real", 5_000),
+    ("linear_regression", "linear_regression", [1, 2.1, 2, 3.9, 3, 5.3, 4, 7.7, 5, 10.2, 6, 12.9], "real", 5_000),
 ]
 
 RECORD = re.compile(rb"^(\(\[.*\]) (\S+)\)$")
